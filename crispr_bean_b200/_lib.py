@@ -1,0 +1,80 @@
+"""ctypes binding of `libbean_b200.so` (declared in include/bean_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbean_b200.so")
+
+BEAN_OK = 0
+MODE_SORTING, MODE_SURVIVAL = 0, 1
+MAX_BINS, MAX_RB, MAX_ALLELES, MAX_LAYERS = 8, 64, 32, 2
+
+
+class BeanError(RuntimeError):
+    pass
+
+
+class BeanScreen(C.Structure):
+    _fields_ = [
+        ("n_guides", C.c_int32), ("n_reps", C.c_int32), ("n_bins", C.c_int32), ("n_layers", C.c_int32),
+        ("mode", C.c_int32), ("mask_thres", C.c_int32),
+        ("x", C.c_void_p), ("a0", C.c_void_p), ("row_mask", C.c_void_p),
+        ("size_factor", C.POINTER(C.c_double)), ("sample_mask", C.POINTER(C.c_double)),
+        ("upper_thres", C.POINTER(C.c_double)), ("lower_thres", C.POINTER(C.c_double)),
+        ("timepoints", C.POINTER(C.c_double)),
+    ]
+
+
+class BeanLLArgs(C.Structure):
+    _fields_ = [
+        ("n_alleles", C.c_int32),
+        ("mu_allele", C.c_void_p), ("sd_allele", C.c_void_p), ("pi", C.c_void_p), ("allele_mask", C.c_void_p),
+        ("ll_row", C.c_void_p), ("ll_partial", C.c_void_p),
+        ("d_mu", C.c_void_p), ("d_sd", C.c_void_p), ("d_pi", C.c_void_p),
+    ]
+
+
+# every symbol include/bean_b200.h declares: name -> (restype, argtypes)
+_PROTOTYPES = {
+    "bean_abi_version": (C.c_int, []),
+    "bean_last_error": (C.c_char_p, []),
+    "bean_device_sm_count": (C.c_int, []),
+    "bean_ll_num_partials": (C.c_int, [C.c_int32]),
+    "bean_ll_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
+    "bean_ll_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_PROTOTYPES)
+
+
+def lib() -> C.CDLL:
+    """Load the library (building it if nvcc is around and it is missing); raise if impossible."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from .build import build
+            build()
+        try:
+            handle = C.CDLL(LIB_PATH)
+        except OSError as exc:  # pragma: no cover
+            raise BeanError(f"cannot load {LIB_PATH}: {exc} (the CUDA extension is required; no CPU fallback)") from exc
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != BEAN_OK:
+        msg = lib().bean_last_error().decode(errors="replace")
+        raise BeanError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,254 @@
+"""Tensorisation of a screen for the SVI hot path (host-side mirror of bean/preprocessing/data_class.py).
+
+Same class names, constructor keywords and tensor attributes as the reference
+(`X, X_masked, X_bcmatch(_masked), size_factor(_bcmatch), sample_mask, repguide_mask, a0, a0_bcmatch,
+pi_a0, allele_counts_control, upper_bounds, lower_bounds, target_lengths, n_targets, ...`; reference
+layout `(R, B, G)`, data_class.py:124-205, 312-397, 493-532, 913-1000), PLUS what the B200 kernels
+need (SURVEY section 7 stage 3): the flat CSR guide->variant arrays `variant_ptr (T+1)`,
+`guide_variant (G)` and -- via `device_pack.pack_*` -- guide-major `(G, R, B)` device records.
+
+Written vectorised (no per-guide Python loops, unlike data_class.py:511-532) so that the 1M-guide
+configuration tensorises in seconds.
+"""
+from __future__ import annotations
+
+from copy import copy
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .alpha0 import (get_fitted_alpha0, get_fitted_pi_alpha0, get_pred_alpha0, get_pred_pi_alpha0,
+                     get_size_factor)
+
+
+def _as_list(control_condition):
+    return control_condition.split(",") if isinstance(control_condition, str) else list(control_condition)
+
+
+class ScreenData:
+    """Base tensoriser (reference: `ScreenData`, data_class.py:35-263)."""
+
+    is_reporter = False
+    is_sorting = False
+    is_survival = False
+
+    def __init__(self, screen, repguide_mask: str = None, sample_mask_column: str = None,
+                 shrink_alpha: bool = False, condition_column: str = "condition",
+                 control_condition: str = "bulk", accessibility_col: str = None,
+                 accessibility_bw_path: str = None, device: str = None,
+                 replicate_column: str = "replicate", popt: Optional[Tuple[float, float]] = None,
+                 pi_popt: Optional[Tuple[float, float]] = None, control_can_be_selected=False,
+                 negctrl_guide_idx: Optional[Sequence[int]] = None, target_col: str = "target",
+                 lower_quantile_column: str = "lower_quantile", upper_quantile_column: str = "upper_quantile",
+                 time_column: str = "time", use_bcmatch: bool = False, impute_pi_popt: bool = False,
+                 **kwargs):
+        if accessibility_bw_path is not None and accessibility_col is None:
+            raise NotImplementedError(
+                "bigWig accessibility lookup (preprocessing/utils.py:111-146) needs pyBigWig, which is out of "
+                "scope; precompute the signal into a guide column and pass accessibility_col.")
+        self.device = device
+        self.condition_column = condition_column
+        self.replicate_column = replicate_column
+        self.control_condition = _as_list(control_condition)
+        self.control_can_be_selected = bool(control_can_be_selected)
+        self.sample_mask_column = sample_mask_column
+        self.repguide_mask_key = repguide_mask
+        self.shrink_alpha = shrink_alpha
+        self.popt = popt
+        self.pi_popt = pi_popt
+        self.negctrl_guide_idx = negctrl_guide_idx
+        self.accessibility_col = accessibility_col
+        self.target_col = target_col
+        self._lq_col, self._uq_col, self.time_column = lower_quantile_column, upper_quantile_column, time_column
+
+        screen = screen.copy()
+        smp = screen.samples
+        smp["size_factor"] = get_size_factor(screen.X)  # all samples incl. control (data_class.py:63)
+        if "X_bcmatch" in screen.layers:
+            smp["size_factor_bcmatch"] = get_size_factor(screen.layers["X_bcmatch"])
+        cond = smp[condition_column]
+        is_control = cond.astype(str).isin(self.control_condition).to_numpy()
+        # the CLI always passes a truthy `control_can_be_selected` (~bool), so the control
+        # sample joins the selected set as a pseudo-bin; False gives the documented intent
+        # (--exclude-control-condition-for-inference) instead of the reference's crash.
+        selected = ~cond.isnull().to_numpy() if self.control_can_be_selected else ~is_control
+        reps = sorted(smp[replicate_column].unique())
+        smp[f"{replicate_column}_id"] = smp[replicate_column].map({r: i for i, r in enumerate(reps)})
+        self.n_reps = len(reps)
+        self._assign_condition_ids(smp, selected)
+        order = np.lexsort((smp[f"{condition_column}_id"].to_numpy(), smp[f"{replicate_column}_id"].to_numpy()))
+        screen = screen[:, order]
+        selected, is_control = selected[order], is_control[order]
+        self.screen = screen
+        self.screen_selected = screen[:, selected]
+        self.screen_control = screen[:, is_control]
+        self.n_condits = len(self.screen_selected.samples[condition_column].unique())
+        self.n_samples = len(screen.samples)
+        self.n_guides = len(screen.guides)
+        self._post_init()
+        if self.target_col is not None and self.target_col in screen.guides.columns:
+            self._variant_init()
+        if self.is_reporter or (use_bcmatch and "X_bcmatch" in screen.layers):
+            self._bcmatch_init()
+        if self.is_reporter:
+            self._reporter_init(impute_pi_popt)
+
+    # -- condition ids ------------------------------------------------------------------------
+    def _assign_condition_ids(self, smp: pd.DataFrame, selected: np.ndarray):
+        """Sorting: bins ordered by (upper, lower) quantile (data_class.py:948-964)."""
+        raise NotImplementedError
+
+    # -- shared tensors ------------------------------------------------------------------------
+    def transform_data(self, X, n_bins=None):
+        n_bins = self.n_condits if n_bins is None else n_bins
+        return torch.as_tensor(np.array(X)).T.reshape((self.n_reps, n_bins, self.n_guides)).float()
+
+    def _post_init(self):
+        R, B, C = self.n_reps, self.n_condits, len(self.control_condition)
+        sel, ctl = self.screen_selected, self.screen_control
+        if self.accessibility_col is not None:
+            self.guide_accessibility = torch.as_tensor(self.screen.guides[self.accessibility_col].to_numpy().copy())
+        else:
+            self.guide_accessibility = None
+        if self.sample_mask_column is not None and self.sample_mask_column in sel.samples.columns:
+            self.sample_mask = torch.as_tensor(sel.samples[self.sample_mask_column].to_numpy().copy()).reshape(R, B)
+            self.control_sample_mask = torch.as_tensor(ctl.samples[self.sample_mask_column].to_numpy().copy()).reshape(R, C)
+        else:
+            self.sample_mask = torch.ones((R, B), dtype=torch.bool)
+            self.control_sample_mask = torch.ones((R, C), dtype=torch.bool)
+        self.X = self.transform_data(sel.X)
+        self.X_masked = self.X * self.sample_mask[:, :, None]
+        self.X_control = self.transform_data(ctl.X, C)
+        self.X_control_masked = self.X_control * self.control_sample_mask[:, :, None]
+        self.repguide_mask = ~(self.X == 0).any(axis=1)
+        if self.repguide_mask_key is not None:
+            tbl = self.screen.uns[self.repguide_mask_key]
+            assert tbl.shape == (self.n_guides, R), tbl.shape
+            self.repguide_mask = torch.logical_and(torch.as_tensor(tbl.to_numpy().T) > 0, self.repguide_mask)
+        self.size_factor = torch.as_tensor(sel.samples["size_factor"].to_numpy().copy()).reshape(R, B)
+        self.size_factor_control = torch.as_tensor(ctl.samples["size_factor"].to_numpy().copy()).reshape(R, C)
+        self.a0, self.popt = get_fitted_alpha0(self.X.clone(), self.size_factor.clone(), self.sample_mask,
+                                               shrink=self.shrink_alpha, popt=self.popt)
+
+    def _variant_init(self):
+        """n_targets / target_lengths (data_class.py:493-532) + CSR guide->variant arrays."""
+        codes = pd.Categorical(self.screen.guides[self.target_col]).codes
+        change = np.flatnonzero(np.diff(codes) != 0) + 1
+        starts = np.concatenate([[0], change])
+        n_unique = len(np.unique(codes))
+        if len(starts) != n_unique:
+            raise ValueError(
+                "Input Screen object not sorted for target identity. Sort the screen object so that guides "
+                f"targeting the same object would occur as consecutive block by screen[screen.guides[{self.target_col}].argsort(),:]")
+        self.n_targets = n_unique
+        ptr = np.concatenate([starts, [len(codes)]]).astype(np.int64)
+        self.target_lengths = torch.as_tensor(np.diff(ptr))
+        self.n_sgRNAs_per_target = int(self.target_lengths.max())
+        self.variant_ptr = torch.as_tensor(ptr.astype(np.int32))
+        self.guide_variant = torch.repeat_interleave(
+            torch.arange(self.n_targets, dtype=torch.int32), self.target_lengths)
+
+    def _bcmatch_init(self):
+        """Barcode-matched count layer (data_class.py:320-345, :1190-1222)."""
+        R, B, C = self.n_reps, self.n_condits, len(self.control_condition)
+        sel, ctl = self.screen_selected, self.screen_control
+        self.X_bcmatch = self.transform_data(sel.layers["X_bcmatch"])
+        self.X_bcmatch_masked = self.X_bcmatch * self.sample_mask[:, :, None]
+        self.X_bcmatch_control = self.transform_data(ctl.layers["X_bcmatch"], C)
+        self.X_bcmatch_control_masked = self.X_bcmatch_control * self.control_sample_mask[:, :, None]
+        self.size_factor_bcmatch = torch.as_tensor(sel.samples["size_factor_bcmatch"].to_numpy().copy()).reshape(R, B)
+        self.size_factor_bcmatch_control = torch.as_tensor(ctl.samples["size_factor_bcmatch"].to_numpy().copy()).reshape(R, C)
+        self.a0_bcmatch = get_pred_alpha0(self.X_bcmatch.clone(), self.size_factor_bcmatch.clone(), self.popt,
+                                          self.sample_mask)
+
+    def _reporter_init(self, impute_pi_popt=False):
+        """Reporter allele counts of the control condition and `pi_a0` (data_class.py:365-397, :416-453)."""
+        C = len(self.control_condition)
+        edited = self.transform_data(self.screen_control.layers["edits"], C)
+        nonedited = (self.X_bcmatch_control - edited).clamp(min=0)
+        self.allele_counts_control = torch.stack([nonedited, edited], axis=-1)  # (R, C, G, 2)
+        pi_popt = self.popt if impute_pi_popt else self.pi_popt
+        if pi_popt is not None:
+            self.pi_a0 = get_pred_pi_alpha0(self.allele_counts_control.clone(), self.size_factor_control.clone(), pi_popt)
+        else:
+            self.pi_a0, self._pi_popt = get_fitted_pi_alpha0(self.allele_counts_control.clone(),
+                                                             self.size_factor_control.clone(), shrink=self.shrink_alpha)
+
+    # -- guide subsetting (negative-control fit: cli/run.py:236-257) --------------------------------
+    _GUIDE_AXIS = {"X": 2, "X_masked": 2, "X_control": 2, "X_control_masked": 2, "repguide_mask": 1, "a0": 0,
+                   "X_bcmatch": 2, "X_bcmatch_masked": 2, "X_bcmatch_control": 2, "X_bcmatch_control_masked": 2,
+                   "a0_bcmatch": 0, "pi_a0": 0, "allele_counts_control": 2, "guide_accessibility": 0,
+                   "allele_counts": 2}
+
+    def __getitem__(self, guide_idx):
+        idx = torch.as_tensor(np.asarray(guide_idx)).long()
+        nd = copy(self)
+        nd.screen = self.screen[idx.numpy(), :]
+        nd.screen_selected = self.screen_selected[idx.numpy(), :]
+        nd.screen_control = self.screen_control[idx.numpy(), :]
+        nd.n_guides = len(idx)
+        for name, axis in self._GUIDE_AXIS.items():
+            v = getattr(self, name, None)
+            if v is not None:
+                setattr(nd, name, v.index_select(axis, idx))
+        if hasattr(self, "target_lengths"):
+            nd._variant_init()
+        return nd
+
+
+class SortingScreenData(ScreenData):
+    """Sorting screens: quantile bins (reference: data_class.py:876-1000)."""
+
+    is_sorting = True
+
+    def _assign_condition_ids(self, smp, selected):
+        lq, uq = smp[self._lq_col].to_numpy(dtype=np.float64), smp[self._uq_col].to_numpy(dtype=np.float64)
+        if ((lq < 0) | (lq > 1)).any() or ((uq < 0) | (uq > 1)).any():
+            raise ValueError("Invalid quantile value in screen.samples: check input.")
+        if (uq - lq < 0).any():
+            raise ValueError(f"Not all screen.samples[{self._uq_col}] larger than screen.samples[{self._lq_col}]: check input.")
+        sizes = smp.groupby([self._uq_col, self._lq_col]).size()
+        if not (sizes == self.n_reps).all():
+            raise ValueError(
+                "Not all replicate share same quantile bin definition. If you have missing bin data, add the sample "
+                "and add 'mask' column in 'screen.samples' or run `bean-qc` that automatically handles this.")
+        bins = np.unique(np.stack([uq[selected], lq[selected]], axis=1), axis=0)  # sorted by (uq, lq)
+        ids = np.full(len(smp), -1, dtype=np.int64)
+        for j, (u, l) in enumerate(bins):
+            ids[selected & (uq == u) & (lq == l)] = j
+        smp[f"{self.condition_column}_id"] = ids
+        self.upper_bounds = torch.as_tensor(bins[:, 0].copy())
+        self.lower_bounds = torch.as_tensor(bins[:, 1].copy())
+
+
+class VariantSortingScreenData(SortingScreenData):
+    """data_class.py:1165-1247: guide counts only (Normal / ControlNormal models)."""
+
+    def __init__(self, screen, *args, condition_column="bin", sample_mask_column="mask", **kwargs):
+        super().__init__(screen, *args, condition_column=condition_column,
+                         sample_mask_column=sample_mask_column, **kwargs)
+
+
+class VariantSortingReporterScreenData(SortingScreenData):
+    """data_class.py:1251-1295: + barcode-matched counts and reporter edits (MixtureNormal models)."""
+
+    is_reporter = True
+
+    def __init__(self, screen, *args, condition_column="bin", sample_mask_column="mask", **kwargs):
+        super().__init__(screen, *args, condition_column=condition_column,
+                         sample_mask_column=sample_mask_column, **kwargs)
+
+
+DATACLASS_DICT = {
+    "sorting": {
+        "Normal": VariantSortingScreenData,
+        "MixtureNormal": VariantSortingReporterScreenData,
+        "_MixtureNormal": VariantSortingReporterScreenData,
+        "MixtureNormal+Acc": VariantSortingReporterScreenData,
+        "_MixtureNormal+Acc": VariantSortingReporterScreenData,
+        "MixtureNormalConstPi": VariantSortingScreenData,
+    },
+    "survival": {},
+}

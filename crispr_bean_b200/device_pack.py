@@ -1,0 +1,75 @@
+"""Guide-major device records of a tensorised screen + the `BeanScreen` C struct that points at them.
+
+The reference keeps counts as `(R, B, G)` with G fastest (data_class.py:220-228) and permutes views per
+step (model.py:362, :534).  The kernels own whole guides, so the screen is re-tiled ONCE here to
+`x[layer][g][r][b]` (a guide's R*B cells are one contiguous record: 128 B at R=8, B=4, fp32).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def quantile_thresholds(upper_bounds: torch.Tensor, lower_bounds: torch.Tensor):
+    """Phi^-1 of the bin bounds in float64; +-inf where the quantile is 1 / 0 (model/utils.py:48-54)."""
+    uq, lq = upper_bounds.double().cpu(), lower_bounds.double().cpu()
+    tu = torch.where(uq == 1.0, torch.full_like(uq, math.inf), torch.erfinv(2 * uq.clamp(max=1 - 1e-16) - 1) * math.sqrt(2))
+    tl = torch.where(lq == 0.0, torch.full_like(lq, -math.inf), torch.erfinv(2 * lq.clamp(min=1e-300) - 1) * math.sqrt(2))
+    return tu.numpy().copy(), tl.numpy().copy()
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class DeviceScreen:
+    """Device-resident, guide-major copy of the per-step data of a *ScreenData object."""
+
+    def __init__(self, data, device="cuda", dtype=torch.float32, use_bcmatch=True, mask_thres=10):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.mode = _lib.MODE_SURVIVAL if getattr(data, "is_survival", False) else _lib.MODE_SORTING
+        G, R, B = data.n_guides, data.n_reps, data.n_condits
+        layers = [(data.X_masked, data.size_factor, data.a0)]
+        if use_bcmatch and getattr(data, "X_bcmatch_masked", None) is not None:
+            layers.append((data.X_bcmatch_masked, data.size_factor_bcmatch, data.a0_bcmatch))
+        self.n_guides, self.n_reps, self.n_bins, self.n_layers = G, R, B, len(layers)
+        self.mask_thres = int(mask_thres)
+        # (R, B, G) -> (G, R, B), layers stacked in front
+        self.x = torch.stack([x.permute(2, 0, 1) for x, _, _ in layers]).to(device=self.device, dtype=dtype).contiguous()
+        self.a0 = torch.stack([torch.as_tensor(a) for _, _, a in layers]).to(device=self.device, dtype=dtype).contiguous()
+        self.row_mask = data.repguide_mask.T.to(torch.uint8).to(self.device).contiguous()  # (G, R)
+        self._sf = np.ascontiguousarray(torch.stack([torch.as_tensor(s).double() for _, s, _ in layers]).numpy())
+        self._smask = np.ascontiguousarray(data.sample_mask.double().numpy())
+        if self.mode == _lib.MODE_SORTING:
+            self._tu, self._tl = quantile_thresholds(data.upper_bounds, data.lower_bounds)
+            self._tp = np.zeros(B)
+        else:
+            self._tu = self._tl = np.zeros(B)
+            self._tp = np.ascontiguousarray(data.timepoints.double().numpy())
+        s = _lib.BeanScreen()
+        s.n_guides, s.n_reps, s.n_bins, s.n_layers = G, R, B, self.n_layers
+        s.mode, s.mask_thres = self.mode, self.mask_thres
+        s.x, s.a0, s.row_mask = self.x.data_ptr(), self.a0.data_ptr(), self.row_mask.data_ptr()
+        s.size_factor, s.sample_mask = _dptr(self._sf), _dptr(self._smask)
+        s.upper_thres, s.lower_thres, s.timepoints = _dptr(self._tu), _dptr(self._tl), _dptr(self._tp)
+        self.c = s
+
+    @property
+    def cells(self) -> int:
+        """guide x replicate x bin cells (the unit of BASELINE.json's cells/s metric)."""
+        return self.n_guides * self.n_reps * self.n_bins
+
+
+def pi_to_guide_major(pi: torch.Tensor) -> torch.Tensor:
+    """reference `pi (R, 1, G, A)` -> kernel layout `(G, R, A)`."""
+    return pi[:, 0].permute(1, 0, 2).contiguous()
+
+
+def pi_from_guide_major(pi_g: torch.Tensor) -> torch.Tensor:
+    return pi_g.permute(1, 0, 2).unsqueeze(1)

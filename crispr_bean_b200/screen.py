@@ -1,0 +1,91 @@
+"""Minimal count-matrix container with the attribute surface `bean run` reads from a ReporterScreen.
+
+The reference's container (`bean/framework/ReporterScreen.py`, an anndata.AnnData subclass) is out of
+scope and not importable here (anndata / perturb_tools are absent).  The tensoriser in
+`data_class.py` only touches `.X`, `.layers[...]`, `.guides`, `.samples`, `.uns` and 2-D slicing
+(SURVEY App. A.10), so this duck-typed stand-in -- or a real ReporterScreen -- can be passed in.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import pandas as pd
+
+
+class MiniScreen:
+    """guides x samples count matrix + per-guide / per-sample tables (+ named layers)."""
+
+    def __init__(self, X, guides: pd.DataFrame, samples: pd.DataFrame,
+                 layers: Optional[Dict[str, np.ndarray]] = None, uns: Optional[dict] = None):
+        self.X = np.asarray(X)
+        self.guides = guides
+        self.samples = samples
+        self.layers = {k: np.asarray(v) for k, v in (layers or {}).items()}
+        self.uns = dict(uns or {})
+        assert self.X.shape == (len(guides), len(samples)), (self.X.shape, len(guides), len(samples))
+        for k, v in self.layers.items():
+            assert v.shape == self.X.shape, (k, v.shape)
+
+    # anndata aliases used by the reference
+    @property
+    def obs(self):
+        return self.guides
+
+    @property
+    def var(self):
+        return self.samples
+
+    @property
+    def n_obs(self):
+        return self.X.shape[0]
+
+    @property
+    def n_vars(self):
+        return self.X.shape[1]
+
+    @staticmethod
+    def _resolve(idx, index: pd.Index):
+        if isinstance(idx, slice):
+            return np.arange(len(index))[idx]
+        if isinstance(idx, (pd.Series, pd.Index)):
+            idx = idx.to_numpy()
+        idx = np.asarray(idx)
+        if idx.dtype == bool:
+            return np.nonzero(idx)[0]
+        if idx.dtype.kind in "OUS":
+            return index.get_indexer(idx)
+        return idx.astype(np.int64)
+
+    def __getitem__(self, key):
+        gi, si = key if isinstance(key, tuple) else (key, slice(None))
+        gi = self._resolve(gi, self.guides.index)
+        si = self._resolve(si, self.samples.index)
+        uns = dict(self.uns)
+        for k, v in self.uns.items():  # per-guide tables follow the guide subset (repguide_mask)
+            if isinstance(v, pd.DataFrame) and len(v) == len(self.guides) and v.index.equals(self.guides.index):
+                uns[k] = v.iloc[gi]
+        return MiniScreen(
+            self.X[np.ix_(gi, si)],
+            self.guides.iloc[gi].copy(),
+            self.samples.iloc[si].copy(),
+            {k: v[np.ix_(gi, si)] for k, v in self.layers.items()},
+            uns,
+        )
+
+    def copy(self):
+        return self[:, :]
+
+
+def read_csvs(guides_csv: str, samples_csv: str, counts_csv: str,
+              layer_csvs: Optional[Dict[str, str]] = None) -> MiniScreen:
+    """Load the CSV triple `bean create-screen` consumes (framework/read_from_csvs.py:9-23)."""
+    guides = pd.read_csv(guides_csv, index_col=0)
+    guides = guides.loc[:, ~guides.columns.duplicated()]
+    samples = pd.read_csv(samples_csv, index_col=0)
+    counts = pd.read_csv(counts_csv, index_col=0)
+    counts = counts.loc[guides.index, samples.index]
+    layers = {}
+    for name, path in (layer_csvs or {}).items():
+        layers[name] = pd.read_csv(path, index_col=0).loc[guides.index, samples.index].to_numpy()
+    return MiniScreen(counts.to_numpy(), guides, samples, layers)

@@ -1,0 +1,116 @@
+/*
+ * bean_b200.h -- C-ABI of the B200-native SVI hot path of `bean run` (pinellolab/crispr-bean).
+ *
+ * The reference has NO FFI / plugin interface for this path (pure Python on pyro + eager torch), so
+ * these entry points replace Python-level op chains; each one cites the reference interface it
+ * replaces (paths relative to the reference root).  See INTEGRATION.md for the ctypes binding a
+ * maintainer would add to bean/model/model.py.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers + sizes + a CUDA stream handle (void*, i.e. cudaStream_t);
+ *    no torch / C++ types cross the boundary.
+ *  - the caller owns every buffer (inputs, outputs, workspace); the library never allocates,
+ *    frees or retains a pointer past the call.
+ *  - every call is asynchronous on `stream`, never synchronises, never prints, never exits.
+ *  - return value: BEAN_OK or a negative BEAN_E* code; `bean_last_error()` gives the message of the
+ *    last failure on the calling thread.
+ *  - there is NO CPU fallback: without a CUDA device every compute call returns BEAN_ECUDA.
+ *  - `_f32` entry points take float buffers, `_f64` double buffers (the struct fields typed `void*`
+ *    below are `real*`); count tensors hold integer-valued reals exactly as the reference stores them
+ *    (`.float()`, bean/preprocessing/data_class.py:220-228).
+ *
+ * Layout (device): GUIDE-MAJOR records, re-tiled once at tensorisation from the reference's
+ * (R, B, G) tensors:  x[layer][g][r][b],  pi[g][r][a],  allele_counts[g][r][a],  row_mask[g][r].
+ */
+#ifndef BEAN_B200_H_
+#define BEAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEAN_ABI_VERSION 1
+
+enum {
+  BEAN_OK = 0,
+  BEAN_EINVAL = -1,   /* null pointer / bad shape / unsupported size */
+  BEAN_ECUDA = -2,    /* CUDA runtime error (message in bean_last_error) */
+  BEAN_EALIGN = -3    /* a buffer is not aligned for 128-bit access */
+};
+
+enum { BEAN_MODE_SORTING = 0, BEAN_MODE_SURVIVAL = 1 };
+
+#define BEAN_MAX_BINS 8        /* n_condits incl. the control pseudo-bin */
+#define BEAN_MAX_RB 64         /* n_reps * n_bins per guide */
+#define BEAN_MAX_ALLELES 32
+#define BEAN_MAX_LAYERS 2
+
+int bean_abi_version(void);
+const char* bean_last_error(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int bean_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Screen constants: everything the *ScreenData object holds that the likelihood reads every step.
+ * Replaces the attribute reads of bean/model/model.py:123-165, :484-547 (data.X_masked,
+ * data.X_bcmatch_masked, data.size_factor(_bcmatch), data.sample_mask, data.a0(_bcmatch),
+ * data.repguide_mask, data.upper_bounds / lower_bounds | data.timepoints).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BeanScreen {
+  int32_t n_guides;            /* G */
+  int32_t n_reps;              /* R */
+  int32_t n_bins;              /* B = n_condits */
+  int32_t n_layers;            /* 1 = guide counts, 2 = + barcode-matched counts (use_bcmatch) */
+  int32_t mode;                /* BEAN_MODE_SORTING | BEAN_MODE_SURVIVAL */
+  int32_t mask_thres;          /* row kept iff sum_b x > mask_thres (model.py:132-137; 10) */
+  const void* x;               /* real [L][G][R][B]   X_masked / X_bcmatch_masked               */
+  const void* a0;              /* real [L][G]         a0 / a0_bcmatch                           */
+  const uint8_t* row_mask;     /* u8   [G][R]         repguide_mask                             */
+  /* small per-sample tables, HOST pointers (copied into kernel arguments):                      */
+  const double* size_factor;   /* [L][R][B]           size_factor / size_factor_bcmatch         */
+  const double* sample_mask;   /* [R][B]                                                        */
+  const double* upper_thres;   /* [B] sorting: Phi^-1(upper_quantile), +inf where quantile == 1  */
+  const double* lower_thres;   /* [B] sorting: Phi^-1(lower_quantile), -inf where quantile == 0  */
+  const double* timepoints;    /* [B] survival: normalised time of each condition               */
+} BeanScreen;
+
+/* ------------------------------------------------------------------------------------------------
+ * bean_ll_{f32,f64}: count log-likelihood forward + local gradients in one pass.
+ *
+ * Replaces, for every model of bean/model/model.py and bean/model/survival_model.py, the op chain
+ *   get_std_normal_prob (model/utils.py:34-76) | exp(mu * t) (survival_model.py:358-361)
+ *   -> mixture over alleles (model.py:495-499) -> get_alpha x L (model/utils.py:10-25)
+ *   -> DirichletMultinomial(a).log_prob(X) under poutine.mask (model.py:526-547)
+ * and its autograd backward.
+ *
+ * in : mu_allele, sd_allele  real [G][A]   per-guide allele mean / sd (sd ignored for survival)
+ *      pi                    real [G][R][A] allele weights, or NULL for "all ones" (A must be 1)
+ *      allele_mask           u8   [G][A]   or NULL (tiling: 0 = allele does not exist, P := 0)
+ * out: ll_row                real [L][G][R] masked per-row log-prob (0 where masked), may be NULL
+ *      ll_partial            double [bean_ll_num_partials(G)] per-CTA partial sums of the masked ll
+ *      d_mu, d_sd            real [G][A]   d(sum ll)/d(mu_allele, sd_allele)
+ *      d_pi                  real [G][R][A] d(sum ll)/d(pi), may be NULL when pi is NULL
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BeanLLArgs {
+  int32_t n_alleles;           /* A */
+  const void* mu_allele;
+  const void* sd_allele;
+  const void* pi;
+  const uint8_t* allele_mask;
+  void* ll_row;
+  double* ll_partial;
+  void* d_mu;
+  void* d_sd;
+  void* d_pi;
+} BeanLLArgs;
+
+int bean_ll_num_partials(int32_t n_guides);
+int bean_ll_f32(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
+int bean_ll_f64(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEAN_B200_H_ */
