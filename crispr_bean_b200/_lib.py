@@ -23,7 +23,7 @@ class BeanScreen(C.Structure):
     _fields_ = [
         ("n_guides", C.c_int32), ("n_reps", C.c_int32), ("n_bins", C.c_int32), ("n_layers", C.c_int32),
         ("mode", C.c_int32), ("mask_thres", C.c_int32),
-        ("x", C.c_void_p), ("a0", C.c_void_p), ("row_mask", C.c_void_p),
+        ("x", C.c_void_p), ("a0", C.c_void_p), ("row_mask", C.c_void_p), ("row_const", C.c_void_p),
         ("size_factor", C.POINTER(C.c_double)), ("sample_mask", C.POINTER(C.c_double)),
         ("upper_thres", C.POINTER(C.c_double)), ("lower_thres", C.POINTER(C.c_double)),
         ("timepoints", C.POINTER(C.c_double)),
@@ -39,6 +39,36 @@ class BeanLLArgs(C.Structure):
     ]
 
 
+class BeanSviConfig(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("sd_is_sqrt", C.c_int32), ("mu_prior_normal", C.c_int32), ("apply_update", C.c_int32),
+        ("mu_prior_loc", C.c_double), ("mu_prior_scale", C.c_double),
+        ("sd_prior_loc", C.c_double), ("sd_prior_scale", C.c_double),
+        ("lr0", C.c_double), ("lrd", C.c_double),
+        ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double), ("clip", C.c_double),
+        ("ll_const", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class BeanSviState(C.Structure):
+    _fields_ = [
+        ("n_variants", C.c_int32), ("loss_capacity", C.c_int32),
+        ("guide_variant", C.c_void_p), ("variant_ptr", C.c_void_p),
+        ("allele_counts", C.c_void_p), ("pi_a0", C.c_void_p),
+        ("var_params", C.c_void_p), ("var_m", C.c_void_p), ("var_v", C.c_void_p),
+        ("alpha_u", C.c_void_p), ("alpha_m", C.c_void_p), ("alpha_v", C.c_void_p),
+        ("d_guide", C.c_void_p), ("var_grad", C.c_void_p), ("alpha_grad", C.c_void_p),
+        ("partial", C.c_void_p), ("counter", C.c_void_p), ("loss", C.c_void_p),
+    ]
+
+
+class BeanSviNoise(C.Structure):
+    _fields_ = [("eps_mu", C.c_void_p), ("eps_sd", C.c_void_p), ("pi", C.c_void_p),
+                ("eps_out", C.c_void_p), ("pi_out", C.c_void_p)]
+
+
+MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
+
 # every symbol include/bean_b200.h declares: name -> (restype, argtypes)
 _PROTOTYPES = {
     "bean_abi_version": (C.c_int, []),
@@ -47,6 +77,11 @@ _PROTOTYPES = {
     "bean_ll_num_partials": (C.c_int, [C.c_int32]),
     "bean_ll_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
     "bean_ll_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
+    "bean_svi_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
+    "bean_svi_run_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSviConfig),
+                                   C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_svi_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSviConfig),
+                                   C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

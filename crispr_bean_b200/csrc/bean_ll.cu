@@ -10,6 +10,7 @@
 
 #include "bean_common.cuh"
 #include "bean_math.cuh"
+#include "bean_row.cuh"
 
 namespace bean {
 
@@ -51,6 +52,7 @@ struct LLParams {
   const real* x;
   const real* a0;
   const uint8_t* row_mask;
+  const double* row_const;
   const real* mu;
   const real* sd;
   const real* pi;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(LL_THREADS) ll_generic_kernel(const LLParams<r
       for (int l = 0; l < p.L; ++l) {
         const real* xr = p.x + (((size_t)l * p.G + g) * R + r) * B;
         const real a0 = p.a0[(size_t)l * p.G + g];
-        real xb[BEAN_MAX_BINS], pb[BEAN_MAX_BINS];
+        real xb[BEAN_MAX_BINS] = {}, pb[BEAN_MAX_BINS];
         real N = real(0), S = real(0);
         for (int b = 0; b < B; ++b) {
           xb[b] = xr[b];
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(LL_THREADS) ll_generic_kernel(const LLParams<r
         }
         const bool w = rmask && (N > p.mask_thres);
         const real inv = real(1) / (S + eps);
-        real ab[BEAN_MAX_BINS], frac[BEAN_MAX_BINS];
+        real ab[BEAN_MAX_BINS] = {}, frac[BEAN_MAX_BINS];
         bool live[BEAN_MAX_BINS];
         real Asum = real(0);
         for (int b = 0; b < B; ++b) {
@@ -127,23 +129,20 @@ __global__ void __launch_bounds__(LL_THREADS) ll_generic_kernel(const LLParams<r
           ab[b] = live[b] ? raw : eps;
           Asum += ab[b];
         }
-        real lgA, dgA, lgNA, dgNA;
-        lgamma_digamma(Asum, lgA, dgA);
-        lgamma_digamma(N + Asum, lgNA, dgNA);
-        real ll = lgA - lgNA + lgamma1p_count(N);
+        real psi_diff[BEAN_MAX_BINS];
+        const real V = dm_row_kl<real, BEAN_MAX_BINS>(B, xb, ab, N, Asum, psi_diff);
+        // data-only part of the log-pmf, hoisted to tensorisation time (row_const is NULL -> 0)
+        const double K = p.row_const ? p.row_const[((size_t)l * p.G + g) * R + r] : 0.0;
+        const double ll = (double)V + K;
         real gb[BEAN_MAX_BINS];
         real dot = real(0);
         for (int b = 0; b < B; ++b) {
-          real lga, dga, lgxa, dgxa;
-          lgamma_digamma(ab[b], lga, dga);
-          lgamma_digamma(xb[b] + ab[b], lgxa, dgxa);
-          ll += lgxa - lga - lgamma1p_count(xb[b]);
-          gb[b] = live[b] ? (dgA - dgNA + dgxa - dga) * p.t.smask[r * B + b] : real(0);
+          gb[b] = live[b] ? psi_diff[b] * p.t.smask[r * B + b] : real(0);
           dot += gb[b] * frac[b];
         }
-        if (p.ll_row) p.ll_row[((size_t)l * p.G + g) * R + r] = w ? ll : real(0);
+        if (p.ll_row) p.ll_row[((size_t)l * p.G + g) * R + r] = w ? real(ll) : real(0);
         if (w) {
-          ll_acc += (double)ll;
+          ll_acc += ll;
           const real c = a0 * inv;
           for (int b = 0; b < B; ++b) de[b] += p.t.sf[l][r * B + b] * c * (gb[b] - dot);
         }
@@ -191,6 +190,7 @@ static int launch_ll(const BeanScreen* s, const BeanLLArgs* a, void* stream) {
   p.x = static_cast<const real*>(s->x);
   p.a0 = static_cast<const real*>(s->a0);
   p.row_mask = s->row_mask;
+  p.row_const = s->row_const;
   p.mu = static_cast<const real*>(a->mu_allele);
   p.sd = static_cast<const real*>(a->sd_allele);
   p.pi = static_cast<const real*>(a->pi);

@@ -1,9 +1,8 @@
 // bean_math.cuh -- in-register special functions for the bean SVI kernels (sm_100a).
 //
-// lgamma/digamma are evaluated as a PAIR sharing log(z) and 1/z (Stirling series, with a fixed
-// 4-step upward recurrence for z < 4 in float so the branch is two-way only).  These replace the
-// torch.lgamma / torch.digamma sweeps behind pyro's DirichletMultinomial.log_prob and its backward
-// (reference call sites: bean/model/model.py:138-164, :531-547).
+// These replace the torch.lgamma / torch.digamma / erf sweeps behind pyro's
+// DirichletMultinomial.log_prob, its backward and get_std_normal_prob
+// (reference call sites: bean/model/model.py:138-164, :531-547; bean/model/utils.py:34-76).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -37,34 +36,38 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
 };
 
-// ---- lgamma + digamma pair, z > 0 --------------------------------------------------------------
-// float: |err| ~ 1e-7 relative to max(1, |value|) for z >= 1e-6 (checked in tests/test_gpu_math.py).
-__device__ __forceinline__ void lgamma_digamma(float z, float& lg, float& dg) {
-  float zs = z, sub_lg = 0.0f, sub_dg = 0.0f;
+// ---- Gamma-function corrections to the Stirling main part, z > 0 ---------------------------------
+// gamma_corr(z) returns
+//   cv = lgamma(z)  - [(z - 1/2) ln z - z + ln(2 pi)/2]
+//   dl = digamma(z) - ln z
+// The Dirichlet-Multinomial row is assembled from these in "KL form" (bean_row.cuh): every large
+// z ln z product cancels ANALYTICALLY and only logs of near-1 ratios remain, so float keeps ~1e-6
+// absolute accuracy on a row whose individual lgamma terms are O(1e3..1e4) (a float lgamma(300) alone
+// is already off by 1e-4, which is the noise floor of the reference's own fp32 torch.lgamma path).
+// float, z >= 4: pure series in 1/z (no log at all); z < 4: 4-step upward recurrence first.
+__device__ __forceinline__ void gamma_corr(float z, float& cv, float& dl) {
+  float zs = z;
+  if (z < 4.0f) zs = z + 4.0f;
+  const float rz = 1.0f / zs;
+  const float r2 = rz * rz;
+  // lgamma tail: 1/(12 z) - 1/(360 z^3) + 1/(1260 z^5) - 1/(1680 z^7)
+  cv = rz * (8.3333333333e-2f + r2 * (-2.7777777778e-3f + r2 * (7.9365079365e-4f + r2 * -5.9523809524e-4f)));
+  // digamma tail: -1/(2z) - 1/(12 z^2) + 1/(120 z^4) - 1/(252 z^6) + 1/(240 z^8)
+  dl = -0.5f * rz - r2 * (8.3333333333e-2f + r2 * (-8.3333333333e-3f + r2 * (3.9682539683e-3f + r2 * -4.1666666667e-3f)));
   if (z < 4.0f) {
-    // Gamma(z) = Gamma(z+4) / (z (z+1) (z+2) (z+3));  psi(z) = psi(z+4) - P'(z)/P(z)
+    // Gamma(z) = Gamma(z+4) / P(z), P = z (z+1) (z+2) (z+3);  psi(z) = psi(z+4) - P'(z)/P(z)
     const float z1 = z + 1.0f, z2 = z + 2.0f, z3 = z + 3.0f;
     const float p01 = z * z1, p23 = z2 * z3;
     const float P = p01 * p23;
     const float dP = (z + z1) * p23 + p01 * (z2 + z3);
-    sub_lg = logf(P);
-    sub_dg = dP / P;
-    zs = z + 4.0f;
+    const float lz = logf(z), lzs = logf(zs);
+    cv += ((zs - 0.5f) * lzs - zs) - ((z - 0.5f) * lz - z) - logf(P);
+    dl += (lzs - lz) - dP / P;
   }
-  const float lz = logf(zs);
-  const float rz = 1.0f / zs;
-  const float r2 = rz * rz;
-  // Stirling: lgamma(z) = (z-1/2) ln z - z + ln(2 pi)/2 + 1/(12 z) - 1/(360 z^3) + 1/(1260 z^5) - 1/(1680 z^7)
-  const float s_lg = rz * (8.3333333333e-2f + r2 * (-2.7777777778e-3f + r2 * (7.9365079365e-4f + r2 * -5.9523809524e-4f)));
-  lg = (zs - 0.5f) * lz - zs + 0.91893853320467274f + s_lg - sub_lg;
-  // psi(z) = ln z - 1/(2z) - 1/(12 z^2) + 1/(120 z^4) - 1/(252 z^6) + 1/(240 z^8)
-  const float s_dg = r2 * (8.3333333333e-2f + r2 * (-8.3333333333e-3f + r2 * (3.9682539683e-3f + r2 * -4.1666666667e-3f)));
-  dg = lz - 0.5f * rz - s_dg - sub_dg;
 }
 
-__device__ __forceinline__ void lgamma_digamma(double z, double& lg, double& dg) {
-  lg = ::lgamma(z);
-  // digamma: recurrence up to z >= 10, then the asymptotic series (7 Bernoulli terms)
+__device__ __forceinline__ double digamma_f64(double z) {
+  // recurrence up to z >= 10, then the asymptotic series (7 Bernoulli terms)
   double sub = 0.0, zs = z;
   while (zs < 10.0) {
     sub += 1.0 / zs;
@@ -72,20 +75,26 @@ __device__ __forceinline__ void lgamma_digamma(double z, double& lg, double& dg)
   }
   const double rz = 1.0 / zs, r2 = rz * rz;
   const double s = r2 * (1.0 / 12 + r2 * (-1.0 / 120 + r2 * (1.0 / 252 + r2 * (-1.0 / 240 + r2 * (1.0 / 132 + r2 * (-691.0 / 32760 + r2 * (1.0 / 12)))))));
-  dg = ::log(zs) - 0.5 * rz - s - sub;
+  return ::log(zs) - 0.5 * rz - s - sub;
 }
 
-// lgamma(1 + x) for a non-negative integer-valued count (data-only term of the DM log-pmf)
-template <typename real>
-__device__ __forceinline__ real lgamma1p_count(real x) {
-  return Num<real>::lgamma(x + real(1));
+__device__ __forceinline__ void gamma_corr(double z, double& cv, double& dl) {
+  const double lz = ::log(z);
+  cv = ::lgamma(z) - ((z - 0.5) * lz - z + 0.91893853320467274178);
+  dl = digamma_f64(z) - lz;
 }
 
-// ---- Normal CDF pieces (reference: torch Normal.cdf = 0.5 * (1 + erf((x - mu) / sd / sqrt(2)))) ---
+// full lgamma / digamma of one argument (off the hot row loop: Dirichlet normalisers)
 template <typename real>
-__device__ __forceinline__ real std_normal_cdf(real z) {
-  return real(0.5) * (real(1) + Num<real>::erf(z * real(0.70710678118654752440)));
+__device__ __forceinline__ void lgamma_digamma(real z, real& lg, real& dg) {
+  real cv, dl;
+  gamma_corr(z, cv, dl);
+  const real lz = Num<real>::log(z);
+  lg = (z - real(0.5)) * lz - z + real(0.91893853320467274178) + cv;
+  dg = lz + dl;
 }
+
+// ---- Normal CDF pieces ----------------------------------------------------------------------------
 template <typename real>
 __device__ __forceinline__ real std_normal_pdf(real z) {
   return real(0.39894228040143267794) * Num<real>::exp(real(-0.5) * z * z);
@@ -93,25 +102,44 @@ __device__ __forceinline__ real std_normal_pdf(real z) {
 
 // Probability mass of one sorting bin and its derivatives w.r.t. (mu, sd).
 // thr_u = +inf / thr_l = -inf encode quantile 1 / 0 (model/utils.py:48-54, :60-72).
-template <typename real>
-__device__ __forceinline__ void bin_prob_sorting(real thr_u, real thr_l, real mu, real sd, real& P,
-                                                 real& dP_dmu, real& dP_dsd) {
-  const real rs = real(1) / sd;
-  real cu = real(1), fu = real(0), zfu = real(0);
-  real cl = real(0), fl = real(0), zfl = real(0);
+// double: exactly the reference expression, Normal.cdf = 0.5 (1 + erf(z / sqrt 2)).
+__device__ __forceinline__ void bin_prob_sorting(double thr_u, double thr_l, double mu, double sd, double& P,
+                                                 double& dP_dmu, double& dP_dsd) {
+  const double rs = 1.0 / sd;
+  double cu = 1.0, fu = 0.0, zfu = 0.0, cl = 0.0, fl = 0.0, zfl = 0.0;
   if (!isinf(thr_u)) {
-    const real z = (thr_u - mu) * rs;
-    cu = std_normal_cdf(z);
+    const double z = (thr_u - mu) * rs;
+    cu = 0.5 * (1.0 + ::erf(z * 0.70710678118654752440));
     fu = std_normal_pdf(z);
     zfu = z * fu;
   }
   if (!isinf(thr_l)) {
-    const real z = (thr_l - mu) * rs;
-    cl = std_normal_cdf(z);
+    const double z = (thr_l - mu) * rs;
+    cl = 0.5 * (1.0 + ::erf(z * 0.70710678118654752440));
     fl = std_normal_pdf(z);
     zfl = z * fl;
   }
   P = cu - cl;
+  dP_dmu = -(fu - fl) * rs;
+  dP_dsd = -(zfu - zfl) * rs;
+}
+
+// float: the same mass written with erfc on the tail side, Q(z) = erfc(z / sqrt 2) / 2, so that a bin far
+// in a tail keeps its RELATIVE accuracy (0.5 (1 + erf) in float loses it below ~1e-3 and that error is
+// amplified by a0 / sum(p) downstream).
+__device__ __forceinline__ void bin_prob_sorting(float thr_u, float thr_l, float mu, float sd, float& P,
+                                                 float& dP_dmu, float& dP_dsd) {
+  const float rs = 1.0f / sd;
+  const bool hu = !isinf(thr_u), hl = !isinf(thr_l);
+  const float zu = hu ? (thr_u - mu) * rs : INFINITY;
+  const float zl = hl ? (thr_l - mu) * rs : -INFINITY;
+  const float k = 0.70710678118654752440f;
+  if (zl > 0.0f)
+    P = 0.5f * (erfcf(zl * k) - erfcf(zu * k));
+  else
+    P = 0.5f * (erfcf(-zu * k) - erfcf(-zl * k));
+  const float fu = hu ? std_normal_pdf(zu) : 0.0f, fl = hl ? std_normal_pdf(zl) : 0.0f;
+  const float zfu = hu ? zu * fu : 0.0f, zfl = hl ? zl * fl : 0.0f;
   dP_dmu = -(fu - fl) * rs;
   dP_dsd = -(zfu - zfl) * rs;
 }

@@ -1,0 +1,58 @@
+// bean_row.cuh -- one Dirichlet-Multinomial row: value and digamma differences in "KL form".
+//
+// Replaces, per (replicate, guide, layer) row, pyro's
+//   DirichletMultinomial(a).log_prob(x) = lgG(A) + lgG(N+1) - lgG(N+A) - sum_b [lgG(x_b+1) + lgG(a_b) - lgG(x_b+a_b)]
+// and the digamma differences autograd would produce, written so that no large
+// term is ever formed.  With u_b = x_b + a_b, U = N + A, num_b = x_b A - a_b N (computed exactly via FMA):
+//
+//   L2_b = log1p( num_b / (U a_b)) = ln(u_b A / (a_b U))          L1_b = log1p(-num_b / (U x_b)) = ln(u_b N / (U x_b))
+//   V    = sum_b [x_b L1_b + a_b L2_b] - 1/2 [sum_b L2_b + (B-1) ln(U/A)] + sum_b [cv(u_b) - cv(a_b)] - [cv(U) - cv(A)]
+//   gb   = psi(A) - psi(U) + psi(u_b) - psi(a_b) = L2_b + [dl(A) - dl(U)] + [dl(u_b) - dl(a_b)]
+//   log_prob = V + K,   K = lgG(N+1) - sum_b lgG(x_b+1) + sum_{x_b>0} x_b ln(x_b / N)      (data only, hoisted)
+//
+// (cv, dl) = gamma_corr: the parts of lgamma / digamma beyond the Stirling main term (bean_math.cuh).
+#pragma once
+#include "bean_math.cuh"
+
+namespace bean {
+
+// x, a: counts and concentrations of the row (a_b > 0); nb = number of bins actually used (<= NB).
+// Returns V; gb[b] receives the digamma difference of bin b.
+template <typename real, int NB>
+__device__ __forceinline__ real dm_row_kl(int nb, const real (&x)[NB], const real (&a)[NB], real N, real A,
+                                          real (&gb)[NB]) {
+  const real U = N + A;
+  const real rU = real(1) / U;
+  real cvA, dlA, cvU, dlU;
+  gamma_corr(A, cvA, dlA);
+  gamma_corr(U, cvU, dlU);
+  const real lUA = Num<real>::log(U / A);
+  const real dlAU = dlA - dlU;
+  real V = real(0), sumL2 = real(0), csum = real(0);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (b < nb) {
+      const real u = x[b] + a[b];
+      real cva, dla, cvu, dlu;
+      gamma_corr(a[b], cva, dla);
+      gamma_corr(u, cvu, dlu);
+      // num = x A - a N without cancellation error: p + e == a N exactly
+      const real p = a[b] * N;
+      const real e = fma(a[b], N, -p);
+      const real num = fma(x[b], A, -p) - e;
+      const real t = num * rU;
+      const real L2 = Num<real>::log1p(t / a[b]);
+      const real L1 = x[b] > real(0) ? Num<real>::log1p(-t / x[b]) : real(0);
+      V += x[b] * L1 + a[b] * L2;
+      sumL2 += L2;
+      csum += cvu - cva;
+      gb[b] = L2 + (dlAU + (dlu - dla));
+    } else {
+      gb[b] = real(0);
+    }
+  }
+  V += real(-0.5) * (sumL2 + real(nb - 1) * lUA) + (csum - (cvU - cvA));
+  return V;
+}
+
+}  // namespace bean

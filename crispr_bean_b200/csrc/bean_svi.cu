@@ -1,0 +1,491 @@
+// bean_svi.cu -- the fused SVI step of the variant sorting models (Normal / ControlNormal / MixtureNormal).
+//
+// Per step, two kernels and no host round trip (reference: one `svi.step`, bean/model/run.py:376-380,
+// ~2,500 eager torch op dispatches):
+//
+//   svi_guide_kernel   one thread per guide, looping over its replicates with everything in registers:
+//       draw (mu, sd) of its variant and pi[r] ~ Dirichlet (counter-based Philox), Normal-CDF bin masses,
+//       allele mixture, get_alpha + Dirichlet-Multinomial of both count layers with their digamma
+//       differences, the Dirichlet / Multinomial editing-rate sites, the pathwise Dirichlet derivative,
+//       the alpha_pi gradient AND its ClippedAdam update (alpha_pi is per-guide, so it never leaves the
+//       thread), per-guide d ELBO / d(mu, sd), ELBO partial per CTA.
+//   svi_variant_kernel 8 lanes per variant: segmented reduction of the per-guide gradients over the CSR
+//       variant range (no atomics; guides of a variant are contiguous, data_class.py:511-532), prior and
+//       entropy terms, ClippedAdam on (mu_loc, mu_scale, sd_loc, sd_scale), and -- in the last CTA to
+//       finish -- the deterministic reduction of all ELBO partials into loss[t].
+#include "bean_common.cuh"
+#include "bean_math.cuh"
+#include "bean_rng.cuh"
+#include "bean_row.cuh"
+
+namespace bean {
+
+constexpr int SVI_THREADS = 128;
+constexpr int VAR_THREADS = 256;
+constexpr int VAR_LANES = 8;  // lanes cooperating on one variant
+constexpr int VAR_PER_CTA = VAR_THREADS / VAR_LANES;
+
+template <typename real>
+struct SviParams {
+  int G, R, B, L, T;
+  int mixture, sd_is_sqrt, mu_prior_normal, apply_update;
+  uint32_t step;
+  uint64_t seed;
+  real mask_thres;
+  // screen
+  const real* x;
+  const real* a0;
+  const uint8_t* row_mask;
+  const int32_t* guide_variant;
+  const int32_t* variant_ptr;
+  const real* allele_counts;
+  const real* pi_a0;
+  // parameters + Adam state
+  real* var_params;
+  real* var_m;
+  real* var_v;
+  real* alpha_u;
+  real* alpha_m;
+  real* alpha_v;
+  // scratch / outputs
+  real* d_guide;
+  real* var_grad;
+  real* alpha_grad;
+  double* partial;
+  uint32_t* counter;
+  double* loss;
+  int n_partial_guide, n_partial_var;
+  // injected noise (parity runs)
+  const real* eps_mu;
+  const real* eps_sd;
+  const real* pi_in;
+  real* eps_out;
+  real* pi_out;
+  // priors / optimiser scalars of this step
+  real mu_prior_loc, mu_prior_scale, sd_prior_loc, sd_prior_scale;
+  real step_size, beta1, beta2, adam_eps, clip;
+  double ll_const;
+  real p_wt[BEAN_MAX_BINS];  // bin masses of the wild-type allele N(0, 1)
+  SampleTables<real> t;
+};
+
+// pyro.optim.ClippedAdam on one unconstrained scalar; step_size carries
+// lr_t * sqrt(1 - beta2^t) / (1 - beta1^t).
+template <typename real>
+__device__ __forceinline__ void clipped_adam(const SviParams<real>& p, real grad, real& theta, real& m, real& v) {
+  const real g = Num<real>::fmin(Num<real>::fmax(grad, -p.clip), p.clip);
+  m = p.beta1 * m + (real(1) - p.beta1) * g;
+  v = p.beta2 * v + (real(1) - p.beta2) * g * g;
+  theta -= p.step_size * m / (Num<real>::sqrt(v) + p.adam_eps);
+}
+
+// reparameterised draw of the variant's (mu, sd) -- recomputed wherever needed instead of stored
+template <typename real>
+__device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, real& mu_t, real& sd_t, real& eps_mu,
+                                             real& eps_sd, real& mu_scale, real& sd_scale, real& log_sd) {
+  const real mu_loc = p.var_params[v];
+  mu_scale = Num<real>::exp(p.var_params[p.T + v]);
+  const real sd_loc = p.var_params[2 * p.T + v];
+  sd_scale = Num<real>::exp(p.var_params[3 * p.T + v]);
+  if (p.eps_mu) {
+    eps_mu = p.eps_mu[v];
+    eps_sd = p.eps_sd[v];
+  } else {
+    float e0, e1;
+    variant_noise(p.seed, (uint32_t)v, p.step, e0, e1);
+    eps_mu = real(e0);
+    eps_sd = real(e1);
+  }
+  mu_t = mu_loc + mu_scale * eps_mu;   // Normal(mu_loc, mu_scale).rsample()          model.py:810
+  log_sd = sd_loc + sd_scale * eps_sd;  // LogNormal(sd_loc, sd_scale).rsample()       model.py:811
+  sd_t = Num<real>::exp(log_sd);
+}
+
+template <typename real, int NB, bool MIXTURE>
+__global__ void __launch_bounds__(SVI_THREADS) svi_guide_kernel(const SviParams<real> p) {
+  __shared__ double red[32];
+  const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
+  const int R = p.R, B = p.B;
+  const real eps = real(1e-5);
+  double elbo = 0.0;
+  if (g < p.G) {
+    const int v = p.guide_variant[g];
+    real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd;
+    variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd);
+    const real sigma = p.sd_is_sqrt ? Num<real>::sqrt(sd_t) : sd_t;  // model.py:92-98
+    real P1[NB], dPm[NB], dPs[NB], dP[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      P1[b] = dPm[b] = dPs[b] = dP[b] = real(0);
+      if (b < B) bin_prob_sorting(p.t.thr_u[b], p.t.thr_l[b], mu_t, sigma, P1[b], dPm[b], dPs[b]);
+    }
+    // editing-rate concentrations (model.py:449 / :835): model = alpha/sum*pi_a0, guide = clamp(model, 1e-5)
+    real al[2] = {real(1), real(1)}, cm[2] = {real(1), real(1)}, cg[2] = {real(1), real(1)};
+    real lg_cm = real(0), lg_cg = real(0), dg_cm[3] = {}, dg_cg[3] = {}, dcm[2] = {}, dcg[2] = {};
+    real asum = real(2), pa0 = real(0);
+    if (MIXTURE) {
+      al[0] = Num<real>::exp(p.alpha_u[2 * (size_t)g]);
+      al[1] = Num<real>::exp(p.alpha_u[2 * (size_t)g + 1]);
+      asum = al[0] + al[1];
+      pa0 = p.pi_a0[g];
+      real lg0, lg1, lgs;
+      cm[0] = al[0] / asum * pa0;
+      cm[1] = al[1] / asum * pa0;
+      lgamma_digamma(cm[0], lg0, dg_cm[0]);
+      lgamma_digamma(cm[1], lg1, dg_cm[1]);
+      lgamma_digamma(cm[0] + cm[1], lgs, dg_cm[2]);
+      lg_cm = lgs - lg0 - lg1;
+      cg[0] = Num<real>::fmax(cm[0], eps);
+      cg[1] = Num<real>::fmax(cm[1], eps);
+      if (cg[0] == cm[0] && cg[1] == cm[1]) {
+        lg_cg = lg_cm;
+        dg_cg[0] = dg_cm[0]; dg_cg[1] = dg_cm[1]; dg_cg[2] = dg_cm[2];
+      } else {
+        lgamma_digamma(cg[0], lg0, dg_cg[0]);
+        lgamma_digamma(cg[1], lg1, dg_cg[1]);
+        lgamma_digamma(cg[0] + cg[1], lgs, dg_cg[2]);
+        lg_cg = lgs - lg0 - lg1;
+      }
+    }
+    real elbo_g = real(0);
+    for (int r = 0; r < R; ++r) {
+      const bool rmask = p.row_mask[(size_t)g * R + r] != 0;
+      real pi0 = real(0), pi1 = real(1);
+      if (MIXTURE) {
+        if (p.pi_in) {
+          pi0 = p.pi_in[((size_t)g * R + r) * 2];
+          pi1 = p.pi_in[((size_t)g * R + r) * 2 + 1];
+        } else {
+          sample_pi2(p.seed, (uint32_t)g, (uint32_t)r, p.step, cg[0], cg[1], pi0, pi1);
+        }
+        if (p.pi_out) {
+          p.pi_out[((size_t)g * R + r) * 2] = pi0;
+          p.pi_out[((size_t)g * R + r) * 2 + 1] = pi1;
+        }
+      }
+      real e[NB], de[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        e[b] = MIXTURE ? pi0 * p.p_wt[b] + pi1 * P1[b] : P1[b];  // model.py:495-499
+        de[b] = real(0);
+      }
+      for (int l = 0; l < p.L; ++l) {
+        const real* xr = p.x + (((size_t)l * p.G + g) * R + r) * B;
+        real xb[NB], pb[NB], ab[NB], frac[NB], gb[NB];
+        bool live[NB];
+        real N = real(0), S = real(0);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          xb[b] = b < B ? xr[b] : real(0);
+          N += xb[b];
+          pb[b] = b < B ? e[b] * p.t.sf[l][r * B + b] : real(0);
+          S += pb[b];
+        }
+        if (!(rmask && N > p.mask_thres)) continue;  // poutine.mask: the row contributes nothing
+        const real a0 = p.a0[(size_t)l * p.G + g];
+        const real inv = real(1) / (S + eps);
+        real Asum = real(0);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          frac[b] = (pb[b] + eps / real(B)) * inv;  // utils.py:19-23
+          const real raw = frac[b] * a0 * p.t.smask[r * B + b];
+          live[b] = raw >= eps;
+          ab[b] = (b < B) ? (live[b] ? raw : eps) : real(0);
+          Asum += ab[b];
+        }
+        elbo_g += dm_row_kl<real, NB>(B, xb, ab, N, Asum, gb);
+        real dot = real(0);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          gb[b] = (b < B && live[b]) ? gb[b] * p.t.smask[r * B + b] : real(0);
+          dot += gb[b] * frac[b];
+        }
+        const real c = a0 * inv;
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+          if (b < B) de[b] += p.t.sf[l][r * B + b] * c * (gb[b] - dot);
+      }
+      if (MIXTURE) {
+        // d ELBO / d pi from the likelihood
+        real go0 = real(0), go1 = real(0);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          go0 += de[b] * p.p_wt[b];
+          go1 += de[b] * P1[b];
+          dP[b] += de[b] * pi1;
+        }
+        const real lp0 = Num<real>::log(pi0), lp1 = Num<real>::log(pi1);
+        // guide site: -log Dirichlet(pi; cg), unmasked (model.py:837-847)
+        elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
+        go0 -= (cg[0] - real(1)) / pi0;
+        go1 -= (cg[1] - real(1)) / pi1;
+        dcg[0] -= dg_cg[2] - dg_cg[0] + lp0;
+        dcg[1] -= dg_cg[2] - dg_cg[1] + lp1;
+        if (rmask) {
+          // model sites under poutine.mask(repguide_mask): Dirichlet prior on pi and Multinomial reporter
+          // counts (model.py:454-474); torch Multinomial normalises probs and clamps them to [eps, 1-eps]
+          elbo_g += lg_cm + (cm[0] - real(1)) * lp0 + (cm[1] - real(1)) * lp1;
+          go0 += (cm[0] - real(1)) / pi0;
+          go1 += (cm[1] - real(1)) / pi1;
+          dcm[0] += dg_cm[2] - dg_cm[0] + lp0;
+          dcm[1] += dg_cm[2] - dg_cm[1] + lp1;
+          const real x0 = p.allele_counts[((size_t)g * R + r) * 2], x1 = p.allele_counts[((size_t)g * R + r) * 2 + 1];
+          const real Sp = pi0 + pi1, pn0 = pi0 / Sp, pn1 = pi1 / Sp;
+          const real lo = Lim<real>::eps(), hi = real(1) - Lim<real>::eps();
+          const real c0 = Num<real>::fmin(Num<real>::fmax(pn0, lo), hi), c1 = Num<real>::fmin(Num<real>::fmax(pn1, lo), hi);
+          elbo_g += x0 * Num<real>::log(c0) + x1 * Num<real>::log(c1);
+          const real h0 = (pn0 >= lo && pn0 <= hi) ? x0 / c0 : real(0), h1 = (pn1 >= lo && pn1 <= hi) ? x1 / c1 : real(0);
+          const real hbar = h0 * pn0 + h1 * pn1;
+          go0 += (h0 - hbar) / Sp;
+          go1 += (h1 - hbar) / Sp;
+        }
+        // pathwise derivative of pi w.r.t. the guide concentration (torch _Dirichlet_backward)
+        // evaluated in double even on the float path, as torch's CPU kernel does (accscalar_t = double):
+        // the saddle-point branch cancels badly in float
+        const double tot = (double)cg[0] + (double)cg[1];
+        const double gbar = (double)pi0 * (double)go0 + (double)pi1 * (double)go1;
+        dcg[0] += real(dirichlet_grad_one<double>((double)pi0, (double)cg[0], tot) * ((double)go0 - gbar));
+        dcg[1] += real(dirichlet_grad_one<double>((double)pi1, (double)cg[1], tot) * ((double)go1 - gbar));
+      } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) dP[b] += de[b];
+      }
+    }
+    // per-guide gradient w.r.t. the edited allele's (mu, sd_targets); reduced per variant by the next kernel
+    real dmu = real(0), dsg = real(0);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      dmu += dP[b] * dPm[b];
+      dsg += dP[b] * dPs[b];
+    }
+    if (p.sd_is_sqrt) dsg *= real(0.5) / sigma;
+    p.d_guide[g] = dmu;
+    p.d_guide[(size_t)p.G + g] = dsg;
+    if (MIXTURE) {
+      // concentration -> log alpha_pi; clamp(min) passes the gradient where its input >= 1e-5
+      const real dC0 = dcm[0] + (cm[0] >= eps ? dcg[0] : real(0));
+      const real dC1 = dcm[1] + (cm[1] >= eps ? dcg[1] : real(0));
+      const real k = pa0 / (asum * asum);
+      const real dal0 = k * (dC0 * (asum - al[0]) - dC1 * al[1]);
+      const real dal1 = k * (dC1 * (asum - al[1]) - dC0 * al[0]);
+      const real gl0 = -dal0 * al[0], gl1 = -dal1 * al[1];  // loss = -ELBO, unconstrained (log) space
+      if (p.alpha_grad) {
+        p.alpha_grad[2 * (size_t)g] = gl0;
+        p.alpha_grad[2 * (size_t)g + 1] = gl1;
+      }
+      if (p.apply_update) {
+        real th0 = p.alpha_u[2 * (size_t)g], th1 = p.alpha_u[2 * (size_t)g + 1];
+        real m0 = p.alpha_m[2 * (size_t)g], m1 = p.alpha_m[2 * (size_t)g + 1];
+        real v0 = p.alpha_v[2 * (size_t)g], v1 = p.alpha_v[2 * (size_t)g + 1];
+        clipped_adam(p, gl0, th0, m0, v0);
+        clipped_adam(p, gl1, th1, m1, v1);
+        p.alpha_u[2 * (size_t)g] = th0; p.alpha_u[2 * (size_t)g + 1] = th1;
+        p.alpha_m[2 * (size_t)g] = m0;  p.alpha_m[2 * (size_t)g + 1] = m1;
+        p.alpha_v[2 * (size_t)g] = v0;  p.alpha_v[2 * (size_t)g + 1] = v1;
+      }
+    }
+    elbo = (double)elbo_g;
+  }
+  const double tot = block_sum(elbo, red);
+  if (threadIdx.x == 0) p.partial[blockIdx.x] = tot;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParams<real> p) {
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  const int v = blockIdx.x * VAR_PER_CTA + threadIdx.x / VAR_LANES;
+  const int sub = threadIdx.x % VAR_LANES;
+  const bool valid = v < p.T;
+  // segmented reduction of the guide gradients over the variant's contiguous guide range
+  real dmu = real(0), dsd = real(0);
+  if (valid) {
+    const int beg = p.variant_ptr[v], end = p.variant_ptr[v + 1];
+    for (int j = beg + sub; j < end; j += VAR_LANES) {
+      dmu += p.d_guide[j];
+      dsd += p.d_guide[(size_t)p.G + j];
+    }
+  }
+#pragma unroll
+  for (int o = VAR_LANES / 2; o > 0; o >>= 1) {
+    dmu += __shfl_xor_sync(0xffffffffu, dmu, o);
+    dsd += __shfl_xor_sync(0xffffffffu, dsd, o);
+  }
+  double elbo = 0.0;
+  if (valid && sub == 0) {
+    real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y;
+    variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y);
+    if (p.eps_out) {
+      p.eps_out[v] = e_mu;
+      p.eps_out[p.T + v] = e_sd;
+    }
+    const real HL2PI = real(0.91893853320467274178);
+    // model priors (model.py:41-65 / :405-428; ControlNormal :178-179)
+    real lp_mu, dlp_mu;
+    if (p.mu_prior_normal) {
+      const real z = (mu_t - p.mu_prior_loc) / p.mu_prior_scale;
+      lp_mu = -Num<real>::log(p.mu_prior_scale) - HL2PI - real(0.5) * z * z;
+      dlp_mu = -z / p.mu_prior_scale;
+    } else {  // Laplace(0, 1)
+      lp_mu = -real(0.69314718055994530942) - (mu_t < real(0) ? -mu_t : mu_t);
+      dlp_mu = mu_t > real(0) ? real(-1) : (mu_t < real(0) ? real(1) : real(0));
+    }
+    const real zs = (y - p.sd_prior_loc) / p.sd_prior_scale;
+    const real lp_sd = -y - Num<real>::log(p.sd_prior_scale) - HL2PI - real(0.5) * zs * zs;
+    const real dlp_sd = (-real(1) - zs / p.sd_prior_scale) / sd_t;
+    // guide densities (entropy side)
+    const real lq_mu = -Num<real>::log(mu_scale) - HL2PI - real(0.5) * e_mu * e_mu;
+    const real lq_sd = -y - Num<real>::log(sd_scale) - HL2PI - real(0.5) * e_sd * e_sd;
+    elbo = (double)lp_mu + (double)lp_sd - (double)lq_mu - (double)lq_sd;
+    const real dE_mu = dmu + dlp_mu;
+    const real dE_sd = dsd + dlp_sd;
+    // gradient of the LOSS (-ELBO) w.r.t. the unconstrained parameters
+    real grad[4];
+    grad[0] = -dE_mu;
+    grad[1] = -(dE_mu * e_mu * mu_scale + real(1));
+    grad[2] = -(dE_sd * sd_t + real(1));
+    grad[3] = -((dE_sd * sd_t * e_sd + e_sd) * sd_scale + real(1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t i = (size_t)k * p.T + v;
+      if (p.var_grad) p.var_grad[i] = grad[k];
+      if (p.apply_update) {
+        real th = p.var_params[i], m = p.var_m[i], vv = p.var_v[i];
+        clipped_adam(p, grad[k], th, m, vv);
+        p.var_params[i] = th;
+        p.var_m[i] = m;
+        p.var_v[i] = vv;
+      }
+    }
+  }
+  const double tot = block_sum(elbo, red);
+  if (threadIdx.x == 0) {
+    p.partial[p.n_partial_guide + blockIdx.x] = tot;
+    __threadfence();
+    const uint32_t done = atomicAdd(p.counter, 1u);
+    is_last = (done == (uint32_t)gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (is_last) {
+    // last CTA: fixed-order reduction of every partial of this step -> loss[t] = -ELBO
+    __threadfence();
+    double acc = 0.0;
+    const int n = p.n_partial_guide + p.n_partial_var;
+    for (int i = threadIdx.x; i < n; i += VAR_THREADS) acc += p.partial[i];
+    const double all = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      p.loss[p.step] = -(all + p.ll_const);
+      *p.counter = 0u;
+    }
+  }
+}
+
+template <typename real, bool MIXTURE>
+static void launch_guide(const SviParams<real>& p, cudaStream_t st) {
+  const int grid = (p.G + SVI_THREADS - 1) / SVI_THREADS;
+  if (p.B <= 4)
+    svi_guide_kernel<real, 4, MIXTURE><<<grid, SVI_THREADS, 0, st>>>(p);
+  else if (p.B == 5)
+    svi_guide_kernel<real, 5, MIXTURE><<<grid, SVI_THREADS, 0, st>>>(p);
+  else
+    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE><<<grid, SVI_THREADS, 0, st>>>(p);
+}
+
+template <typename real>
+static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSviConfig* cfg, const BeanSviNoise* noise,
+                   int32_t first_step, int32_t n_steps, void* stream) {
+  int rc = validate_screen(s);
+  if (rc != BEAN_OK) return rc;
+  BEAN_REQUIRE(state && cfg, BEAN_EINVAL, "state / cfg is NULL");
+  BEAN_REQUIRE(s->mode == BEAN_MODE_SORTING, BEAN_EINVAL, "bean_svi_run supports the sorting models only");
+  BEAN_REQUIRE(cfg->model == BEAN_MODEL_NORMAL || cfg->model == BEAN_MODEL_MIXTURE_NORMAL, BEAN_EINVAL, "bad model %d", cfg->model);
+  BEAN_REQUIRE(state->n_variants > 0, BEAN_EINVAL, "n_variants must be > 0");
+  BEAN_REQUIRE(state->guide_variant && state->variant_ptr, BEAN_EINVAL, "guide_variant / variant_ptr must be non-NULL");
+  BEAN_REQUIRE(state->var_params && state->var_m && state->var_v, BEAN_EINVAL, "variant parameter buffers must be non-NULL");
+  BEAN_REQUIRE(state->d_guide && state->partial && state->counter && state->loss, BEAN_EINVAL, "scratch buffers must be non-NULL");
+  const bool mix = cfg->model == BEAN_MODEL_MIXTURE_NORMAL;
+  if (mix) {
+    BEAN_REQUIRE(state->allele_counts && state->pi_a0, BEAN_EINVAL, "MixtureNormal needs allele_counts / pi_a0");
+    BEAN_REQUIRE(state->alpha_u && state->alpha_m && state->alpha_v, BEAN_EINVAL, "MixtureNormal needs alpha_u / alpha_m / alpha_v");
+  }
+  BEAN_REQUIRE(first_step >= 0 && n_steps >= 0, BEAN_EINVAL, "first_step / n_steps must be >= 0");
+  BEAN_REQUIRE(first_step + n_steps <= state->loss_capacity, BEAN_EINVAL, "loss buffer too small: %d + %d > %d", first_step,
+               n_steps, state->loss_capacity);
+  if (noise && (noise->eps_mu || noise->eps_sd))
+    BEAN_REQUIRE(noise->eps_mu && noise->eps_sd, BEAN_EINVAL, "eps_mu and eps_sd must be injected together");
+
+  SviParams<real> p;
+  p.G = s->n_guides; p.R = s->n_reps; p.B = s->n_bins; p.L = s->n_layers; p.T = state->n_variants;
+  p.mixture = mix; p.sd_is_sqrt = cfg->sd_is_sqrt; p.mu_prior_normal = cfg->mu_prior_normal; p.apply_update = cfg->apply_update;
+  p.seed = cfg->seed;
+  p.mask_thres = real(s->mask_thres);
+  p.x = static_cast<const real*>(s->x);
+  p.a0 = static_cast<const real*>(s->a0);
+  p.row_mask = s->row_mask;
+  p.guide_variant = state->guide_variant;
+  p.variant_ptr = state->variant_ptr;
+  p.allele_counts = static_cast<const real*>(state->allele_counts);
+  p.pi_a0 = static_cast<const real*>(state->pi_a0);
+  p.var_params = static_cast<real*>(state->var_params);
+  p.var_m = static_cast<real*>(state->var_m);
+  p.var_v = static_cast<real*>(state->var_v);
+  p.alpha_u = static_cast<real*>(state->alpha_u);
+  p.alpha_m = static_cast<real*>(state->alpha_m);
+  p.alpha_v = static_cast<real*>(state->alpha_v);
+  p.d_guide = static_cast<real*>(state->d_guide);
+  p.var_grad = static_cast<real*>(state->var_grad);
+  p.alpha_grad = static_cast<real*>(state->alpha_grad);
+  p.partial = state->partial;
+  p.counter = state->counter;
+  p.loss = state->loss;
+  p.n_partial_guide = (p.G + SVI_THREADS - 1) / SVI_THREADS;
+  p.n_partial_var = (p.T + VAR_PER_CTA - 1) / VAR_PER_CTA;
+  p.eps_mu = noise ? static_cast<const real*>(noise->eps_mu) : nullptr;
+  p.eps_sd = noise ? static_cast<const real*>(noise->eps_sd) : nullptr;
+  p.pi_in = noise ? static_cast<const real*>(noise->pi) : nullptr;
+  p.eps_out = noise ? static_cast<real*>(noise->eps_out) : nullptr;
+  p.pi_out = noise ? static_cast<real*>(noise->pi_out) : nullptr;
+  p.mu_prior_loc = real(cfg->mu_prior_loc); p.mu_prior_scale = real(cfg->mu_prior_scale);
+  p.sd_prior_loc = real(cfg->sd_prior_loc); p.sd_prior_scale = real(cfg->sd_prior_scale);
+  p.beta1 = real(cfg->beta1); p.beta2 = real(cfg->beta2); p.adam_eps = real(cfg->adam_eps); p.clip = real(cfg->clip);
+  p.ll_const = cfg->ll_const;
+  fill_tables(s, p.t);
+  for (int b = 0; b < BEAN_MAX_BINS; ++b) {
+    double m = 0.0;
+    if (b < s->n_bins) {  // wild-type allele N(0, 1): Phi(t_u) - Phi(t_l), as get_std_normal_prob does in float64
+      const double cu = isinf(s->upper_thres[b]) ? 1.0 : 0.5 * (1.0 + erf(s->upper_thres[b] * 0.70710678118654752440));
+      const double cl = isinf(s->lower_thres[b]) ? 0.0 : 0.5 * (1.0 + erf(s->lower_thres[b] * 0.70710678118654752440));
+      m = cu - cl;
+    }
+    p.p_wt[b] = real(m);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n_steps; ++i) {
+    const int t = first_step + i;  // 0-based step; ClippedAdam's state["step"] = t + 1
+    p.step = (uint32_t)t;
+    const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
+    p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
+    if (mix) launch_guide<real, true>(p, st); else launch_guide<real, false>(p, st);
+    svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
+  }
+  BEAN_CUDA(cudaPeekAtLastError());
+  return BEAN_OK;
+}
+
+}  // namespace bean
+
+extern "C" {
+
+int bean_svi_num_partials(int32_t n_guides, int32_t n_variants) {
+  return (n_guides + bean::SVI_THREADS - 1) / bean::SVI_THREADS + (n_variants + bean::VAR_PER_CTA - 1) / bean::VAR_PER_CTA;
+}
+int bean_svi_run_f32(const BeanScreen* s, const BeanSviState* st, const BeanSviConfig* c, const BeanSviNoise* n,
+                     int32_t first_step, int32_t n_steps, void* stream) {
+  return bean::svi_run<float>(s, st, c, n, first_step, n_steps, stream);
+}
+int bean_svi_run_f64(const BeanScreen* s, const BeanSviState* st, const BeanSviConfig* c, const BeanSviNoise* n,
+                     int32_t first_step, int32_t n_steps, void* stream) {
+  return bean::svi_run<double>(s, st, c, n, first_step, n_steps, stream);
+}
+
+}  // extern "C"

@@ -52,10 +52,20 @@ class DeviceScreen:
         else:
             self._tu = self._tl = np.zeros(B)
             self._tp = np.ascontiguousarray(data.timepoints.double().numpy())
+        # data-only part of every row's Dirichlet-Multinomial log-pmf, hoisted out of the SVI loop
+        # (recomputed every step by the reference: L*(B+1) of its L*(3B+3) lgammas per row)
+        x64 = self.x.double()
+        n64 = x64.sum(-1)
+        self.row_const = (torch.lgamma(n64 + 1) - torch.lgamma(x64 + 1).sum(-1)
+                          + torch.xlogy(x64, x64 / n64.clamp(min=1.0).unsqueeze(-1)).sum(-1)).contiguous()  # (L, G, R)
+        self.row_weight = (n64 > self.mask_thres) & (self.row_mask != 0).unsqueeze(0)  # (L, G, R)
+        self.ll_const = float((self.row_const * self.row_weight).sum())
+        del x64, n64
         s = _lib.BeanScreen()
         s.n_guides, s.n_reps, s.n_bins, s.n_layers = G, R, B, self.n_layers
         s.mode, s.mask_thres = self.mode, self.mask_thres
         s.x, s.a0, s.row_mask = self.x.data_ptr(), self.a0.data_ptr(), self.row_mask.data_ptr()
+        s.row_const = self.row_const.data_ptr()
         s.size_factor, s.sample_mask = _dptr(self._sf), _dptr(self._smask)
         s.upper_thres, s.lower_thres, s.timepoints = _dptr(self._tu), _dptr(self._tl), _dptr(self._tp)
         self.c = s

@@ -68,6 +68,8 @@ typedef struct BeanScreen {
   const void* x;               /* real [L][G][R][B]   X_masked / X_bcmatch_masked               */
   const void* a0;              /* real [L][G]         a0 / a0_bcmatch                           */
   const uint8_t* row_mask;     /* u8   [G][R]         repguide_mask                             */
+  const double* row_const;     /* f64  [L][G][R] or NULL: data-only part of each row's log-pmf,
+                                  lgamma(N+1) - sum_b lgamma(x_b+1) + sum_{x_b>0} x_b ln(x_b/N)   */
   /* small per-sample tables, HOST pointers (copied into kernel arguments):                      */
   const double* size_factor;   /* [L][R][B]           size_factor / size_factor_bcmatch         */
   const double* sample_mask;   /* [R][B]                                                        */
@@ -109,6 +111,75 @@ typedef struct BeanLLArgs {
 int bean_ll_num_partials(int32_t n_guides);
 int bean_ll_f32(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
 int bean_ll_f64(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bean_svi_run_{f32,f64}: n_steps complete SVI steps on the device, no host round trip per step.
+ *
+ * One step = what `svi.step(data)` does in bean/model/run.py:376-380 for the variant sorting models:
+ *   guide program  (model.py:754-782 Normal, :785-858 MixtureNormal, :861-875 ControlNormal):
+ *       reparameterised draws  mu_targets ~ Normal, sd_targets ~ LogNormal, pi ~ Dirichlet
+ *   model program  (model.py:19-165, :168-252, :378-547): priors, Dirichlet / Multinomial editing-rate
+ *       sites, Normal-CDF bin probabilities, allele mixture, get_alpha, Dirichlet-Multinomial sites
+ *   Trace_ELBO (1 particle) loss and its gradient (pyro.infer; pathwise Dirichlet derivative as
+ *       torch._dirichlet_grad), then pyro.optim.ClippedAdam on the unconstrained parameters.
+ * Two kernels per step: a per-guide kernel (sampling, likelihood, editing-rate sites, alpha_pi gradient
+ * and its Adam update, per-guide d/d(mu, sd)) and a per-variant kernel (segmented reduction of the guide
+ * gradients over the CSR variant ranges, prior / entropy terms, Adam on the variant parameters, loss).
+ *
+ * Randomness is counter-based (Philox4x32-10 keyed by `seed`, indexed by (entity, replicate, step)),
+ * so a run is reproducible and independent of the launch geometry.  For parity tests the noise can be
+ * injected instead (BeanSviNoise), and `apply_update = 0` returns the loss gradient w.r.t. the
+ * unconstrained parameters without touching them.
+ * ---------------------------------------------------------------------------------------------- */
+enum { BEAN_MODEL_NORMAL = 0, BEAN_MODEL_MIXTURE_NORMAL = 1 };
+
+typedef struct BeanSviConfig {
+  int32_t model;            /* BEAN_MODEL_* (ControlNormal = NORMAL with one variant, sd_is_sqrt = 0) */
+  int32_t sd_is_sqrt;       /* NormalModel feeds sqrt(sd_targets) to the CDF (model.py:92-98)        */
+  int32_t mu_prior_normal;  /* 0: Laplace(0,1) (model.py:43); 1: Normal(mu_prior_loc, mu_prior_scale) */
+  int32_t apply_update;     /* 1: ClippedAdam step; 0: only write gradients                          */
+  double mu_prior_loc, mu_prior_scale;
+  double sd_prior_loc, sd_prior_scale; /* LogNormal prior on sd_targets: (0, 0.01); ControlNormal (0, 1) */
+  double lr0, lrd;          /* ClippedAdam: lr_t = lr0 * lrd^t, lrd = gamma^(1/num_steps) (run.py:367) */
+  double beta1, beta2, adam_eps, clip;
+  double ll_const;          /* data-only part of the ELBO (sum of masked lgamma(1+N) - sum lgamma(1+x)) */
+  uint64_t seed;
+} BeanSviConfig;
+
+typedef struct BeanSviState {
+  int32_t n_variants;            /* T */
+  int32_t loss_capacity;
+  const int32_t* guide_variant;  /* i32 [G]   variant of each guide (guides of a variant contiguous)  */
+  const int32_t* variant_ptr;    /* i32 [T+1] CSR: guides of variant v are [ptr[v], ptr[v+1])          */
+  const void* allele_counts;     /* real [G][R][2] control-condition reporter allele counts (MIXTURE)  */
+  const void* pi_a0;             /* real [G]                                                            */
+  void* var_params;              /* real [4][T]: mu_loc, log mu_scale, sd_loc, log sd_scale             */
+  void* var_m;                   /* real [4][T] Adam first moments                                      */
+  void* var_v;                   /* real [4][T] Adam second moments                                     */
+  void* alpha_u;                 /* real [G][2] log alpha_pi (MIXTURE)                                  */
+  void* alpha_m;
+  void* alpha_v;
+  void* d_guide;                 /* real [2][G] scratch: d ELBO / d(mu, sd) of each guide's edited allele */
+  void* var_grad;                /* real [4][T] out (loss gradient, unconstrained) or NULL              */
+  void* alpha_grad;              /* real [G][2] out or NULL                                             */
+  double* partial;               /* f64 [bean_svi_num_partials(G, T)] scratch                           */
+  uint32_t* counter;             /* u32 [1], zero before the first call                                 */
+  double* loss;                  /* f64 [loss_capacity]: loss[t] = -ELBO of step t                      */
+} BeanSviState;
+
+typedef struct BeanSviNoise {    /* all optional (NULL = draw with Philox) */
+  const void* eps_mu;            /* real [T] */
+  const void* eps_sd;            /* real [T] */
+  const void* pi;                /* real [G][R][2] */
+  void* eps_out;                 /* real [2][T]    out: the (eps_mu, eps_sd) the step used, or NULL */
+  void* pi_out;                  /* real [G][R][2] out: the pi draws the step used, or NULL         */
+} BeanSviNoise;
+
+int bean_svi_num_partials(int32_t n_guides, int32_t n_variants);
+int bean_svi_run_f32(const BeanScreen* screen, const BeanSviState* state, const BeanSviConfig* cfg,
+                     const BeanSviNoise* noise, int32_t first_step, int32_t n_steps, void* stream);
+int bean_svi_run_f64(const BeanScreen* screen, const BeanSviState* state, const BeanSviConfig* cfg,
+                     const BeanSviNoise* noise, int32_t first_step, int32_t n_steps, void* stream);
 
 #ifdef __cplusplus
 }
