@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- SVI throughput of the `bean run` hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5_genome_scale] [--impl reference]
+
+One "step" = one complete SVI step (guide sampling + ELBO forward/backward + ClippedAdam) of the
+MixtureNormal sorting model over one synthetic screen.  N=1 workload: the configuration BASELINE.json's
+target is quoted on, c5 = 1M guides x 8 replicates x 4 bins (+ barcode-matched layer, reporter edits).
+N>1 (torchrun): every rank owns its own 1M-guide shard of variants (weak scaling; the path has no
+data-path collective -- MixtureNormal has no global parameter, SURVEY section 8e -- only the ELBO
+scalar is all-reduced, once, after the timed loop).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path
+(pyro is not installable here, so the reference itself cannot run) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_variants, guides_per_variant, n_reps) ; 4 sort bins, bulk used for the reporter only
+    "c5_genome_scale": (200_000, 5, 8),
+    "c2_ldlc_variant": (690, 5, 4),
+    "tiny": (2_000, 5, 8),
+}
+BASELINE_MD_PUBLISHED = None  # BASELINE.md holds no published number for this metric -> vs_baseline null
+
+
+def algorithmic_bytes_per_guide(R, B, L, guides_per_variant, itemsize=4):
+    """HBM bytes the guide kernel must move per guide (every input read once, every output written once).
+
+    counts L*R*B + a0 L + row mask R (u8) + CSR id 4 B + reporter allele counts 2R + pi_a0 1
+    + alpha_pi (param, m, v) read+write 2*3*2 + per-guide (d_mu, d_sd) out 2 + variant params 4/guide-per-variant.
+    pi never touches HBM (sampled and consumed in registers), unlike SURVEY 8d's 15.3 B/cell estimate."""
+    w = itemsize
+    return (L * R * B * w + L * w + R + 4 + 2 * R * w + w + 12 * w + 2 * w + 4.0 * w / guides_per_variant)
+
+
+def build_data(workload, seed):
+    from crispr_bean_b200.data_class import VariantSortingReporterScreenData
+    from crispr_bean_b200.synth import make_sorting_screen
+
+    nv, gpv, nr = WORKLOADS[workload]
+    scr = make_sorting_screen(nv, gpv, n_reps=nr, seed=seed)
+    # 4 sort bins; the bulk sample only feeds the reporter editing-rate sites ("c5")
+    return VariantSortingReporterScreenData(scr, control_can_be_selected=False)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # pragma: no cover
+            self.nv = None
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def time_steps(engine, steps, phases=0):
+    """CUDA-event time of `steps` steps on the launching (current) stream, in ms."""
+    engine.cfg.phases = phases
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    engine.run(steps)
+    stop.record()
+    torch.cuda.synchronize()
+    engine.cfg.phases = 0
+    return start.elapsed_time(stop)
+
+
+def oracle_step_time(data, n_guides_sample, steps, warmup=1):
+    """Seconds per SVI step of the CPU oracle (plain-torch restatement of the reference) on a guide subset."""
+    from oracle import bean_oracle as O
+
+    sub = data[torch.arange(n_guides_sample)] if n_guides_sample < data.n_guides else data
+    ps = O.ParamStore()
+    opt = O.ClippedAdam(lr=0.01, lrd=0.1 ** (1 / 2000))
+    times = []
+    for t in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _ = O.elbo_mixture_normal(sub, ps)
+        ps.zero_grad()
+        loss.backward()
+        opt.step(ps.unconstrained)
+        float(loss.detach())  # the reference syncs the loss every step (run.py:377-380)
+        if t >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), sub
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5_genome_scale", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--cpu-sample-guides", type=int, default=50_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    nv, gpv, nr = WORKLOADS[args.workload]
+    R, B, L = nr, 4, 2
+    cells_per_step_rank = nv * gpv * R * B
+    config = {"workload": f"{args.workload}: MixtureNormal sorting, {nv * gpv} guides x {R} reps x {B} bins per GPU, "
+                          f"{nv} variants, bcmatch layer + reporter edits",
+              "model": None, "l2": "per-step inputs (0.40 GB) exceed the 126 MB L2; no flush needed",
+              "sharding": f"variants sharded, {world} shard(s) of {nv} variants (weak scaling)"}
+    config.pop("model")
+
+    # ------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        torch.set_num_threads(os.cpu_count() or 1)
+        data = build_data(args.workload, seed=101)
+        n_sample = min(args.cpu_sample_guides, data.n_guides)
+        # warm-up + timed steps on a bounded sample of the workload's guides
+        sec, sub = oracle_step_time(data, n_sample, max(args.steps, 1), warmup=max(args.warmup, 1))
+        cells = sub.n_guides * R * B
+        value = cells / sec
+        line = {
+            "impl": "reference", "metric": "guide_rep_bin_cells_per_sec", "value": value, "unit": "cells/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 mixed (as the reference)",
+            "data": "synthetic", "config": config,
+            "svi_steps_per_sec_at_full_size_extrapolated": value / cells_per_step_rank,
+            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"first {sub.n_guides} guides of the workload, {args.steps} SVI steps of the plain-torch "
+                                       "oracle port (pyro is not installable; no poutine overhead, anomaly mode off)"},
+            "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from crispr_bean_b200.svi import SviEngine
+
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    data = build_data(args.workload, seed=101 + rank)
+    total_steps = args.warmup + args.steps
+    eng = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=4 * total_steps + 64, seed=101 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- device-resident throughput: inputs already in HBM --------------------------------------
+    eng.run(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = time_steps(eng, args.steps)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    steps_per_sec = args.steps / (ms * 1e-3)
+    value = cells_per_step_rank * world * steps_per_sec
+
+    final_loss = float(eng.loss[eng.step - 1].item())
+    # --- per-kernel timing for the roofline (guide kernel alone, same launches, CUDA events) -----
+    ms_guide = time_steps(eng, args.steps, phases=1) / args.steps
+    ms_var = time_steps(eng, args.steps, phases=2) / args.steps
+    itemsize = 4 if dtype == torch.float32 else 8
+    bytes_launch = algorithmic_bytes_per_guide(R, B, L, gpv, itemsize) * nv * gpv
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = bytes_launch / (ms_guide * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "svi_guide_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": ms_guide,
+                "ms_per_launch_variant_kernel": ms_var,
+                "note": "the kernel is FP32/SFU-bound (lgamma/digamma/log1p series per cell), see DESIGN.md and profiles/"}
+
+    # --- e2e: host-resident screen -> public API -> host-resident results ------------------------
+    from crispr_bean_b200.device_pack import DeviceScreen
+
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    e2e_steps = args.steps
+    loss_host = torch.zeros(e2e_steps, dtype=torch.float64).pin_memory()
+    t0.record()
+    eng2 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=e2e_steps, seed=7 + rank)  # H2D of the whole screen
+    for t in range(e2e_steps):
+        eng2.run(1)
+        loss_host[t].copy_(eng2.loss[t], non_blocking=True)  # the step's result back on the host, every step
+    params_host = {k: v.cpu() for k, v in eng2.params().items()}
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    scr = eng2.screen
+    h2d = (scr.x.numel() + scr.a0.numel()) * itemsize + scr.row_mask.numel() + (eng2.allele_counts.numel() + eng2.pi_a0.numel()) * itemsize \
+        + eng2.guide_variant.numel() * 4 + eng2.variant_ptr.numel() * 4
+    d2h = 8 * e2e_steps + sum(v.numel() * v.element_size() for v in params_host.values())
+    e2e_value = cells_per_step_rank * world * e2e_steps / (ms_e2e * 1e-3)
+    assert torch.isfinite(loss_host).all()
+
+    if world > 1:  # the only collective of the path: the ELBO scalar, outside the timed loops
+        l = eng.loss[: eng.step].clone()
+        dist.all_reduce(l)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    line = {
+        "metric": "guide_rep_bin_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": BASELINE_MD_PUBLISHED, "dtype": args.dtype, "data": "synthetic", "config": config,
+        "svi_steps_per_sec": steps_per_sec,
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
+                "what": f"SviEngine built from HOST tensors (screen upload + re-tiling inside the timed region), {e2e_steps} steps, "
+                        "each step's loss copied to pinned host memory, final parameters copied to host"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": roofline,
+        "final_loss": final_loss,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_sample = min(args.cpu_sample_guides, data.n_guides)
+        sec, sub = oracle_step_time(data, n_sample, steps=3, warmup=1)
+        cpu_val = sub.n_guides * R * B / sec
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"first {sub.n_guides} guides of the workload, 3 timed SVI steps of the plain-torch oracle "
+                                          f"port ({sec * 1e3:.0f} ms/step); pyro itself is not installable here"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

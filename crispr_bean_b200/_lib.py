@@ -42,6 +42,7 @@ class BeanLLArgs(C.Structure):
 class BeanSviConfig(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("sd_is_sqrt", C.c_int32), ("mu_prior_normal", C.c_int32), ("apply_update", C.c_int32),
+        ("phases", C.c_int32), ("reserved_", C.c_int32),
         ("mu_prior_loc", C.c_double), ("mu_prior_scale", C.c_double),
         ("sd_prior_loc", C.c_double), ("sd_prior_scale", C.c_double),
         ("lr0", C.c_double), ("lrd", C.c_double),

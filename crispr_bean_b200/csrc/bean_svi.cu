@@ -465,8 +465,10 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
     p.step = (uint32_t)t;
     const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
     p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
-    if (mix) launch_guide<real, true>(p, st); else launch_guide<real, false>(p, st);
-    svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
+    if (cfg->phases != 2) {
+      if (mix) launch_guide<real, true>(p, st); else launch_guide<real, false>(p, st);
+    }
+    if (cfg->phases != 1) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
   }
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;

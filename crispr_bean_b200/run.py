@@ -1,0 +1,81 @@
+"""`run_inference` / `identify_model_guide` with the reference's signatures (bean/model/run.py:347-474).
+
+`run_inference(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000)` returns
+`(param_store_like, {"loss": [float per step], "params": {name: cpu tensor}})` exactly like
+bean/model/run.py:391-396, but the loop runs on the GPU with no host sync per step.
+"""
+from __future__ import annotations
+
+from functools import partial
+from logging import info
+
+import torch
+
+from . import model as sorting_model
+from ._lib import BeanError
+from .model import resolve
+from .svi import SviEngine
+
+FUSED_MODELS = ("Normal", "ControlNormal", "MixtureNormal")
+
+
+def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, device="cuda", dtype=torch.float32,
+                seed=101) -> SviEngine:
+    name, mkw = resolve(model)
+    gname, gkw = resolve(guide)
+    if name != gname:
+        raise ValueError(f"model {name} and guide {gname} do not belong together")
+    if not torch.cuda.is_available():
+        raise BeanError("run_inference needs a CUDA device: crispr_bean_b200 has no CPU fallback")
+    if name not in FUSED_MODELS or mkw.get("scale_by_accessibility"):
+        raise NotImplementedError(f"model {name}{'+Acc' if mkw.get('scale_by_accessibility') else ''} is not lowered "
+                                  "onto the fused CUDA step yet")
+    use_bcmatch = mkw.get("use_bcmatch", True)
+    if isinstance(use_bcmatch, tuple):  # reference passes the 1-tuple (not args.ignore_bcmatch,): always truthy (App. B2)
+        use_bcmatch = True
+    return SviEngine(
+        data, name, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps, initial_lr=initial_lr,
+        gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)), sd_scale=float(mkw.get("sd_scale", 0.01)),
+        mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"))
+
+
+def run_inference(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, autoguide=False, device="cuda",
+                  dtype=torch.float32, seed=101, log_every=100):
+    """Run SVI (one-particle Trace_ELBO + ClippedAdam, lr decaying by `gamma` over the run)."""
+    eng = make_engine(model, guide, data, initial_lr, gamma, num_steps, device, dtype, seed)
+    done = 0
+    while done < num_steps:
+        n = min(log_every, num_steps - done)
+        losses = eng.run(n)
+        info(f"loss {losses[0].item()} @ iter {done}")  # reference prints every 100 steps (run.py:378-379)
+        done += n
+    params = eng.params()
+    return params, {"loss": eng.losses().tolist(), "params": {k: v.detach().cpu() for k, v in params.items()}}
+
+
+def identify_model_guide(args):
+    """bean/model/run.py:399-457 for the sorting selection."""
+    if args.selection != "sorting":
+        raise NotImplementedError("survival models")
+    m = sorting_model
+    if args.library_design == "tiling":
+        return (
+            f"MultiMixtureNormal{'+Acc' if args.scale_by_acc else ''}",
+            partial(m.MultiMixtureNormalModel, scale_by_accessibility=args.scale_by_acc, use_bcmatch=(not args.ignore_bcmatch,)),
+            partial(m.MultiMixtureNormalGuide, scale_by_accessibility=args.scale_by_acc, fit_noise=True),
+        )
+    if args.uniform_edit:
+        if args.guide_activity_col is not None:
+            raise ValueError("Can't use the guide activity column while constraining uniform edit.")
+        return "Normal", partial(m.NormalModel, use_bcmatch=(not args.ignore_bcmatch)), m.NormalGuide
+    return (
+        f"{'_' if args.dont_fit_noise else ''}MixtureNormal{'+Acc' if args.scale_by_acc else ''}",
+        partial(m.MixtureNormalModel, scale_by_accessibility=args.scale_by_acc, use_bcmatch=(not args.ignore_bcmatch,)),
+        partial(m.MixtureNormalGuide, scale_by_accessibility=args.scale_by_acc, fit_noise=(not args.dont_fit_noise)),
+    )
+
+
+def identify_negctrl_model_guide(args, data_has_bcmatch):
+    """bean/model/run.py:460-474."""
+    use = (not args.ignore_bcmatch) and data_has_bcmatch
+    return partial(sorting_model.ControlNormalModel, use_bcmatch=use), partial(sorting_model.ControlNormalGuide, use_bcmatch=use)

@@ -138,6 +138,9 @@ typedef struct BeanSviConfig {
   int32_t sd_is_sqrt;       /* NormalModel feeds sqrt(sd_targets) to the CDF (model.py:92-98)        */
   int32_t mu_prior_normal;  /* 0: Laplace(0,1) (model.py:43); 1: Normal(mu_prior_loc, mu_prior_scale) */
   int32_t apply_update;     /* 1: ClippedAdam step; 0: only write gradients                          */
+  int32_t phases;           /* 0 or 3: both kernels; 1: guide kernel only; 2: variant kernel only
+                               (1 / 2 exist so a benchmark can time each kernel with CUDA events)      */
+  int32_t reserved_;
   double mu_prior_loc, mu_prior_scale;
   double sd_prior_loc, sd_prior_scale; /* LogNormal prior on sd_targets: (0, 0.01); ControlNormal (0, 1) */
   double lr0, lrd;          /* ClippedAdam: lr_t = lr0 * lrd^t, lrd = gamma^(1/num_steps) (run.py:367) */
