@@ -21,7 +21,11 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float log1p(float x) { return log1pf(x); }
   static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
-  static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  // 2-ulp division (MUFU.RCP + FMUL) for quantities whose own rounding already dominates
+  static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+  // 3-ulp log (MUFU.LG2 + FMUL): only where the value is multiplied by O(1) factors
+  static __device__ __forceinline__ float flog(float x) { return __logf(x); }
 };
 template <> struct Num<double> {
   static __device__ __forceinline__ double log(double x) { return ::log(x); }
@@ -34,6 +38,8 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double fmax(double a, double b) { return ::fmax(a, b); }
   static __device__ __forceinline__ double fmin(double a, double b) { return ::fmin(a, b); }
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+  static __device__ __forceinline__ double flog(double x) { return ::log(x); }
 };
 
 // ---- Gamma-function corrections to the Stirling main part, z > 0 ---------------------------------
@@ -48,21 +54,25 @@ template <> struct Num<double> {
 __device__ __forceinline__ void gamma_corr(float z, float& cv, float& dl) {
   float zs = z;
   if (z < 4.0f) zs = z + 4.0f;
-  const float rz = 1.0f / zs;
+  const float rz = __frcp_rn(zs);
   const float r2 = rz * rz;
   // lgamma tail: 1/(12 z) - 1/(360 z^3) + 1/(1260 z^5) - 1/(1680 z^7)
   cv = rz * (8.3333333333e-2f + r2 * (-2.7777777778e-3f + r2 * (7.9365079365e-4f + r2 * -5.9523809524e-4f)));
   // digamma tail: -1/(2z) - 1/(12 z^2) + 1/(120 z^4) - 1/(252 z^6) + 1/(240 z^8)
   dl = -0.5f * rz - r2 * (8.3333333333e-2f + r2 * (-8.3333333333e-3f + r2 * (3.9682539683e-3f + r2 * -4.1666666667e-3f)));
   if (z < 4.0f) {
-    // Gamma(z) = Gamma(z+4) / P(z), P = z (z+1) (z+2) (z+3);  psi(z) = psi(z+4) - P'(z)/P(z)
+    // Gamma(z) = Gamma(z+4) / P(z), P = z (z+1) (z+2) (z+3);  psi(z) = psi(z+4) - P'(z)/P(z).
+    //   cv(z) = cv(z+4) + (z + 1/2) ln(1 + 4/z) + ln((z+4)^3 / ((z+1)(z+2)(z+3))) - 4
+    //   dl(z) = dl(z+4) + ln(1 + 4/z) - P'/P
+    // Both logs are multiplied by factors <= 4.5, so the 3-ulp MUFU log is accurate enough here.
     const float z1 = z + 1.0f, z2 = z + 2.0f, z3 = z + 3.0f;
-    const float p01 = z * z1, p23 = z2 * z3;
-    const float P = p01 * p23;
-    const float dP = (z + z1) * p23 + p01 * (z2 + z3);
-    const float lz = logf(z), lzs = logf(zs);
-    cv += ((zs - 0.5f) * lzs - zs) - ((z - 0.5f) * lz - z) - logf(P);
-    dl += (lzs - lz) - dP / P;
+    const float p123 = z1 * z2 * z3;
+    const float iz = __frcp_rn(z), ip = __frcp_rn(p123);
+    const float ls = __logf(zs * iz);
+    const float lr = __logf(zs * zs * zs * ip);
+    cv += (z + 0.5f) * ls + lr - 4.0f;
+    // P'/P = 1/z + ((z+1)(z+2) + (z+1)(z+3) + (z+2)(z+3)) / ((z+1)(z+2)(z+3))
+    dl += ls - (iz + (z1 * z2 + z1 * z3 + z2 * z3) * ip);
   }
 }
 

@@ -148,37 +148,49 @@ __device__ __forceinline__ real beta_grad_beta_small(real x, real alpha, real be
   return isnan(result) ? real(0) : result;
 }
 
-// alpha, beta both large: Rice saddle-point expansion (torch: _beta_grad_alpha_mid)
+// alpha, beta both large: Rice saddle-point expansion (torch: _beta_grad_alpha_mid).  Same expression as
+// torch, algebraically regrouped so that it costs 2 logs, 2 rsqrt and a handful of divisions instead of
+// 3 logs, 2 pows, 4 sqrts and ~15 divisions:
+//   q = 2ab/T, s = sqrt(q);  prefactor = -x/s;  term3 = 2s/axbx;  term1_den = s T^2 axbx^2 / b;
+//   term4 = base^-1.5 = rsqrt(base)^3;  the three Stirling factors share one division.
+// It must run in double: term1 and term2*term4 are both O((x-mean)^-2) and cancel to O(1).
 template <typename real>
 __device__ __forceinline__ real beta_grad_alpha_mid(real x, real alpha, real beta) {
   const real total = alpha + beta;
-  const real mean = alpha / total;
-  const real sd = Num<real>::sqrt(alpha * beta / (total + real(1))) / total;
-  if (mean - real(0.1) * sd <= x && x <= mean + real(0.1) * sd) {
+  const real iT = real(1) / total;
+  const real mean = alpha * iT;
+  const real dx = x - mean;
+  // |x - mean| <= 0.1 std  <=>  dx^2 (T+1) T^2 <= 0.01 a b
+  if (dx * dx * (total + real(1)) * total * total <= real(0.01) * alpha * beta) {
     const real b2 = beta * beta;
     const real poly = real(47) * x * b2 * b2 +
                       alpha * ((real(43) + real(20) * (real(16) + real(27) * beta) * x) * b2 * beta +
                                alpha * (real(3) * (real(59) + real(180) * beta - real(90) * x) * b2 +
                                         alpha * ((real(453) + real(1620) * beta * (real(1) - x) - real(455) * x) * beta +
                                                  alpha * (real(8) * (real(1) - x) * (real(135) * beta - real(11))))));
-    const real pre_num = (real(1) + real(12) * alpha) * (real(1) + real(12) * beta) / (total * total);
+    const real pre_num = (real(1) + real(12) * alpha) * (real(1) + real(12) * beta) * iT * iT;
     const real pre_den = real(12960) * alpha * alpha * alpha * beta * beta * (real(1) + real(12) * total);
-    return pre_num / (real(1) - x) * poly / pre_den;
+    return pre_num * poly / ((real(1) - x) * pre_den);
   }
-  const real prefactor = -x / Num<real>::sqrt(real(2) * alpha * beta / total);
-  const real stirling = (real(1) + real(1) / (real(12) * alpha) + real(1) / (real(288) * alpha * alpha)) *
-                        (real(1) + real(1) / (real(12) * beta) + real(1) / (real(288) * beta * beta)) /
-                        (real(1) + real(1) / (real(12) * total) + real(1) / (real(288) * total * total));
-  const real term1_num = real(2) * (alpha * alpha) * (x - real(1)) + alpha * beta * (x - real(1)) - x * (beta * beta);
-  const real axbx = alpha * (x - real(1)) + beta * x;
-  const real term1_den = Num<real>::sqrt(real(2) * alpha / beta) * Num<real>::pow(total, real(1.5)) * axbx * axbx;
-  const real term1 = term1_num / term1_den;
-  const real term2 = real(0.5) * Num<real>::log(alpha / (total * x));
-  const real term3 = Num<real>::sqrt(real(8) * alpha * beta / total) / (beta * x + alpha * (x - real(1)));
-  const real term4_base = beta * Num<real>::log(beta / (total * (real(1) - x))) + alpha * Num<real>::log(alpha / (total * x));
-  const real term4 = Num<real>::pow(term4_base, real(-1.5));
-  const real term1234 = term1 + term2 * (term3 + (x < mean ? term4 : -term4));
-  return stirling * prefactor * term1234;
+  const real q = real(2) * alpha * beta * iT;
+  const real rs = real(1) / Num<real>::sqrt(q);
+  const real s = q * rs;
+  const real a2 = alpha * alpha, be2 = beta * beta, t2 = total * total;
+  // (1 + 1/12a + 1/288a^2)(1 + 1/12b + 1/288b^2) / (1 + 1/12T + 1/288T^2) with one division
+  const real stirling = (real(288) * a2 + real(24) * alpha + real(1)) * (real(288) * be2 + real(24) * beta + real(1)) * t2 /
+                        (real(288) * a2 * be2 * (real(288) * t2 + real(24) * total + real(1)));
+  const real xm1 = x - real(1);
+  const real axbx = alpha * xm1 + beta * x;
+  const real iax = real(1) / axbx;
+  const real term1 = (real(2) * a2 * xm1 + alpha * beta * xm1 - x * be2) * beta * rs * iT * iT * iax * iax;
+  const real L1 = Num<real>::log(mean / x);
+  const real L2 = Num<real>::log(beta * iT / (real(1) - x));
+  const real term3 = real(2) * s * iax;
+  const real base = beta * L2 + alpha * L1;
+  const real rb = real(1) / Num<real>::sqrt(base);
+  const real term4 = rb * rb * rb;
+  const real term1234 = term1 + real(0.5) * L1 * (term3 + (x < mean ? term4 : -term4));
+  return stirling * (-x * rs) * term1234;
 }
 
 // -(d/dalpha cdf(x; alpha, total - alpha)) / pdf / (1 - x): what torch._dirichlet_grad evaluates per element.
@@ -227,6 +239,11 @@ __device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real tota
   }
   const real approx = x * (digamma_full(total) - digamma_full(alpha)) / beta;
   return p / q * approx;
+}
+
+// out-of-line double evaluation: keeps the (register-hungry) double code out of the float kernels' bodies
+__device__ __noinline__ double dirichlet_grad_one_f64(double x, double alpha, double total) {
+  return dirichlet_grad_one<double>(x, alpha, total);
 }
 
 }  // namespace bean

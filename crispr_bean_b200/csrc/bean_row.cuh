@@ -22,11 +22,11 @@ template <typename real, int NB>
 __device__ __forceinline__ real dm_row_kl(int nb, const real (&x)[NB], const real (&a)[NB], real N, real A,
                                           real (&gb)[NB]) {
   const real U = N + A;
-  const real rU = real(1) / U;
+  const real rU = Num<real>::rcp(U);
   real cvA, dlA, cvU, dlU;
   gamma_corr(A, cvA, dlA);
   gamma_corr(U, cvU, dlU);
-  const real lUA = Num<real>::log(U / A);
+  const real lUA = Num<real>::flog(Num<real>::div(U, A));  // enters V with weight (B-1)/2 only
   const real dlAU = dlA - dlU;
   real V = real(0), sumL2 = real(0), csum = real(0);
 #pragma unroll
@@ -41,8 +41,8 @@ __device__ __forceinline__ real dm_row_kl(int nb, const real (&x)[NB], const rea
       const real e = fma(a[b], N, -p);
       const real num = fma(x[b], A, -p) - e;
       const real t = num * rU;
-      const real L2 = Num<real>::log1p(t / a[b]);
-      const real L1 = x[b] > real(0) ? Num<real>::log1p(-t / x[b]) : real(0);
+      const real L2 = Num<real>::log1p(Num<real>::div(t, a[b]));
+      const real L1 = x[b] > real(0) ? Num<real>::log1p(Num<real>::div(-t, x[b])) : real(0);
       V += x[b] * L1 + a[b] * L2;
       sumL2 += L2;
       csum += cvu - cva;

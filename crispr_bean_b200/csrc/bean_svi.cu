@@ -21,6 +21,7 @@
 namespace bean {
 
 constexpr int SVI_THREADS = 128;
+constexpr int SVI_MIN_CTAS = 4;  // <= 128 registers: 16 warps/SM resident
 constexpr int VAR_THREADS = 256;
 constexpr int VAR_LANES = 8;  // lanes cooperating on one variant
 constexpr int VAR_PER_CTA = VAR_THREADS / VAR_LANES;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, re
 }
 
 template <typename real, int NB, bool MIXTURE>
-__global__ void __launch_bounds__(SVI_THREADS) svi_guide_kernel(const SviParams<real> p) {
+__global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
   __shared__ double red[32];
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = p.B;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(SVI_THREADS) svi_guide_kernel(const SviParams<
         }
         if (!(rmask && N > p.mask_thres)) continue;  // poutine.mask: the row contributes nothing
         const real a0 = p.a0[(size_t)l * p.G + g];
-        const real inv = real(1) / (S + eps);
+        const real inv = Num<real>::rcp(S + eps);
         real Asum = real(0);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -244,8 +245,8 @@ __global__ void __launch_bounds__(SVI_THREADS) svi_guide_kernel(const SviParams<
         // the saddle-point branch cancels badly in float
         const double tot = (double)cg[0] + (double)cg[1];
         const double gbar = (double)pi0 * (double)go0 + (double)pi1 * (double)go1;
-        dcg[0] += real(dirichlet_grad_one<double>((double)pi0, (double)cg[0], tot) * ((double)go0 - gbar));
-        dcg[1] += real(dirichlet_grad_one<double>((double)pi1, (double)cg[1], tot) * ((double)go1 - gbar));
+        dcg[0] += real(dirichlet_grad_one_f64((double)pi0, (double)cg[0], tot) * ((double)go0 - gbar));
+        dcg[1] += real(dirichlet_grad_one_f64((double)pi1, (double)cg[1], tot) * ((double)go1 - gbar));
       } else {
 #pragma unroll
         for (int b = 0; b < NB; ++b) dP[b] += de[b];
