@@ -21,7 +21,7 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float log1p(float x) { return log1pf(x); }
   static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
-  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }  // MUFU.RCP, ~1 ulp
   // 2-ulp division (MUFU.RCP + FMUL) for quantities whose own rounding already dominates
   static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
   // 3-ulp log (MUFU.LG2 + FMUL): only where the value is multiplied by O(1) factors
@@ -54,7 +54,7 @@ template <> struct Num<double> {
 __device__ __forceinline__ void gamma_corr(float z, float& cv, float& dl) {
   float zs = z;
   if (z < 4.0f) zs = z + 4.0f;
-  const float rz = __frcp_rn(zs);
+  const float rz = __fdividef(1.0f, zs);
   const float r2 = rz * rz;
   // lgamma tail: 1/(12 z) - 1/(360 z^3) + 1/(1260 z^5) - 1/(1680 z^7)
   cv = rz * (8.3333333333e-2f + r2 * (-2.7777777778e-3f + r2 * (7.9365079365e-4f + r2 * -5.9523809524e-4f)));
@@ -67,7 +67,7 @@ __device__ __forceinline__ void gamma_corr(float z, float& cv, float& dl) {
     // Both logs are multiplied by factors <= 4.5, so the 3-ulp MUFU log is accurate enough here.
     const float z1 = z + 1.0f, z2 = z + 2.0f, z3 = z + 3.0f;
     const float p123 = z1 * z2 * z3;
-    const float iz = __frcp_rn(z), ip = __frcp_rn(p123);
+    const float iz = __fdividef(1.0f, z), ip = __fdividef(1.0f, p123);
     const float ls = __logf(zs * iz);
     const float lr = __logf(zs * zs * zs * ip);
     cv += (z + 0.5f) * ls + lr - 4.0f;

@@ -36,9 +36,9 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 
 // two standard normals from two 32-bit words (Box-Muller)
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  const float r = sqrtf(-2.0f * logf(u01(a)));
+  const float r = sqrtf(-2.0f * __logf(u01(a)));
   float s, c;
-  sincospif(2.0f * u01(b), &s, &c);
+  __sincosf(6.283185307179586f * (u01(b) - 0.5f), &s, &c);  // angle in (-pi, pi): MUFU.SIN/COS range
   n0 = r * c;
   n1 = r * s;
 }
@@ -51,23 +51,35 @@ __device__ __forceinline__ void variant_noise(uint64_t seed, uint32_t v, uint32_
   box_muller(w.x, w.y, e0, e1);
 }
 
-// One Marsaglia-Tsang proposal for shape alpha >= 1; returns true and the draw when accepted.
+// Marsaglia-Tsang constants of one shape parameter (boosted to >= 1); they depend on the guide only, so
+// they are computed once per guide, not once per replicate.
 template <typename real>
-__device__ __forceinline__ bool gamma_mt_try(real alpha, float nrm, float uni, real& out) {
-  const real d = alpha - real(1.0 / 3.0);
-  const real c = real(1) / Num<real>::sqrt(real(9) * d);
-  const real x = real(nrm);
-  const real y = real(1) + c * x;
-  if (y <= real(0)) return false;
-  const real v = y * y * y;
-  const real u = real(uni);
-  const real xx = x * x;
-  if (u < real(1) - real(0.0331) * xx * xx || Num<real>::log(u) < real(0.5) * xx + d * (real(1) - v + Num<real>::log(v))) {
-    out = d * v;
-    return true;
+struct GammaMT {
+  real d, c, inv_alpha;  // d = a - 1/3, c = 1/sqrt(9 d); inv_alpha = 1/alpha if alpha < 1 (boost) else 0
+  __device__ __forceinline__ void init(real alpha) {
+    inv_alpha = real(0);
+    if (alpha < real(1)) {
+      inv_alpha = real(1) / alpha;
+      alpha += real(1);
+    }
+    d = alpha - real(1.0 / 3.0);
+    c = real(1) / Num<real>::sqrt(real(9) * d);
   }
-  return false;
-}
+  // one proposal; returns true and the draw when accepted
+  __device__ __forceinline__ bool attempt(float nrm, float uni, real& out) const {
+    const real x = real(nrm);
+    const real y = real(1) + c * x;
+    if (y <= real(0)) return false;
+    const real v = y * y * y;
+    const real xx = x * x;
+    if (real(uni) < real(1) - real(0.0331) * xx * xx ||
+        Num<real>::flog(real(uni)) < real(0.5) * xx + d * (real(1) - v + Num<real>::flog(v))) {
+      out = d * v;
+      return true;
+    }
+    return false;
+  }
+};
 
 template <typename real> struct Lim;
 template <> struct Lim<float> {
@@ -83,14 +95,14 @@ template <> struct Lim<double> {
 
 // pi ~ Dirichlet(c0, c1) for guide g, replicate r at `step` (a Beta draw as two gammas).
 template <typename real>
-__device__ __forceinline__ void sample_pi2(uint64_t seed, uint32_t g, uint32_t r, uint32_t step, real c0, real c1,
-                                           real& pi0, real& pi1) {
+__device__ __forceinline__ void sample_pi2(uint64_t seed, uint32_t g, uint32_t r, uint32_t step, const GammaMT<real>& m0,
+                                           const GammaMT<real>& m1, real& pi0, real& pi1) {
   const uint2 key = seed_key(seed);
-  real s0 = real(1), s1 = real(1), a0 = c0, a1 = c1;
-  if (c0 < real(1) || c1 < real(1)) {  // boost: Gamma(a) = Gamma(a + 1) * U^(1/a)
+  real s0 = real(1), s1 = real(1);
+  if (m0.inv_alpha != real(0) || m1.inv_alpha != real(0)) {  // boost: Gamma(a) = Gamma(a + 1) * U^(1/a)
     const uint4 w = philox4x32_10(make_uint4(g, r, step, STREAM_BOOST), key);
-    if (c0 < real(1)) { s0 = Num<real>::pow(real(1) - real(u01(w.x)), real(1) / c0); a0 = c0 + real(1); }
-    if (c1 < real(1)) { s1 = Num<real>::pow(real(1) - real(u01(w.y)), real(1) / c1); a1 = c1 + real(1); }
+    if (m0.inv_alpha != real(0)) s0 = Num<real>::pow(real(1) - real(u01(w.x)), m0.inv_alpha);
+    if (m1.inv_alpha != real(0)) s1 = Num<real>::pow(real(1) - real(u01(w.y)), m1.inv_alpha);
   }
   real g0 = real(0), g1 = real(0);
   bool ok0 = false, ok1 = false;
@@ -98,8 +110,8 @@ __device__ __forceinline__ void sample_pi2(uint64_t seed, uint32_t g, uint32_t r
     const uint4 w = philox4x32_10(make_uint4(g, r, step, STREAM_PI + k), key);
     float n0, n1;
     box_muller(w.x, w.y, n0, n1);
-    if (!ok0) ok0 = gamma_mt_try(a0, n0, 1.0f - u01(w.z), g0);
-    if (!ok1) ok1 = gamma_mt_try(a1, n1, 1.0f - u01(w.w), g1);
+    if (!ok0) ok0 = m0.attempt(n0, 1.0f - u01(w.z), g0);
+    if (!ok1) ok1 = m1.attempt(n1, 1.0f - u01(w.w), g1);
   }
   g0 = Num<real>::fmax(g0 * s0, Lim<real>::tiny());
   g1 = Num<real>::fmax(g1 * s1, Lim<real>::tiny());

@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         lg_cg = lgs - lg0 - lg1;
       }
     }
+    GammaMT<real> mt0, mt1;
+    if (MIXTURE && !p.pi_in) {
+      mt0.init(cg[0]);
+      mt1.init(cg[1]);
+    }
     real elbo_g = real(0);
     for (int r = 0; r < R; ++r) {
       const bool rmask = p.row_mask[(size_t)g * R + r] != 0;
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
           pi0 = p.pi_in[((size_t)g * R + r) * 2];
           pi1 = p.pi_in[((size_t)g * R + r) * 2 + 1];
         } else {
-          sample_pi2(p.seed, (uint32_t)g, (uint32_t)r, p.step, cg[0], cg[1], pi0, pi1);
+          sample_pi2(p.seed, (uint32_t)g, (uint32_t)r, p.step, mt0, mt1, pi0, pi1);
         }
         if (p.pi_out) {
           p.pi_out[((size_t)g * R + r) * 2] = pi0;
@@ -216,29 +221,30 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
           dP[b] += de[b] * pi1;
         }
         const real lp0 = Num<real>::log(pi0), lp1 = Num<real>::log(pi1);
+        const real ip0 = Num<real>::rcp(pi0), ip1 = Num<real>::rcp(pi1);
         // guide site: -log Dirichlet(pi; cg), unmasked (model.py:837-847)
         elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
-        go0 -= (cg[0] - real(1)) / pi0;
-        go1 -= (cg[1] - real(1)) / pi1;
+        go0 -= (cg[0] - real(1)) * ip0;
+        go1 -= (cg[1] - real(1)) * ip1;
         dcg[0] -= dg_cg[2] - dg_cg[0] + lp0;
         dcg[1] -= dg_cg[2] - dg_cg[1] + lp1;
         if (rmask) {
           // model sites under poutine.mask(repguide_mask): Dirichlet prior on pi and Multinomial reporter
           // counts (model.py:454-474); torch Multinomial normalises probs and clamps them to [eps, 1-eps]
           elbo_g += lg_cm + (cm[0] - real(1)) * lp0 + (cm[1] - real(1)) * lp1;
-          go0 += (cm[0] - real(1)) / pi0;
-          go1 += (cm[1] - real(1)) / pi1;
+          go0 += (cm[0] - real(1)) * ip0;
+          go1 += (cm[1] - real(1)) * ip1;
           dcm[0] += dg_cm[2] - dg_cm[0] + lp0;
           dcm[1] += dg_cm[2] - dg_cm[1] + lp1;
           const real x0 = p.allele_counts[((size_t)g * R + r) * 2], x1 = p.allele_counts[((size_t)g * R + r) * 2 + 1];
-          const real Sp = pi0 + pi1, pn0 = pi0 / Sp, pn1 = pi1 / Sp;
+          const real Sp = pi0 + pi1, iSp = Num<real>::rcp(Sp), pn0 = pi0 * iSp, pn1 = pi1 * iSp;
           const real lo = Lim<real>::eps(), hi = real(1) - Lim<real>::eps();
           const real c0 = Num<real>::fmin(Num<real>::fmax(pn0, lo), hi), c1 = Num<real>::fmin(Num<real>::fmax(pn1, lo), hi);
           elbo_g += x0 * Num<real>::log(c0) + x1 * Num<real>::log(c1);
-          const real h0 = (pn0 >= lo && pn0 <= hi) ? x0 / c0 : real(0), h1 = (pn1 >= lo && pn1 <= hi) ? x1 / c1 : real(0);
+          const real h0 = (pn0 >= lo && pn0 <= hi) ? Num<real>::div(x0, c0) : real(0), h1 = (pn1 >= lo && pn1 <= hi) ? Num<real>::div(x1, c1) : real(0);
           const real hbar = h0 * pn0 + h1 * pn1;
-          go0 += (h0 - hbar) / Sp;
-          go1 += (h1 - hbar) / Sp;
+          go0 += (h0 - hbar) * iSp;
+          go1 += (h1 - hbar) * iSp;
         }
         // pathwise derivative of pi w.r.t. the guide concentration (torch _Dirichlet_backward)
         // evaluated in double even on the float path, as torch's CPU kernel does (accscalar_t = double):
