@@ -189,7 +189,9 @@ def main():
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     data = build_data(args.workload, seed=101 + rank)
     total_steps = args.warmup + args.steps
-    eng = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=4 * total_steps + 64, seed=101 + rank)
+    G_rank = nv * gpv
+    eng = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=4 * total_steps + 64, seed=101,
+                    guide_offset=rank * G_rank, variant_offset=rank * nv)
 
     def barrier():
         if world > 1:
@@ -214,8 +216,8 @@ def main():
 
     final_loss = float(eng.loss[eng.step - 1].item())
     # --- per-kernel timing for the roofline (guide kernel alone, same launches, CUDA events) -----
-    ms_guide = time_steps(eng, args.steps, phases=1) / args.steps
     ms_var = time_steps(eng, args.steps, phases=2) / args.steps
+    ms_guide = ms / args.steps - ms_var  # the guide kernel's share of the timed steps themselves
     itemsize = 4 if dtype == torch.float32 else 8
     bytes_launch = algorithmic_bytes_per_guide(R, B, L, gpv, itemsize) * nv * gpv
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -239,7 +241,8 @@ def main():
     e2e_steps = args.steps
     loss_host = torch.zeros(e2e_steps, dtype=torch.float64).pin_memory()
     t0.record()
-    eng2 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=e2e_steps, seed=7 + rank)  # H2D of the whole screen
+    eng2 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=e2e_steps, seed=7,  # H2D of the whole screen
+                     guide_offset=rank * G_rank, variant_offset=rank * nv)
     for t in range(e2e_steps):
         eng2.run(1)
         loss_host[t].copy_(eng2.loss[t], non_blocking=True)  # the step's result back on the host, every step

@@ -30,7 +30,7 @@ template <typename real>
 struct SviParams {
   int G, R, B, L, T;
   int mixture, sd_is_sqrt, mu_prior_normal, apply_update;
-  uint32_t step;
+  uint32_t step, guide_offset, variant_offset;
   uint64_t seed;
   real mask_thres;
   // screen
@@ -93,7 +93,7 @@ __device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, re
     eps_sd = p.eps_sd[v];
   } else {
     float e0, e1;
-    variant_noise(p.seed, (uint32_t)v, p.step, e0, e1);
+    variant_noise(p.seed, (uint32_t)v + p.variant_offset, p.step, e0, e1);
     eps_mu = real(e0);
     eps_sd = real(e1);
   }
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
           pi0 = p.pi_in[((size_t)g * R + r) * 2];
           pi1 = p.pi_in[((size_t)g * R + r) * 2 + 1];
         } else {
-          sample_pi2(p.seed, (uint32_t)g, (uint32_t)r, p.step, mt0, mt1, pi0, pi1);
+          sample_pi2(p.seed, (uint32_t)g + p.guide_offset, (uint32_t)r, p.step, mt0, mt1, pi0, pi1);
         }
         if (p.pi_out) {
           p.pi_out[((size_t)g * R + r) * 2] = pi0;
@@ -425,6 +425,8 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.G = s->n_guides; p.R = s->n_reps; p.B = s->n_bins; p.L = s->n_layers; p.T = state->n_variants;
   p.mixture = mix; p.sd_is_sqrt = cfg->sd_is_sqrt; p.mu_prior_normal = cfg->mu_prior_normal; p.apply_update = cfg->apply_update;
   p.seed = cfg->seed;
+  p.guide_offset = cfg->guide_offset;
+  p.variant_offset = cfg->variant_offset;
   p.mask_thres = real(s->mask_thres);
   p.x = static_cast<const real*>(s->x);
   p.a0 = static_cast<const real*>(s->a0);

@@ -29,7 +29,8 @@ class SviEngine:
     def __init__(self, data, model: str = "MixtureNormal", device="cuda", dtype=torch.float32,
                  use_bcmatch: bool = True, num_steps: int = 2000, initial_lr: float = 0.01, gamma: float = 0.1,
                  seed: int = 101, alpha_prior: float = 1.0, sd_scale: float = 0.01, mask_thres: int = 10,
-                 prior_params: Optional[dict] = None, screen: Optional[DeviceScreen] = None):
+                 prior_params: Optional[dict] = None, screen: Optional[DeviceScreen] = None,
+                 guide_offset: int = 0, variant_offset: int = 0):
         if model not in ("Normal", "ControlNormal", "MixtureNormal"):
             raise ValueError(f"SviEngine does not implement model {model!r}")
         self.lib = _lib.lib()
@@ -90,6 +91,7 @@ class SviEngine:
         c.lr0, c.lrd = float(initial_lr), float(gamma) ** (1.0 / max(self.num_steps, 1))
         c.beta1, c.beta2, c.adam_eps, c.clip = 0.9, 0.999, 1e-8, 10.0
         c.ll_const, c.seed = ll_const, int(seed)
+        c.guide_offset, c.variant_offset = int(guide_offset), int(variant_offset)
         self.cfg = c
 
         s = _lib.BeanSviState()

@@ -147,6 +147,8 @@ typedef struct BeanSviConfig {
   double beta1, beta2, adam_eps, clip;
   double ll_const;          /* data-only part of the ELBO (sum of masked lgamma(1+N) - sum lgamma(1+x)) */
   uint64_t seed;
+  uint32_t guide_offset;    /* global index of this shard's first guide / variant: the Philox counters   */
+  uint32_t variant_offset;  /* use GLOBAL ids, so a variant-sharded run draws exactly the unsharded noise */
 } BeanSviConfig;
 
 typedef struct BeanSviState {
