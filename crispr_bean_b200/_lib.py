@@ -42,7 +42,7 @@ class BeanLLArgs(C.Structure):
 class BeanSviConfig(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("sd_is_sqrt", C.c_int32), ("mu_prior_normal", C.c_int32), ("apply_update", C.c_int32),
-        ("phases", C.c_int32), ("reserved_", C.c_int32),
+        ("phases", C.c_int32), ("fit_noise", C.c_int32),
         ("mu_prior_loc", C.c_double), ("mu_prior_scale", C.c_double),
         ("sd_prior_loc", C.c_double), ("sd_prior_scale", C.c_double),
         ("lr0", C.c_double), ("lrd", C.c_double),
@@ -61,11 +61,13 @@ class BeanSviState(C.Structure):
         ("alpha_u", C.c_void_p), ("alpha_m", C.c_void_p), ("alpha_v", C.c_void_p),
         ("d_guide", C.c_void_p), ("var_grad", C.c_void_p), ("alpha_grad", C.c_void_p),
         ("partial", C.c_void_p), ("counter", C.c_void_p), ("loss", C.c_void_p),
+        ("acc_k", C.c_void_p), ("noise_u", C.c_void_p), ("noise_m", C.c_void_p), ("noise_v", C.c_void_p),
+        ("noise_grad", C.c_void_p),
     ]
 
 
 class BeanSviNoise(C.Structure):
-    _fields_ = [("eps_mu", C.c_void_p), ("eps_sd", C.c_void_p), ("pi", C.c_void_p),
+    _fields_ = [("eps_mu", C.c_void_p), ("eps_sd", C.c_void_p), ("pi", C.c_void_p), ("eps_noise", C.c_void_p),
                 ("eps_out", C.c_void_p), ("pi_out", C.c_void_p)]
 
 

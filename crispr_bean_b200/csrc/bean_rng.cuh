@@ -43,12 +43,20 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   n1 = r * s;
 }
 
-enum : uint32_t { STREAM_VARIANT = 0, STREAM_BOOST = 8, STREAM_PI = 16 };
+enum : uint32_t { STREAM_VARIANT = 0, STREAM_NOISE = 4, STREAM_BOOST = 8, STREAM_PI = 16 };
 
 // (eps_mu, eps_sd) of variant v at `step`
 __device__ __forceinline__ void variant_noise(uint64_t seed, uint32_t v, uint32_t step, float& e0, float& e1) {
   const uint4 w = philox4x32_10(make_uint4(v, 0u, step, STREAM_VARIANT), seed_key(seed));
   box_muller(w.x, w.y, e0, e1);
+}
+
+// standard normal behind logit_pi_noise of guide g at `step`
+__device__ __forceinline__ float guide_noise(uint64_t seed, uint32_t g, uint32_t step) {
+  const uint4 w = philox4x32_10(make_uint4(g, 0u, step, STREAM_NOISE), seed_key(seed));
+  float e0, e1;
+  box_muller(w.x, w.y, e0, e1);
+  return e0;
 }
 
 // Marsaglia-Tsang constants of one shape parameter (boosted to >= 1); they depend on the guide only, so

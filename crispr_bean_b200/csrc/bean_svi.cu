@@ -29,7 +29,7 @@ constexpr int VAR_PER_CTA = VAR_THREADS / VAR_LANES;
 template <typename real>
 struct SviParams {
   int G, R, B, L, T;
-  int mixture, sd_is_sqrt, mu_prior_normal, apply_update;
+  int mixture, sd_is_sqrt, mu_prior_normal, apply_update, fit_noise;
   uint32_t step, guide_offset, variant_offset;
   uint64_t seed;
   real mask_thres;
@@ -48,6 +48,11 @@ struct SviParams {
   real* alpha_u;
   real* alpha_m;
   real* alpha_v;
+  const real* acc_k;
+  real* noise_u;
+  real* noise_m;
+  real* noise_v;
+  real* noise_grad;
   // scratch / outputs
   real* d_guide;
   real* var_grad;
@@ -60,6 +65,7 @@ struct SviParams {
   const real* eps_mu;
   const real* eps_sd;
   const real* pi_in;
+  const real* eps_noise;
   real* eps_out;
   real* pi_out;
   // priors / optimiser scalars of this step
@@ -148,6 +154,19 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         lg_cg = lgs - lg0 - lg1;
       }
     }
+    // --scale-by-acc: per-guide logit-space noise (utils.py:133-178)
+    const bool acc = MIXTURE && p.acc_k != nullptr;
+    const real PI_NOISE_SD = real(0.655);
+    real kacc = real(1), n_eps = real(0), n_loc = real(0), n_scale = PI_NOISE_SD, n_val = real(0), dnoise = real(0);
+    if (acc) {
+      kacc = p.acc_k[g];
+      n_eps = p.eps_noise ? p.eps_noise[g] : real(guide_noise(p.seed, (uint32_t)g + p.guide_offset, p.step));
+      if (p.fit_noise) {
+        n_loc = p.noise_u[g];
+        n_scale = Num<real>::exp(p.noise_u[(size_t)p.G + g]);
+      }
+      n_val = n_loc + n_scale * n_eps;
+    }
     GammaMT<real> mt0, mt1;
     if (MIXTURE && !p.pi_in) {
       mt0.init(cg[0]);
@@ -169,10 +188,26 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
           p.pi_out[((size_t)g * R + r) * 2 + 1] = pi1;
         }
       }
+      // allele weights seen by the likelihood: pi itself, or its accessibility-scaled, noised version
+      real q0 = pi0, q1 = pi1, dq1_dpi1 = real(1), dq1_dnoise = real(0);
+      if (acc) {
+        const real lo3 = real(1e-3), hi3 = real(1) - real(1e-3);
+        const real scaled = pi1 * kacc;                       // _scale_edited_pi
+        const real den = Num<real>::fmax((real(1) - scaled) + scaled, real(1));
+        const real s1 = scaled / den;
+        const real c1 = Num<real>::fmin(Num<real>::fmax(s1, lo3), hi3);
+        const real logit = Num<real>::log(c1 / (real(1) - c1)) + n_val;
+        const real ex = Num<real>::exp(logit);
+        const real praw = ex / (real(1) + ex);
+        q1 = Num<real>::fmin(Num<real>::fmax(praw, lo3), hi3);
+        q0 = real(1) - q1;
+        dq1_dnoise = (praw >= lo3 && praw <= hi3) ? praw * (real(1) - praw) : real(0);
+        dq1_dpi1 = (s1 >= lo3 && s1 <= hi3) ? dq1_dnoise * kacc / (den * c1 * (real(1) - c1)) : real(0);
+      }
       real e[NB], de[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        e[b] = MIXTURE ? pi0 * p.p_wt[b] + pi1 * P1[b] : P1[b];  // model.py:495-499
+        e[b] = MIXTURE ? q0 * p.p_wt[b] + q1 * P1[b] : P1[b];  // model.py:495-499
         de[b] = real(0);
       }
       for (int l = 0; l < p.L; ++l) {
@@ -218,7 +253,13 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         for (int b = 0; b < NB; ++b) {
           go0 += de[b] * p.p_wt[b];
           go1 += de[b] * P1[b];
-          dP[b] += de[b] * pi1;
+          dP[b] += de[b] * q1;
+        }
+        if (acc) {  // chain through q1(pi1, noise), q0 = 1 - q1; pi0 does not reach the likelihood
+          const real gq = go1 - go0;
+          dnoise += gq * dq1_dnoise;
+          go1 = gq * dq1_dpi1;
+          go0 = real(0);
         }
         const real lp0 = Num<real>::log(pi0), lp1 = Num<real>::log(pi1);
         const real ip0 = Num<real>::rcp(pi0), ip1 = Num<real>::rcp(pi1);
@@ -289,6 +330,28 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         p.alpha_u[2 * (size_t)g] = th0; p.alpha_u[2 * (size_t)g + 1] = th1;
         p.alpha_m[2 * (size_t)g] = m0;  p.alpha_m[2 * (size_t)g + 1] = m1;
         p.alpha_v[2 * (size_t)g] = v0;  p.alpha_v[2 * (size_t)g + 1] = v1;
+      }
+    }
+    if (acc) {
+      // logit_pi_noise site: model Normal(0, 0.655); guide Normal(noise_loc, noise_scale) or the prior itself
+      if (p.fit_noise) {
+        const real z0 = n_val / PI_NOISE_SD;
+        elbo_g += (-Num<real>::log(PI_NOISE_SD) - real(0.5) * z0 * z0) - (-Num<real>::log(n_scale) - real(0.5) * n_eps * n_eps);
+        const real dE = dnoise - n_val / (PI_NOISE_SD * PI_NOISE_SD);
+        const real gl = -dE, gs = -(dE * n_eps * n_scale + real(1));
+        if (p.noise_grad) {
+          p.noise_grad[g] = gl;
+          p.noise_grad[(size_t)p.G + g] = gs;
+        }
+        if (p.apply_update) {
+          real th = p.noise_u[g], m = p.noise_m[g], v = p.noise_v[g];
+          clipped_adam(p, gl, th, m, v);
+          p.noise_u[g] = th; p.noise_m[g] = m; p.noise_v[g] = v;
+          const size_t j = (size_t)p.G + g;
+          th = p.noise_u[j]; m = p.noise_m[j]; v = p.noise_v[j];
+          clipped_adam(p, gs, th, m, v);
+          p.noise_u[j] = th; p.noise_m[j] = m; p.noise_v[j] = v;
+        }
       }
     }
     elbo = (double)elbo_g;
@@ -415,6 +478,8 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
     BEAN_REQUIRE(state->allele_counts && state->pi_a0, BEAN_EINVAL, "MixtureNormal needs allele_counts / pi_a0");
     BEAN_REQUIRE(state->alpha_u && state->alpha_m && state->alpha_v, BEAN_EINVAL, "MixtureNormal needs alpha_u / alpha_m / alpha_v");
   }
+  if (mix && state->acc_k && cfg->fit_noise)
+    BEAN_REQUIRE(state->noise_u && state->noise_m && state->noise_v, BEAN_EINVAL, "fit_noise needs noise_u / noise_m / noise_v");
   BEAN_REQUIRE(first_step >= 0 && n_steps >= 0, BEAN_EINVAL, "first_step / n_steps must be >= 0");
   BEAN_REQUIRE(first_step + n_steps <= state->loss_capacity, BEAN_EINVAL, "loss buffer too small: %d + %d > %d", first_step,
                n_steps, state->loss_capacity);
@@ -441,6 +506,12 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.alpha_u = static_cast<real*>(state->alpha_u);
   p.alpha_m = static_cast<real*>(state->alpha_m);
   p.alpha_v = static_cast<real*>(state->alpha_v);
+  p.acc_k = mix ? static_cast<const real*>(state->acc_k) : nullptr;
+  p.noise_u = static_cast<real*>(state->noise_u);
+  p.noise_m = static_cast<real*>(state->noise_m);
+  p.noise_v = static_cast<real*>(state->noise_v);
+  p.noise_grad = static_cast<real*>(state->noise_grad);
+  p.fit_noise = cfg->fit_noise;
   p.d_guide = static_cast<real*>(state->d_guide);
   p.var_grad = static_cast<real*>(state->var_grad);
   p.alpha_grad = static_cast<real*>(state->alpha_grad);
@@ -452,6 +523,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.eps_mu = noise ? static_cast<const real*>(noise->eps_mu) : nullptr;
   p.eps_sd = noise ? static_cast<const real*>(noise->eps_sd) : nullptr;
   p.pi_in = noise ? static_cast<const real*>(noise->pi) : nullptr;
+  p.eps_noise = noise ? static_cast<const real*>(noise->eps_noise) : nullptr;
   p.eps_out = noise ? static_cast<real*>(noise->eps_out) : nullptr;
   p.pi_out = noise ? static_cast<real*>(noise->pi_out) : nullptr;
   p.mu_prior_loc = real(cfg->mu_prior_loc); p.mu_prior_scale = real(cfg->mu_prior_scale);

@@ -27,16 +27,18 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
         raise ValueError(f"model {name} and guide {gname} do not belong together")
     if not torch.cuda.is_available():
         raise BeanError("run_inference needs a CUDA device: crispr_bean_b200 has no CPU fallback")
-    if name not in FUSED_MODELS or mkw.get("scale_by_accessibility"):
-        raise NotImplementedError(f"model {name}{'+Acc' if mkw.get('scale_by_accessibility') else ''} is not lowered "
-                                  "onto the fused CUDA step yet")
+    if name not in FUSED_MODELS:
+        raise NotImplementedError(f"model {name} is not lowered onto the fused CUDA step yet")
     use_bcmatch = mkw.get("use_bcmatch", True)
     if isinstance(use_bcmatch, tuple):  # reference passes the 1-tuple (not args.ignore_bcmatch,): always truthy (App. B2)
         use_bcmatch = True
     return SviEngine(
         data, name, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps, initial_lr=initial_lr,
         gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)), sd_scale=float(mkw.get("sd_scale", 0.01)),
-        mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"))
+        mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"),
+        scale_by_accessibility=bool(mkw.get("scale_by_accessibility", False)),
+        # only the GUIDE's fit_noise matters: the model is never given it
+        fit_noise=bool(gkw.get("fit_noise", False)))
 
 
 def run_inference(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, autoguide=False, device="cuda",

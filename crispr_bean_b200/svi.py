@@ -7,6 +7,7 @@ bean/model/run.py:377-380).
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional
 
 import torch
@@ -30,7 +31,8 @@ class SviEngine:
                  use_bcmatch: bool = True, num_steps: int = 2000, initial_lr: float = 0.01, gamma: float = 0.1,
                  seed: int = 101, alpha_prior: float = 1.0, sd_scale: float = 0.01, mask_thres: int = 10,
                  prior_params: Optional[dict] = None, screen: Optional[DeviceScreen] = None,
-                 guide_offset: int = 0, variant_offset: int = 0):
+                 guide_offset: int = 0, variant_offset: int = 0, scale_by_accessibility: bool = False,
+                 fit_noise: bool = False):
         if model not in ("Normal", "ControlNormal", "MixtureNormal"):
             raise ValueError(f"SviEngine does not implement model {model!r}")
         self.lib = _lib.lib()
@@ -68,6 +70,17 @@ class SviEngine:
             a64 = self.allele_counts.double()
             mconst = torch.lgamma(a64.sum(-1) + 1) - torch.lgamma(a64 + 1).sum(-1)  # (G, R)
             ll_const += float((mconst * (self.screen.row_mask != 0)).sum())
+        self.acc = bool(scale_by_accessibility) and self.mixture
+        self.fit_noise = bool(fit_noise) and self.acc
+        if self.acc:
+            if getattr(data, "guide_accessibility", None) is None:
+                raise ValueError("scale_by_accessibility needs data.guide_accessibility (accessibility_col)")
+            # _scale_edited_pi: pi * exp(b) * accessibility^a with a = 0.2513, b = -1.9458 (utils.py:79-103)
+            acc = torch.as_tensor(data.guide_accessibility).double()
+            self.acc_k = (math.exp(-1.9458) * acc.pow(0.2513)).to(**kw).contiguous()
+            self.noise_u = torch.stack([torch.zeros(G), torch.full((G,), 0.655).log()]).to(**kw).contiguous()
+            self.noise_m, self.noise_v = torch.zeros((2, G), **kw), torch.zeros((2, G), **kw)
+            self.noise_grad = torch.zeros((2, G), **kw)
         self.partial = torch.zeros((self.lib.bean_svi_num_partials(G, T),), dtype=torch.float64, device=dev)
         self.counter = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.loss = torch.zeros((max(self.num_steps, 1),), dtype=torch.float64, device=dev)
@@ -77,6 +90,7 @@ class SviEngine:
         c.model = _lib.MODEL_MIXTURE_NORMAL if self.mixture else _lib.MODEL_NORMAL
         c.sd_is_sqrt = 1 if model == "Normal" else 0
         c.apply_update = 1
+        c.fit_noise = 1 if self.fit_noise else 0
         c.mu_prior_normal, c.mu_prior_loc, c.mu_prior_scale = 0, 0.0, 1.0
         c.sd_prior_loc, c.sd_prior_scale = 0.0, (1.0 if model == "ControlNormal" else float(sd_scale))
         if prior_params:
@@ -104,6 +118,10 @@ class SviEngine:
         s.var_params, s.var_m, s.var_v = self.var_params.data_ptr(), self.var_m.data_ptr(), self.var_v.data_ptr()
         s.d_guide, s.var_grad = self.d_guide.data_ptr(), self.var_grad.data_ptr()
         s.partial, s.counter, s.loss = self.partial.data_ptr(), self.counter.data_ptr(), self.loss.data_ptr()
+        if self.acc:
+            s.acc_k = self.acc_k.data_ptr()
+            s.noise_u, s.noise_m, s.noise_v = self.noise_u.data_ptr(), self.noise_m.data_ptr(), self.noise_v.data_ptr()
+            s.noise_grad = self.noise_grad.data_ptr()
         self.state = s
 
     # ---------------------------------------------------------------------------------------------
@@ -124,6 +142,11 @@ class SviEngine:
             assert em.numel() == self.T == es.numel()
             n.eps_mu, n.eps_sd = em.data_ptr(), es.data_ptr()
             keep += [em, es]
+        if self.acc and "eps_noise" in noise:
+            en = noise["eps_noise"].reshape(-1).to(**kw).contiguous()
+            assert en.numel() == self.screen.n_guides
+            n.eps_noise = en.data_ptr()
+            keep.append(en)
         if self.mixture and "pi" in noise:
             pi = noise["pi"]
             if pi.dim() == 4:  # reference layout (R, 1, G, 2)
@@ -157,6 +180,8 @@ class SviEngine:
             out[k] = self.var_grad[i].clone()
         if self.mixture:
             out["alpha_pi"] = self.alpha_grad.clone()
+        if self.fit_noise:
+            out["noise_loc"], out["noise_scale"] = self.noise_grad[0].clone(), self.noise_grad[1].clone()
         return out
 
     def params(self) -> Dict[str, torch.Tensor]:
@@ -168,6 +193,8 @@ class SviEngine:
                "sd_loc": vp[2].reshape(shape).clone(), "sd_scale": vp[3].exp().reshape(shape)}
         if self.mixture:
             out["alpha_pi"] = self.alpha_u.exp()
+        if self.fit_noise:
+            out["noise_loc"], out["noise_scale"] = self.noise_u[0].clone(), self.noise_u[1].exp()
         return out
 
     def losses(self):

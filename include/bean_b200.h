@@ -140,7 +140,8 @@ typedef struct BeanSviConfig {
   int32_t apply_update;     /* 1: ClippedAdam step; 0: only write gradients                          */
   int32_t phases;           /* 0 or 3: both kernels; 1: guide kernel only; 2: variant kernel only
                                (1 / 2 exist so a benchmark can time each kernel with CUDA events)      */
-  int32_t reserved_;
+  int32_t fit_noise;        /* --scale-by-acc only: 1 = guide Normal(noise_loc, noise_scale) on logit_pi_noise
+                               (utils.py:145-155), 0 = drawn from the prior Normal(0, 0.655)           */
   double mu_prior_loc, mu_prior_scale;
   double sd_prior_loc, sd_prior_scale; /* LogNormal prior on sd_targets: (0, 0.01); ControlNormal (0, 1) */
   double lr0, lrd;          /* ClippedAdam: lr_t = lr0 * lrd^t, lrd = gamma^(1/num_steps) (run.py:367) */
@@ -170,12 +171,19 @@ typedef struct BeanSviState {
   double* partial;               /* f64 [bean_svi_num_partials(G, T)] scratch                           */
   uint32_t* counter;             /* u32 [1], zero before the first call                                 */
   double* loss;                  /* f64 [loss_capacity]: loss[t] = -ELBO of step t                      */
+  /* --scale-by-acc (bean/model/utils.py:79-178); acc_k == NULL switches the whole block off           */
+  const void* acc_k;             /* real [G]    exp(b) * accessibility^a  (a = 0.2513, b = -1.9458)     */
+  void* noise_u;                 /* real [2][G] noise_loc, log noise_scale (fit_noise)                  */
+  void* noise_m;
+  void* noise_v;
+  void* noise_grad;              /* real [2][G] out or NULL                                             */
 } BeanSviState;
 
 typedef struct BeanSviNoise {    /* all optional (NULL = draw with Philox) */
   const void* eps_mu;            /* real [T] */
   const void* eps_sd;            /* real [T] */
   const void* pi;                /* real [G][R][2] */
+  const void* eps_noise;         /* real [G]  standard-normal draw behind logit_pi_noise (--scale-by-acc) */
   void* eps_out;                 /* real [2][T]    out: the (eps_mu, eps_sd) the step used, or NULL */
   void* pi_out;                  /* real [G][R][2] out: the pi draws the step used, or NULL         */
 } BeanSviNoise;

@@ -43,7 +43,9 @@ def oracle_at(model, data, noise, unconstrained=None, **kw):
 def check_grads(model, data, cuda_device, dtype, tol, tol_alpha, perturb_seed=None, use_bcmatch=True, oracle_kw=None):
     oracle_kw = dict(oracle_kw or {})
     noise = H.fixed_noise(model, data, seed=21)
-    eng = SviEngine(data, model, cuda_device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=10)
+    eng = SviEngine(data, model, cuda_device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=10,
+                    scale_by_accessibility=oracle_kw.get("scale_by_accessibility", False),
+                    fit_noise=oracle_kw.get("fit_noise", False))
     unconstrained = None
     if perturb_seed is not None:
         g = torch.Generator().manual_seed(perturb_seed)
@@ -54,6 +56,11 @@ def check_grads(model, data, cuda_device, dtype, tol, tol_alpha, perturb_seed=No
             au = 0.5 * torch.randn(eng.alpha_u.shape, generator=g, dtype=torch.float64)
             eng.alpha_u.copy_(au)
             unconstrained["alpha_pi"] = au
+        if eng.fit_noise:
+            nu = 0.4 * torch.randn(eng.noise_u.shape, generator=g, dtype=torch.float64)
+            nu[1] += math.log(0.655)
+            eng.noise_u.copy_(nu)
+            unconstrained["noise_loc"], unconstrained["noise_scale"] = nu[0], nu[1]
     got = eng.gradients(noise)
     if model != "MixtureNormal":
         oracle_kw["use_bcmatch"] = use_bcmatch and getattr(data, "X_bcmatch_masked", None) is not None
@@ -66,6 +73,10 @@ def check_grads(model, data, cuda_device, dtype, tol, tol_alpha, perturb_seed=No
     if eng.mixture:
         errs["alpha_pi"] = rel_err(got["alpha_pi"], ref["alpha_pi"])
         assert errs["alpha_pi"] <= tol_alpha, f"alpha_pi: {errs['alpha_pi']:.3e}"
+    if eng.fit_noise:
+        for k in ("noise_loc", "noise_scale"):
+            errs[k] = rel_err(got[k], ref[k])
+            assert errs[k] <= tol, f"{k}: {errs[k]:.3e}"
     print(model, dtype, errs)
     return errs
 
@@ -102,6 +113,15 @@ def test_normal_models_on_reference_fixture(cuda_device, dtype, tol, tol_alpha, 
 def test_normal_model_with_bcmatch_layer(cuda_device, dtype, tol, tol_alpha):
     data = H.make_small_mixture_data(n_variants=30, n_reps=4)
     check_grads("Normal", data, cuda_device, dtype, tol, tol_alpha, perturb_seed=1, use_bcmatch=True)
+
+
+@pytest.mark.parametrize("dtype,tol,tol_alpha", CASES)
+@pytest.mark.parametrize("fit_noise", [True, False])
+def test_mixture_normal_scale_by_accessibility(cuda_device, dtype, tol, tol_alpha, fit_noise):
+    """--scale-by-acc: pi scaled by accessibility + logit-space noise site (bean/model/utils.py:79-178)."""
+    data = H.make_small_mixture_data(n_variants=30, n_reps=3, accessibility=True)
+    check_grads("MixtureNormal", data, cuda_device, dtype, tol, tol_alpha, perturb_seed=8,
+                oracle_kw=dict(scale_by_accessibility=True, fit_noise=fit_noise))
 
 
 def test_steps_follow_oracle_clipped_adam(cuda_device):
