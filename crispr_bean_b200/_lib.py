@@ -71,7 +71,14 @@ class BeanSviNoise(C.Structure):
                 ("eps_out", C.c_void_p), ("pi_out", C.c_void_p)]
 
 
+class BeanAlleleMap(C.Structure):
+    _fields_ = [("n_guides", C.c_int32), ("n_alleles", C.c_int32), ("n_edits", C.c_int32), ("nnz", C.c_int32),
+                ("allele_ptr", C.c_void_p), ("allele_edit", C.c_void_p), ("edit_ptr", C.c_void_p), ("edit_slot", C.c_void_p)]
+
+
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
+_GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+_SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
 # every symbol include/bean_b200.h declares: name -> (restype, argtypes)
 _PROTOTYPES = {
@@ -81,6 +88,8 @@ _PROTOTYPES = {
     "bean_ll_num_partials": (C.c_int, [C.c_int32]),
     "bean_ll_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
     "bean_ll_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
+    "bean_allele_gather_f32": (C.c_int, _GATHER), "bean_allele_gather_f64": (C.c_int, _GATHER),
+    "bean_allele_scatter_f32": (C.c_int, _SCATTER), "bean_allele_scatter_f64": (C.c_int, _SCATTER),
     "bean_svi_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
     "bean_svi_run_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSviConfig),
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),

@@ -241,6 +241,87 @@ class VariantSortingReporterScreenData(SortingScreenData):
                          sample_mask_column=sample_mask_column, **kwargs)
 
 
+class TilingSortingReporterScreenData(SortingScreenData):
+    """data_class.py:536-872 + :1298-1355: tiling screens -- every guide has up to `n_max_alleles - 1` edited
+    alleles, each a set of edits shared across guides (MultiMixtureNormal models).
+
+    `screen.uns[allele_df_key]` is the filtered allele-count table `bean filter` writes: columns `guide`,
+    `allele` | `aa_allele`, then one count column per sample.  An allele's edits are the comma-separated
+    tokens of `str(allele)` (the reference's `Allele.__str__`).  Emits the reference attributes
+    (`n_edits, n_max_alleles, edit_index, allele_mask, allele_counts_control`, dense `allele_to_edit` on
+    demand) plus the flat CSR `allele_ptr / allele_edit` the kernels use.  Vectorised: the reference's
+    per-guide / per-allele Python loops (:696-698, :756-788, :868-871) are gone.
+    """
+
+    is_reporter = True
+    is_tiling = True
+
+    def __init__(self, screen, *args, condition_column="bin", sample_mask_column="mask", allele_df_key=None,
+                 allele_col=None, control_guide_tag=None, **kwargs):
+        if allele_df_key is None:
+            raise ValueError("tiling screens need allele_df_key (a table in screen.uns)")
+        self._allele_df_key, self._allele_col = allele_df_key, allele_col
+        kwargs["target_col"] = None
+        super().__init__(screen, *args, condition_column=condition_column, sample_mask_column=sample_mask_column, **kwargs)
+
+    def _reporter_init(self, impute_pi_popt=False):
+        self._tiling_init()
+        pi_popt = self.popt if impute_pi_popt else self.pi_popt
+        if pi_popt is not None:
+            self.pi_a0 = get_pred_pi_alpha0(self.allele_counts_control.clone(), self.size_factor_control.clone(), pi_popt)
+        else:
+            self.pi_a0, self._pi_popt = get_fitted_pi_alpha0(self.allele_counts_control.clone(),
+                                                             self.size_factor_control.clone(), shrink=self.shrink_alpha)
+
+    def _tiling_init(self):
+        df = self.screen.uns[self._allele_df_key].reset_index(drop=True)
+        col = self._allele_col or ("aa_allele" if "aa_allele" in df.columns else "allele")
+        G = self.n_guides
+        gi = self.screen.guides.index.get_indexer(df["guide"])
+        df = df.loc[gi >= 0].reset_index(drop=True)
+        gi = gi[gi >= 0]
+        aid = df.groupby("guide", sort=False).cumcount().to_numpy() + 1  # allele_id_for_guide, table order
+        self.n_max_alleles = int(aid.max()) + 1 if len(aid) else 1
+        A = self.n_max_alleles
+        tokens = [[t.strip() for t in str(a).split(",") if t.strip()] for a in df[col]]
+        self.edit_index = {}
+        for ts in tokens:  # unique edits in order of first appearance (preprocessing/utils.py:149-173)
+            for t in ts:
+                self.edit_index.setdefault(t, len(self.edit_index))
+        self.n_edits = len(self.edit_index)
+        slot = gi.astype(np.int64) * (A - 1) + (aid - 1)
+        order = np.argsort(slot, kind="stable")
+        counts = np.zeros(G * (A - 1), dtype=np.int64)
+        counts[slot] = [len(ts) for ts in tokens]
+        self.allele_ptr = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32))
+        self.allele_edit = torch.as_tensor(np.array([self.edit_index[t] for r in order for t in tokens[r]], dtype=np.int32))
+        n_valid = np.zeros(G, dtype=np.int64)
+        np.maximum.at(n_valid, gi, aid)
+        self.allele_mask = torch.as_tensor(np.arange(A)[None, :] <= n_valid[:, None])  # column 0 = WT always exists
+        self.allele_counts_control = self._allele_tensor(self.screen_control, df, gi, aid, len(self.control_condition))
+
+    def _allele_tensor(self, scr, df, gi, aid, n_cond):
+        """(R, n_cond, G, A) allele counts; WT = barcode-matched total minus the edited alleles, floored at 0."""
+        G, A = self.n_guides, self.n_max_alleles
+        out = np.zeros((len(scr.samples), G, A), dtype=np.float32)
+        for j, name in enumerate(scr.samples.index):
+            out[j, gi, aid] = df[name].to_numpy(dtype=np.float32)
+        bc = np.asarray(scr.layers["X_bcmatch"]).T.astype(np.float32)  # (S, G)
+        out[:, :, 0] = np.clip(bc - out[:, :, 1:].sum(-1), 0, None)
+        return torch.as_tensor(out).reshape(self.n_reps, n_cond, G, A)
+
+    @property
+    def allele_to_edit(self):
+        """Dense (G, A-1, E) 0/1 tensor of the reference (data_class.py:656-699); tests / oracle only."""
+        dense = torch.zeros((self.n_guides * (self.n_max_alleles - 1), self.n_edits))
+        rows = torch.repeat_interleave(torch.arange(len(self.allele_ptr) - 1), self.allele_ptr[1:].long() - self.allele_ptr[:-1].long())
+        dense[rows, self.allele_edit.long()] = 1
+        return dense.reshape(self.n_guides, self.n_max_alleles - 1, self.n_edits)
+
+    def __getitem__(self, guide_idx):
+        raise NotImplementedError("guide subsetting of tiling screens")
+
+
 DATACLASS_DICT = {
     "sorting": {
         "Normal": VariantSortingScreenData,
@@ -249,6 +330,8 @@ DATACLASS_DICT = {
         "MixtureNormal+Acc": VariantSortingReporterScreenData,
         "_MixtureNormal+Acc": VariantSortingReporterScreenData,
         "MixtureNormalConstPi": VariantSortingScreenData,
+        "MultiMixtureNormal": TilingSortingReporterScreenData,
+        "MultiMixtureNormal+Acc": TilingSortingReporterScreenData,
     },
     "survival": {},
 }

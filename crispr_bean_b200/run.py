@@ -20,15 +20,24 @@ FUSED_MODELS = ("Normal", "ControlNormal", "MixtureNormal")
 
 
 def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, device="cuda", dtype=torch.float32,
-                seed=101) -> SviEngine:
+                seed=101):
     name, mkw = resolve(model)
     gname, gkw = resolve(guide)
     if name != gname:
         raise ValueError(f"model {name} and guide {gname} do not belong together")
     if not torch.cuda.is_available():
         raise BeanError("run_inference needs a CUDA device: crispr_bean_b200 has no CPU fallback")
+    if name == "MultiMixtureNormal":
+        if mkw.get("scale_by_accessibility"):
+            raise NotImplementedError("MultiMixtureNormal+Acc is not built yet")
+        from .generic import TilingSviEngine
+
+        return TilingSviEngine(data, device=device, dtype=dtype, use_bcmatch=True, num_steps=num_steps, initial_lr=initial_lr,
+                               gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
+                               sd_scale=float(mkw.get("sd_scale", 0.01)), epsilon=float(mkw.get("epsilon", 1e-5)),
+                               prior_params=mkw.get("prior_params"))
     if name not in FUSED_MODELS:
-        raise NotImplementedError(f"model {name} is not lowered onto the fused CUDA step yet")
+        raise NotImplementedError(f"model {name} is not built yet")
     use_bcmatch = mkw.get("use_bcmatch", True)
     if isinstance(use_bcmatch, tuple):  # reference passes the 1-tuple (not args.ignore_bcmatch,): always truthy (App. B2)
         use_bcmatch = True

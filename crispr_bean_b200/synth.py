@@ -117,3 +117,72 @@ def make_config(name: str, seed: int = 101, **override) -> MiniScreen:
     kw = dict(CONFIGS[name])
     kw.update(override)
     return make_sorting_screen(seed=seed, **kw)
+
+
+def make_tiling_screen(n_guides: int = 200, window: int = 6, max_alleles: int = 5, n_reps: int = 3,
+                       bins: Sequence[Tuple[float, float]] = DEFAULT_BINS, depth: float = 400.0, seed: int = 101,
+                       frac_effect: float = 0.2) -> MiniScreen:
+    """Tiling screen (c3 shape): guide g can edit positions [g, g + window); each of its 1..max_alleles-1 edited
+    alleles is a small subset of those positions, so edits are shared by overlapping guides.
+    `uns["allele_counts"]` holds the per-sample allele-count table `bean filter` would write."""
+    gen = torch.Generator().manual_seed(seed)
+    n_pos = n_guides + window
+    lap_u = torch.rand(n_pos, generator=gen) - 0.5
+    mu_edit = -torch.sign(lap_u) * torch.log1p(-2 * lap_u.abs()) * (torch.rand(n_pos, generator=gen) < frac_effect)
+    B = len(bins)
+    uq = torch.tensor([b[1] for b in bins], dtype=torch.float64)
+    lq = torch.tensor([b[0] for b in bins], dtype=torch.float64)
+    tu = torch.where(uq == 1, torch.tensor(math.inf, dtype=torch.float64), torch.erfinv(2 * uq.clamp(max=1 - 1e-16) - 1) * math.sqrt(2))
+    tl = torch.where(lq == 0, torch.tensor(-math.inf, dtype=torch.float64), torch.erfinv(2 * lq.clamp(min=1e-300) - 1) * math.sqrt(2))
+    n_all = torch.randint(1, max_alleles, (n_guides,), generator=gen)  # edited alleles per guide
+    rows, alleles_of = [], []
+    for g in range(n_guides):
+        al = []
+        for j in range(int(n_all[g])):
+            k = int(torch.randint(1, 3, (1,), generator=gen))
+            pos = (g + torch.randperm(window, generator=gen)[:k]).sort().values.tolist()
+            if pos not in al:
+                al.append(pos)
+        alleles_of.append(al)
+    n_g = torch.exp(math.log(depth) + 0.7 * torch.randn(n_guides, generator=gen)).clamp(min=20.0)
+    s_rb = 0.7 + 0.6 * torch.rand(n_reps, B + 1, generator=gen)
+    X = torch.zeros(n_reps, B + 1, n_guides)
+    cond_names = [f"bin{j}" for j in range(B)] + ["bulk"]
+    sample_names = [f"rep{r}_{c}" for r in range(n_reps) for c in cond_names]
+    table = []
+    frac_all = []
+    for g in range(n_guides):
+        al = alleles_of[g]
+        conc = torch.cat([torch.tensor([6.0]), torch.full((len(al),), 1.5)])
+        gam = torch._standard_gamma(conc, generator=gen)
+        frac = gam / gam.sum()  # allele fractions incl. WT
+        frac_all.append(frac)
+        mus = torch.cat([torch.zeros(1), torch.stack([mu_edit[p].sum() for p in al])]).double()
+        sds = torch.cat([torch.ones(1), torch.tensor([math.sqrt(len(p)) for p in al])]).double()
+        P = _phi((tu[:, None] - mus[None]) / sds[None]) - _phi((tl[:, None] - mus[None]) / sds[None])  # (B, A_g)
+        p = (P * frac.double()[None]).sum(-1)
+        p = (p / p.sum()).float()
+        lam = n_g[g] * s_rb[:, :B] * p[None, :] * B
+        X[:, :B, g] = torch.poisson(lam, generator=gen)
+        X[:, B, g] = torch.poisson(n_g[g] * s_rb[:, B], generator=gen)
+    Xbc = torch.binomial(X, torch.full_like(X, 0.6), generator=gen)
+    for g in range(n_guides):
+        frac = frac_all[g]
+        for j, pos in enumerate(alleles_of[g]):
+            cnt = torch.binomial(Xbc[:, :, g], torch.full_like(Xbc[:, :, g], float(frac[j + 1])), generator=gen)  # (R, B+1)
+            table.append([f"g{g}", ",".join(f"{p}:A>G" for p in pos)] + cnt.reshape(-1).tolist())
+    allele_df = pd.DataFrame(table, columns=["guide", "allele"] + sample_names)
+    rows = []
+    for r in range(n_reps):
+        for j in range(B + 1):
+            lo, hi = (bins[j] if j < B else (0.0, 1.0))
+            rows.append((f"rep{r}_{cond_names[j]}", f"rep{r}", cond_names[j], lo, hi, 1))
+    samples = pd.DataFrame(rows, columns=["name", "replicate", "bin", "lower_quantile", "upper_quantile", "mask"]).set_index("name")
+    guides = pd.DataFrame({"start_pos": np.arange(n_guides)}, index=pd.Index([f"g{g}" for g in range(n_guides)], name="name"))
+
+    def flat(t):
+        return t.permute(2, 0, 1).reshape(n_guides, -1).numpy().astype(np.float32)
+
+    scr = MiniScreen(flat(X), guides, samples, {"X_bcmatch": flat(Xbc), "edits": np.zeros((n_guides, len(samples)), dtype=np.float32)},
+                     uns={"allele_counts": allele_df, "true_mu_edit": {f"{p}:A>G": float(mu_edit[p]) for p in range(n_pos)}})
+    return scr

@@ -113,6 +113,36 @@ int bean_ll_f32(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
 int bean_ll_f64(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * bean_allele_gather / bean_allele_scatter: allele <- edit contraction of the tiling models.
+ *
+ * Replaces `torch.matmul(data.allele_to_edit, mu_edits)`, `torch.linalg.norm(data.allele_to_edit *
+ * sd_edits, dim=-1)` and the prepended WT column (0, 1) (bean/model/model.py:618-625, :907-918;
+ * survival_model.py:484-493) plus their autograd backward.  The dense 0/1 (G, A-1, E) tensor becomes
+ * CSR (slot -> edits) for the forward and CSC (edit -> slots) for the deterministic backward.
+ *   gather : mu_allele[g][0] = 0, sd_allele[g][0] = 1;  a >= 1: mu = sum_e mu_edit[e], sd = sqrt(sum_e sd_edit[e]^2)
+ *   scatter: d_mu_edit[e] = sum_slots d_mu_allele;  d_sd_edit[e] = sum_slots d_sd_allele * sd_edit[e] / sd_allele
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BeanAlleleMap {
+  int32_t n_guides;            /* G */
+  int32_t n_alleles;           /* A = n_max_alleles, wild type included */
+  int32_t n_edits;             /* E */
+  int32_t nnz;
+  const int32_t* allele_ptr;   /* i32 [G*(A-1)+1]  CSR over slots, slot = g*(A-1) + (a-1) */
+  const int32_t* allele_edit;  /* i32 [nnz]        edit ids of each slot                  */
+  const int32_t* edit_ptr;     /* i32 [E+1]        CSC over edits                         */
+  const int32_t* edit_slot;    /* i32 [nnz]        slots containing each edit             */
+} BeanAlleleMap;
+
+int bean_allele_gather_f32(const BeanAlleleMap* map, const void* mu_edit, const void* sd_edit, void* mu_allele,
+                           void* sd_allele, void* stream);
+int bean_allele_gather_f64(const BeanAlleleMap* map, const void* mu_edit, const void* sd_edit, void* mu_allele,
+                           void* sd_allele, void* stream);
+int bean_allele_scatter_f32(const BeanAlleleMap* map, const void* sd_edit, const void* sd_allele, const void* d_mu_allele,
+                            const void* d_sd_allele, void* d_mu_edit, void* d_sd_edit, void* stream);
+int bean_allele_scatter_f64(const BeanAlleleMap* map, const void* sd_edit, const void* sd_allele, const void* d_mu_allele,
+                            const void* d_sd_allele, void* d_mu_edit, void* d_sd_edit, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * bean_svi_run_{f32,f64}: n_steps complete SVI steps on the device, no host round trip per step.
  *
  * One step = what `svi.step(data)` does in bean/model/run.py:376-380 for the variant sorting models:

@@ -456,6 +456,22 @@ def sorting_ll_core(data, mu_alleles, sd_alleles, pi, use_bcmatch=True, mask_thr
     return total, out
 
 
+def survival_ll_core(data, mu_alleles, pi, use_bcmatch=True, mask_thres=10, allele_mask=None):
+    """Survival counterpart of `sorting_ll_core`: exp(mu * t) replaces the Normal-CDF bin masses
+    (bean/model/survival_model.py:352-424; masked alleles are multiplied by 0, :566-567)."""
+    G, A = mu_alleles.shape
+    B = data.n_condits
+    out = {}
+    time = data.timepoints
+    P = torch.exp(mu_alleles.unsqueeze(0).expand((B, -1, -1)) * time.unsqueeze(-1).unsqueeze(-1).expand((-1, G, 1)))
+    if allele_mask is not None:
+        P = P * allele_mask.unsqueeze(0)
+    e = (pi.expand(data.n_reps, B, -1, -1) * P[None]).sum(axis=-1)
+    total = _count_sites(data, e, use_bcmatch, mask_thres, out)
+    out["alleles_p_time"] = P
+    return total, out
+
+
 # ----------------------------------------------------------------------------------------------
 # run_inference restated (bean/model/run.py:347-396)
 # ----------------------------------------------------------------------------------------------

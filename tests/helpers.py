@@ -55,7 +55,7 @@ def load_var_mini():
 
 
 def make_small_mixture_data(n_variants=12, n_reps=3, seed=3, with_bulk_bin=True, **kw):
-    scr = make_sorting_screen(n_variants, 4, n_reps=n_reps, seed=seed, n_negctrl_guides=6, depth=120.0, **kw)
+    scr = make_sorting_screen(n_variants, 4, n_reps=n_reps, seed=seed, n_negctrl_guides=6, depth=kw.pop("depth", 120.0), **kw)
     return VariantSortingReporterScreenData(scr, control_can_be_selected=with_bulk_bin,
                                             accessibility_col="accessibility" if kw.get("accessibility") else None)
 

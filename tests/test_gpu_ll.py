@@ -147,3 +147,31 @@ def test_bad_arguments_return_error_codes(cuda_device):
     assert b"mu_allele" in _lib.lib().bean_last_error()
     with pytest.raises(_lib.BeanError):
         launch_ll(scr, torch.zeros((data.n_guides, 2)), torch.ones((data.n_guides, 2)))  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_survival_mode_exp_growth(cuda_device, dtype):
+    """mode = SURVIVAL: e = sum_a pi_a exp(mu_a t_b) (survival_model.py:352-424), timepoints 0, .5, 1."""
+    from oracle import bean_oracle as O
+
+    data = H.make_small_mixture_data(n_variants=30, n_reps=3, with_bulk_bin=False, bins=((0.0, 0.3), (0.3, 0.6), (0.6, 1.0)))
+    data.is_survival = True
+    data.timepoints = torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64)
+    G, R = data.n_guides, data.n_reps
+    g = torch.Generator().manual_seed(4)
+    mu = 0.8 * torch.randn((G, 2), generator=g, dtype=torch.float64)
+    gam = torch._standard_gamma(torch.full((R, 1, G, 2), 1.5, dtype=torch.float64), generator=g)
+    pi = gam / gam.sum(-1, keepdim=True)
+    with H.default_dtype(torch.float64):
+        d = H.cast_data(data, torch.float64)
+        m, p_ = mu.clone().requires_grad_(True), pi.clone().requires_grad_(True)
+        total, aux = O.survival_ll_core(d, m, p_, mask_thres=10)
+        total.backward()
+    scr = DeviceScreen(data, cuda_device, dtype=dtype)
+    assert scr.mode == 1
+    out = launch_ll(scr, mu.to(cuda_device), torch.ones_like(mu).to(cuda_device), pi_to_guide_major(pi).to(cuda_device))
+    tol = TOL[dtype]
+    assert abs(out["ll"].item() - float(total)) <= tol * abs(float(total))
+    rel_close(out["d_mu"], m.grad, tol, "survival d_mu")
+    rel_close(out["d_pi"], pi_to_guide_major(p_.grad), tol, "survival d_pi")
+    assert float(out["d_sd"].abs().max()) == 0.0
