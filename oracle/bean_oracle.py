@@ -496,3 +496,116 @@ def run_inference(elbo_fn, data, initial_lr=0.01, gamma=0.1, num_steps=2000, noi
 
 def as_namespace(**kw):
     return SimpleNamespace(**kw)
+
+
+# ----------------------------------------------------------------------------------------------
+# Survival models (bean/model/survival_model.py).  exp(mu * t) replaces the Normal-CDF bin masses; the
+# quirks of SURVEY App. B8 are reproduced: the guide samples `initial_abundance` although the model observes
+# it, `q0` is the guide's (G,) parameter, `mu_negctrl` is a model-only latent drawn from its prior.
+# ----------------------------------------------------------------------------------------------
+def _survival_p(mu_alleles, timepoints):
+    B = timepoints.shape[0]
+    G = mu_alleles.shape[0]
+    return torch.exp(mu_alleles.unsqueeze(0).expand((B, -1, -1)) * timepoints.unsqueeze(-1).unsqueeze(-1).expand((-1, G, 1)))
+
+
+def elbo_survival_normal(data, ps: ParamStore, noise=None, mask_thres=10, use_bcmatch=True, prior_params=None):
+    """survival NormalModel / NormalGuide (survival_model.py:15-130, :629-650): A = 1, e = exp(mu t) q_0[r, g]."""
+    T, G, R = data.n_targets, data.n_guides, data.n_reps
+    out = {}
+    init_ab = ps.param("initial_abundance", torch.ones(G) / G, positive=True)
+    mu_loc = ps.param("mu_loc", torch.zeros((T, 1)))
+    mu_scale = ps.param("mu_scale", torch.ones((T, 1)), positive=True)
+    conc_q = init_ab.unsqueeze(0).expand(R, -1)
+    q_0 = dirichlet_rsample(conc_q, noise.get("q0") if noise is not None else None)
+    mu_t = mu_loc + mu_scale * _draw(noise, "eps_mu", (T, 1))
+    guide_lp = tdist.Dirichlet(conc_q, validate_args=False).log_prob(q_0).sum() + tdist.Normal(mu_loc, mu_scale).log_prob(mu_t).sum()
+    mu_dist = tdist.Laplace(0.0, 1.0)
+    prior_ab = torch.ones(G) / G
+    if prior_params is not None:
+        if "mu_loc" in prior_params or "mu_scale" in prior_params:
+            mu_dist = tdist.Normal(prior_params.get("mu_loc", 0.0), prior_params.get("mu_scale", 1.0))
+        prior_ab = prior_params.get("initial_abundance", prior_ab)
+    model_lp = mu_dist.log_prob(mu_t).sum()
+    mu = torch.repeat_interleave(mu_t, data.target_lengths, dim=0)
+    if hasattr(data, "negctrl_guide_idx"):  # survival_model.py:59-60 (None indexes EVERY guide, as in the reference)
+        keep = torch.ones((G, 1))
+        if data.negctrl_guide_idx is None:
+            keep = torch.zeros((G, 1))
+        else:
+            keep[torch.as_tensor(data.negctrl_guide_idx).long()] = 0.0
+        mu = mu * keep
+    model_lp = model_lp + tdist.Dirichlet(prior_ab.unsqueeze(0).expand(R, -1), validate_args=False).log_prob(q_0).sum()
+    P = _survival_p(mu, data.timepoints)  # (B, G, 1)
+    e = (P.unsqueeze(0).expand(R, -1, -1, -1) * q_0.unsqueeze(1).unsqueeze(-1)).sum(axis=-1)
+    model_lp = model_lp + _count_sites(data, e, use_bcmatch, mask_thres, out)
+    out["model_lp"], out["guide_lp"] = model_lp, guide_lp
+    return -(model_lp - guide_lp), out
+
+
+def elbo_survival_control_normal(data, ps: ParamStore, noise=None, mask_thres=10, use_bcmatch=True):
+    """survival ControlNormalModel / Guide (survival_model.py:133-213, :742-757): one shared growth rate."""
+    G = data.n_guides
+    out = {}
+    mu_loc = ps.param("mu_loc", torch.tensor(0.0))
+    mu_scale = ps.param("mu_scale", torch.tensor(1.0), positive=True)
+    mu_t = mu_loc + mu_scale * _draw(noise, "eps_mu", ())
+    guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_t).sum()
+    model_lp = tdist.Normal(0.0, 1.0).log_prob(mu_t).sum()
+    mu = mu_t.repeat(G)
+    B = data.n_condits
+    P = torch.exp(mu.unsqueeze(0).expand((B, -1)) * data.timepoints.unsqueeze(-1).expand((-1, G)))
+    e = P.unsqueeze(0).expand(data.n_reps, -1, -1)
+    model_lp = model_lp + _count_sites(data, e, use_bcmatch, mask_thres, out)
+    out["model_lp"], out["guide_lp"] = model_lp, guide_lp
+    return -(model_lp - guide_lp), out
+
+
+def elbo_survival_mixture_normal(data, ps: ParamStore, noise=None, alpha_prior=1.0, use_bcmatch=True, mask_thres=10,
+                                 prior_params=None, mu_negctrl=(0.0, 0.1)):
+    """survival MixtureNormalModel / Guide (survival_model.py:215-424, :651-739), without accessibility scaling."""
+    T, G, R = data.n_targets, data.n_guides, data.n_reps
+    out = {}
+    q0 = ps.param("q0", torch.ones(G) / G, positive=True)
+    mu_loc = ps.param("mu_loc", torch.zeros((T, 1)))
+    mu_scale = ps.param("mu_scale", torch.ones((T, 1)), positive=True)
+    alpha_pi = ps.param("alpha_pi", torch.ones((G, 2)) * alpha_prior, positive=True)
+    conc_q = q0.unsqueeze(0).expand(R, -1)
+    ia_sample = dirichlet_rsample(conc_q, noise.get("q0") if noise is not None else None)  # guide-only draw (App. B8)
+    mu_t = mu_loc + mu_scale * _draw(noise, "eps_mu", (T, 1))
+    guide_lp = tdist.Dirichlet(conc_q, validate_args=False).log_prob(ia_sample).sum() + tdist.Normal(mu_loc, mu_scale).log_prob(mu_t).sum()
+    mu_dist = tdist.Laplace(0.0, 1.0)
+    if prior_params is not None and ("mu_loc" in prior_params or "mu_scale" in prior_params):
+        mu_dist = tdist.Normal(prior_params.get("mu_loc", 0.0), prior_params.get("mu_scale", 1.0))
+    model_lp = mu_dist.log_prob(mu_t).sum()
+    u = mu_negctrl[0] + mu_negctrl[1] * _draw(noise, "eps_negctrl", (G,))  # model-only latent, prior draw
+    model_lp = model_lp + tdist.Normal(mu_negctrl[0], mu_negctrl[1]).log_prob(u).sum()
+    mu_edit = torch.repeat_interleave(mu_t, data.target_lengths, dim=0)
+    mu = torch.cat([u.unsqueeze(-1), mu_edit + u.unsqueeze(-1)], axis=-1)
+    obs_ab = (data.X[:, 0, :] + 1) / (data.X[:, 0, :] + 1).sum(-1, keepdims=True)
+    model_lp = model_lp + tdist.Dirichlet(conc_q, validate_args=False).log_prob(obs_ab).sum()
+    pi_a_scaled = alpha_pi / alpha_pi.sum(axis=-1)[:, None] * data.pi_a0[:, None]
+    rg_mask = data.repguide_mask.unsqueeze(1)
+    conc_g = pi_a_scaled.clamp(1e-5).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+    pi = dirichlet_rsample(conc_g, noise.get("pi") if noise is not None else None)
+    guide_lp = guide_lp + tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi).sum()
+    conc_m = pi_a_scaled.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+    model_lp = model_lp + _masked_sum(rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
+    tc = data.control_timepoint
+    C = tc.shape[0]
+    expanded = pi.expand(-1, C, -1, -1) * torch.exp(
+        mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1) * tc.unsqueeze(0).unsqueeze(-1).unsqueeze(-1).expand(R, -1, G, 2))
+    lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(data.allele_counts_control)
+    model_lp = model_lp + _masked_sum(rg_mask.expand(lp_mult.shape), lp_mult)
+    P = _survival_p(mu, data.timepoints)  # (B, G, 2)
+    e = (pi.expand(-1, data.n_condits, -1, -1) * P[None]).sum(axis=-1)
+    model_lp = model_lp + _count_sites(data, e, use_bcmatch, mask_thres, out)
+    out["model_lp"], out["guide_lp"] = model_lp, guide_lp
+    return -(model_lp - guide_lp), out
+
+
+SURVIVAL_ELBOS = {
+    "Normal": elbo_survival_normal,
+    "ControlNormal": elbo_survival_control_normal,
+    "MixtureNormal": elbo_survival_mixture_normal,
+}
