@@ -18,14 +18,14 @@ FALLBACK_PI_POPT = (-3.214, 0.9873)   # get_pi_alpha0.py:110
 
 def get_size_factor(X: np.ndarray) -> np.ndarray:
     """Per-sample depth / mean depth (data_class.py:237-251)."""
-    sf = np.mean(np.asarray(X, dtype=np.float64), axis=0)
+    sf = np.mean(np.asarray(X), axis=0)  # dtype follows the count matrix, as in the reference (float32 counts -> float32)
     return sf / np.mean(sf)
 
 
 def _ols_line(x: np.ndarray, y: np.ndarray) -> Tuple[float, float]:
     xm, ym = x.mean(), y.mean()
     b1 = ((x - xm) * (y - ym)).sum() / ((x - xm) ** 2).sum()
-    return float(ym - b1 * xm), float(b1)
+    return np.float64(ym - b1 * xm), np.float64(b1)  # numpy scalars, like curve_fit's popt: they promote float32 to float64
 
 
 def _valid(x: torch.Tensor, y: torch.Tensor):
@@ -71,9 +71,9 @@ def get_fitted_alpha0(X, size_factor, sample_mask=None, shrink=False, shrink_pri
             popt = FALLBACK_POPT
     else:
         popt = _ols_line(x, y)
-    log_a0_est = torch.as_tensor(popt[0] + popt[1] * n.log().double().numpy())
+    log_a0_est = torch.as_tensor(popt[0] + popt[1] * n.log().numpy())  # dtype: numpy promotion, as the reference
     if shrink:
-        yy = a0.log().double()
+        yy = a0.log().to(log_a0_est.dtype)
         yy = torch.where(torch.isnan(yy), log_a0_est, yy)
         var = ((yy - log_a0_est) ** 2).sum() / (len(yy) - 1)
         pw = var / (var + shrink_prior_var)
@@ -87,7 +87,7 @@ def get_pred_alpha0(X, size_factor, popt, sample_mask=None):
     if sample_mask is None:
         sample_mask = torch.ones((R, B))
     q, _ = _moments(X + 1, size_factor, sample_mask, allele_axis=False)
-    return torch.as_tensor(np.exp(popt[0] + popt[1] * q.sum(axis=0).log().double().numpy()))
+    return torch.as_tensor(np.exp(popt[0] + popt[1] * q.sum(axis=0).log().numpy()))
 
 
 def get_fitted_pi_alpha0(allele_counts, size_factor, shrink=False, shrink_prior_var=1.0):
@@ -104,9 +104,9 @@ def get_fitted_pi_alpha0(allele_counts, size_factor, shrink=False, shrink_prior_
     a0 = torch.nanmean((n[:, None] - 1) / (r - 1 + 1 / (1 - p)) - 1, axis=-1)
     x, y = _valid(n.log(), a0.log())
     popt = FALLBACK_PI_POPT if len(y) < 10 else _ols_line(x, y)
-    log_a0_est = torch.as_tensor(popt[0] + popt[1] * n.log().double().numpy())
+    log_a0_est = torch.as_tensor(popt[0] + popt[1] * n.log().numpy())  # dtype: numpy promotion, as the reference
     if shrink:
-        yy = a0.log().double()
+        yy = a0.log().to(log_a0_est.dtype)
         yy = torch.where(torch.isnan(yy), log_a0_est, yy)
         var = (yy - log_a0_est) ** 2 / len(yy)  # get_pi_alpha0.py:66-67 (elementwise, as the reference)
         pw = var / (var + shrink_prior_var)
@@ -117,4 +117,4 @@ def get_fitted_pi_alpha0(allele_counts, size_factor, shrink=False, shrink_prior_
 def get_pred_pi_alpha0(allele_counts, size_factor, popt):
     R, C, G, A = allele_counts.shape
     q, _ = _moments(allele_counts + 1, size_factor, torch.ones((R, C)), allele_axis=True)
-    return torch.as_tensor(np.exp(popt[0] + popt[1] * q[0].sum(axis=-1).log().double().numpy()))
+    return torch.as_tensor(np.exp(popt[0] + popt[1] * q[0].sum(axis=-1).log().numpy()))

@@ -490,7 +490,7 @@ def run_inference(elbo_fn, data, initial_lr=0.01, gamma=0.1, num_steps=2000, noi
         ps.zero_grad()
         loss.backward()
         opt.step(ps.unconstrained)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     return ps, {"loss": losses, "params": {k: v.cpu() for k, v in ps.constrained().items()}}
 
 

@@ -1,0 +1,124 @@
+"""Golden vectors computed by the REFERENCE's own source (run in the build container only).
+
+    python tests/golden/make_reference_golden.py          # writes tests/golden/ref_*.npz
+
+The reference's unmodified files are imported in place from /root/reference through tests/refharness
+(bean/preprocessing/data_class.py + get_alpha0.py + get_pi_alpha0.py for the tensors; bean/model/model.py,
+survival_model.py, utils.py, run.py for the programs).  pyro-ppl cannot be installed here, so the programs
+run on tests/refharness/pyro -- a restatement of the handful of pyro primitives they call (see its
+docstring).  What the vectors therefore pin: the tensoriser, the site lists / masks / shapes / formulas of every
+model-guide pair, torch's distributions and `_dirichlet_grad`, and the ClippedAdam trajectory of
+`run_inference` -- against the reference's CODE; pyro's own handler semantics stay restated.
+"""
+import copy
+import os
+import sys
+import warnings
+from functools import partial
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+from tests.refharness import load_reference  # noqa: E402
+from tests.refharness import golden as G  # noqa: E402
+
+
+def sorting_cases(ns):
+    from crispr_bean_b200.synth import make_sorting_screen
+    from tests.helpers import var_mini_screen
+
+    m, dc = ns.model, ns.data_class
+    c1 = var_mini_screen()
+    c1 = c1[np.argsort(c1.guides["target"].to_numpy(), kind="stable"), :]  # prepare_bdata sorts guides by target
+    c1.samples["mask"] = 1
+    c1_kw = dict(condition_column="condition", control_condition="bulk", control_can_be_selected=True)
+    small = make_sorting_screen(12, 4, n_reps=3, seed=3, n_negctrl_guides=6, depth=120.0, accessibility=True)
+    wide = make_sorting_screen(10, 5, n_reps=8, seed=5, depth=300.0)  # c5 row shape (8 replicates) + bulk pseudo-bin
+    ragged = make_sorting_screen(9, "lognormal", n_reps=2, seed=8, depth=25.0, n_negctrl_guides=3)  # low depth: masked rows
+    rep_kw = dict(control_can_be_selected=True)
+    return [
+        # name, screen, data class, data kwargs, model, guide, oracle model name, oracle kwargs
+        ("normal_c1", c1, dc.VariantSortingScreenData, c1_kw, partial(m.NormalModel, use_bcmatch=False), m.NormalGuide,
+         "Normal", dict(use_bcmatch=False)),
+        ("control_normal_c1", c1, dc.VariantSortingScreenData, c1_kw, partial(m.ControlNormalModel, use_bcmatch=False),
+         partial(m.ControlNormalGuide, use_bcmatch=False), "ControlNormal", dict(use_bcmatch=False)),
+        ("mixture_small", small, dc.VariantSortingReporterScreenData, rep_kw, m.MixtureNormalModel, m.MixtureNormalGuide,
+         "MixtureNormal", {}),
+        ("mixture_wide8", wide, dc.VariantSortingReporterScreenData, rep_kw, m.MixtureNormalModel, m.MixtureNormalGuide,
+         "MixtureNormal", {}),
+        ("mixture_ragged_lowdepth", ragged, dc.VariantSortingReporterScreenData, rep_kw, m.MixtureNormalModel,
+         m.MixtureNormalGuide, "MixtureNormal", {}),
+        ("mixture_acc_fitnoise", small, dc.VariantSortingReporterScreenData, dict(rep_kw, accessibility_col="accessibility"),
+         partial(m.MixtureNormalModel, scale_by_accessibility=True),
+         partial(m.MixtureNormalGuide, scale_by_accessibility=True, fit_noise=True), "MixtureNormal",
+         dict(scale_by_accessibility=True, fit_noise=True)),
+        ("mixture_acc_priornoise", small, dc.VariantSortingReporterScreenData, dict(rep_kw, accessibility_col="accessibility"),
+         partial(m.MixtureNormalModel, scale_by_accessibility=True),
+         partial(m.MixtureNormalGuide, scale_by_accessibility=True, fit_noise=False), "MixtureNormal",
+         dict(scale_by_accessibility=True, fit_noise=False)),
+        ("mixture_prior_params", small, dc.VariantSortingReporterScreenData, rep_kw,
+         partial(m.MixtureNormalModel, prior_params={"mu_loc": 0.1, "mu_scale": 2.0}), m.MixtureNormalGuide,
+         "MixtureNormal", dict(prior_params={"mu_loc": 0.1, "mu_scale": 2.0})),
+        ("normal_bcmatch", small, dc.VariantSortingScreenData, dict(rep_kw, use_bcmatch=True),
+         partial(m.NormalModel, use_bcmatch=True), m.NormalGuide, "Normal", dict(use_bcmatch=True)),
+    ]
+
+
+def write_case(ns, name, screen, cls, data_kw, model, guide, oracle_model, oracle_kw, n_traj=0):
+    data = cls(copy.deepcopy(screen), **data_kw)
+    arrays = dict(G.screen_to_arrays(screen))
+    arrays.update({f"data/{k}": v for k, v in G.data_tensors(data).items()})
+    arrays["meta/data_class"] = np.asarray(cls.__name__)
+    arrays["meta/data_kwargs"] = np.asarray(repr(data_kw))
+    arrays["meta/oracle_model"] = np.asarray(oracle_model)
+    arrays["meta/oracle_kwargs"] = np.asarray(repr(oracle_kw))
+    for tag, dtype in (("f64", torch.float64), ("native", torch.float32)):
+        out, noise = G.reference_loss_and_grads(ns.pyro, model, guide, data, seed=11, dtype=dtype)
+        arrays.update({f"{tag}/{k}": v for k, v in out.items()})
+        arrays.update({f"{tag}/{k}": v for k, v in noise.items()})
+    if n_traj:
+        arrays.update(trajectory(ns, model, guide, data, n_traj))
+    path = os.path.join(HERE, f"ref_{name}.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name:28s} f64 loss {float(arrays['f64/loss']):.10g}  native loss {float(arrays['native/loss']):.10g}  "
+          f"{os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def trajectory(ns, model, guide, data, n_steps):
+    """`run_inference` of the reference (bean/model/run.py:347-396), float64, recording every step's guide draws."""
+    pyro = ns.pyro
+    rec = []
+
+    def recording_guide(d):
+        tr = pyro.poutine.trace(guide).get_trace(d)  # inner trace: sees the same messages as SVI's own
+        rec.append({k: v.double().numpy() for k, v in G.noise_from_guide_trace(pyro, tr).items()})
+
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(23)
+        store, hist = ns.run.run_inference(model, recording_guide, G.cast_floats(data, torch.float64), num_steps=n_steps)
+    finally:
+        torch.set_default_dtype(old)
+        torch.autograd.set_detect_anomaly(False)
+    out = {"traj/loss": np.asarray(hist["loss"], dtype=np.float64), "traj/n_steps": np.asarray(n_steps)}
+    for k, v in hist["params"].items():
+        out[f"traj/param/{k}"] = v.double().numpy()
+    for k in rec[0]:
+        out[f"traj/noise/{k}"] = np.stack([r[k] for r in rec])
+    return out
+
+
+def main():
+    ns = load_reference()
+    for case in sorting_cases(ns):
+        write_case(ns, *case, n_traj=6 if case[0] in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise") else 0)
+
+
+if __name__ == "__main__":
+    main()

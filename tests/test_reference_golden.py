@@ -1,0 +1,141 @@
+"""The tensoriser and the CPU oracle against vectors computed by the REFERENCE's own source files
+(tests/golden/ref_*.npz, written by tests/golden/make_reference_golden.py through tests/refharness)."""
+import ast
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from crispr_bean_b200 import data_class as dc
+from oracle import bean_oracle as O
+from tests.helpers import GOLDEN, default_dtype, cast_data
+from tests.refharness.golden import screen_from_arrays
+
+CASES = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
+SORTING = [c for c in CASES if not c.startswith(("survival", "tiling"))]
+
+
+def load_case(name, reference_fits=True):
+    """Fixture + the screen pushed through OUR tensoriser.  `reference_fits`: take the three curve_fit products
+    (a0, a0_bcmatch, pi_a0) from the fixture, so that program parity is not blurred by scipy's 1.5e-8
+    Levenberg-Marquardt stopping tolerance (ours is the closed-form least-squares optimum)."""
+    z = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    scr = screen_from_arrays(z)
+    cls = getattr(dc, str(z["meta/data_class"]))
+    data = cls(scr, **ast.literal_eval(str(z["meta/data_kwargs"])))
+    if reference_fits:
+        for k in ("a0", "a0_bcmatch", "pi_a0"):
+            if f"data/{k}" in z.files and hasattr(data, k):
+                setattr(data, k, torch.as_tensor(z[f"data/{k}"]))
+    return z, data
+
+
+def group(z, prefix):
+    return {k[len(prefix):]: z[k] for k in z.files if k.startswith(prefix)}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_golden_cases_exist():
+    assert len(CASES) >= 9
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tensoriser_equals_reference_data_class(name):
+    """Every tensor the reference's *ScreenData built from the screen (data_class.py) -- same values and dtypes."""
+    z, data = load_case(name, reference_fits=False)
+    ref = group(z, "data/")
+    checked = 0
+    for k, v in ref.items():
+        if not hasattr(data, k):
+            continue
+        mine = getattr(data, k)
+        if torch.is_tensor(mine):
+            assert tuple(mine.shape) == v.shape, k
+            assert str(mine.dtype).replace("torch.", "") == str(v.dtype), (k, mine.dtype, v.dtype)
+            if k in ("a0", "a0_bcmatch", "pi_a0"):  # closed-form OLS here vs curve_fit (ftol 1.5e-8) there
+                assert rel(mine.numpy(), v) < 1e-7, k
+            else:
+                assert np.array_equal(mine.numpy(), v, equal_nan=True), k
+        else:
+            assert mine == v.item(), k
+        checked += 1
+    assert checked >= 12
+    missing = [k for k in ref if not hasattr(data, k) and ref[k].ndim > 0]
+    assert not missing, f"tensors of the reference data class absent from the mirror: {missing}"
+
+
+def oracle_eval(z, data, tag, dtype):
+    noise = {k: torch.as_tensor(v).to(dtype) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
+    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    with default_dtype(dtype):
+        d = cast_data(data, dtype) if dtype == torch.float64 else data
+        ps = O.ParamStore()
+        loss, aux = O.SORTING_ELBOS[str(z["meta/oracle_model"])](d, ps, noise=noise, **kw)
+        loss.backward()
+    return float(loss.detach()), {k: v.grad.detach().double().numpy() for k, v in ps.unconstrained.items()}, ps
+
+
+@pytest.mark.parametrize("name", SORTING)
+def test_oracle_equals_reference_programs_float64(name):
+    """-ELBO and d(-ELBO)/d(unconstrained params) of the reference model/guide programs, float64, same noise."""
+    z, data = load_case(name)
+    loss, grads, _ = oracle_eval(z, data, "f64", torch.float64)
+    assert abs(loss - float(z["f64/loss"])) <= 1e-11 * abs(float(z["f64/loss"]))
+    ref_grads = group(z, "f64/grad/")
+    assert set(grads) == set(ref_grads)
+    for k, g in ref_grads.items():
+        assert rel(grads[k].reshape(g.shape), g) < 1e-9, k
+
+
+@pytest.mark.parametrize("name", SORTING)
+def test_oracle_equals_reference_programs_native_precision(name):
+    """Same in the reference's own mixed float32/float64 arithmetic (tolerance: float32 rounding)."""
+    z, data = load_case(name)
+    loss, grads, _ = oracle_eval(z, data, "native", torch.float32)
+    assert abs(loss - float(z["native/loss"])) <= 2e-6 * abs(float(z["native/loss"]))
+    for k, g in group(z, "native/grad/").items():
+        assert rel(grads[k].reshape(g.shape), g) < 2e-4, k
+
+
+@pytest.mark.parametrize("name", [c for c in SORTING if "traj/n_steps" in np.load(os.path.join(GOLDEN, f"ref_{c}.npz")).files])
+def test_oracle_run_inference_follows_reference_trajectory(name):
+    """bean/model/run.py:run_inference (SVI + ClippedAdam, lr decay) for a few steps with the recorded draws."""
+    z, data = load_case(name)
+    n = int(z["traj/n_steps"])
+    tn = group(z, "traj/noise/")
+    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    with default_dtype(torch.float64):
+        d = cast_data(data, torch.float64)
+        ps, hist = O.run_inference(O.SORTING_ELBOS[str(z["meta/oracle_model"])], d, num_steps=n,
+                                   noise_fn=lambda t: {k: torch.as_tensor(v[t]) for k, v in tn.items()}, **kw)
+    assert rel(hist["loss"], z["traj/loss"]) < 1e-11
+    for k, v in group(z, "traj/param/").items():
+        assert rel(hist["params"][k].numpy().reshape(v.shape), v) < 1e-9, k
+
+
+def test_live_reference_matches_committed_vectors():
+    """Where the reference sources are mounted (build container): re-run one case live -- guards the vectors
+    against drifting from the generator."""
+    from tests.refharness import available, load_reference
+
+    if not available():
+        pytest.skip("reference sources not mounted")
+    import copy
+    import warnings
+    from tests.refharness import golden as G
+
+    warnings.filterwarnings("ignore")
+    ns = load_reference()
+    z = np.load(os.path.join(GOLDEN, "ref_mixture_small.npz"))
+    scr = screen_from_arrays(z)
+    data = ns.data_class.VariantSortingReporterScreenData(copy.deepcopy(scr), **ast.literal_eval(str(z["meta/data_kwargs"])))
+    out, _ = G.reference_loss_and_grads(ns.pyro, ns.model.MixtureNormalModel, ns.model.MixtureNormalGuide, data, seed=11,
+                                        dtype=torch.float64)
+    assert float(out["loss"]) == float(z["f64/loss"])
+    assert np.array_equal(out["grad/alpha_pi"], z["f64/grad/alpha_pi"])
