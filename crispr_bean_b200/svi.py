@@ -78,7 +78,7 @@ class SviEngine:
             # _scale_edited_pi: pi * exp(b) * accessibility^a with a = 0.2513, b = -1.9458 (utils.py:79-103)
             acc = torch.as_tensor(data.guide_accessibility).double()
             self.acc_k = (math.exp(-1.9458) * acc.pow(0.2513)).to(**kw).contiguous()
-            self.noise_u = torch.stack([torch.zeros(G), torch.full((G,), 0.655).log()]).to(**kw).contiguous()
+            self.noise_u = torch.stack([torch.zeros(G, dtype=torch.float64), torch.full((G,), 0.655, dtype=torch.float64).log()]).to(**kw).contiguous()
             self.noise_m, self.noise_v = torch.zeros((2, G), **kw), torch.zeros((2, G), **kw)
             self.noise_grad = torch.zeros((2, G), **kw)
         self.partial = torch.zeros((self.lib.bean_svi_num_partials(G, T),), dtype=torch.float64, device=dev)
