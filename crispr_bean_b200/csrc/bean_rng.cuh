@@ -135,6 +135,8 @@ __device__ __forceinline__ real digamma_full(real z) {
   lgamma_digamma(z, lg, dg);
   return dg;
 }
+template <>
+__device__ __forceinline__ double digamma_full<double>(double z) { return digamma_f64(z); }  // no lgamma needed
 
 // x near 0: Taylor series in x (torch: _beta_grad_alpha_small)
 template <typename real>
@@ -168,6 +170,21 @@ __device__ __forceinline__ real beta_grad_beta_small(real x, real alpha, real be
   return isnan(result) ? real(0) : result;
 }
 
+// |x - mean| <= 0.1 std inside the saddle-point regime: torch's polynomial in (x, alpha, beta)
+template <typename real>
+__device__ __forceinline__ real beta_grad_mid_near_mean(real x, real alpha, real beta, real iT) {
+  const real total = alpha + beta;
+  const real b2 = beta * beta;
+  const real poly = real(47) * x * b2 * b2 +
+                    alpha * ((real(43) + real(20) * (real(16) + real(27) * beta) * x) * b2 * beta +
+                             alpha * (real(3) * (real(59) + real(180) * beta - real(90) * x) * b2 +
+                                      alpha * ((real(453) + real(1620) * beta * (real(1) - x) - real(455) * x) * beta +
+                                               alpha * (real(8) * (real(1) - x) * (real(135) * beta - real(11))))));
+  const real pre_num = (real(1) + real(12) * alpha) * (real(1) + real(12) * beta) * iT * iT;
+  const real pre_den = real(12960) * alpha * alpha * alpha * beta * beta * (real(1) + real(12) * total);
+  return pre_num * poly / ((real(1) - x) * pre_den);
+}
+
 // alpha, beta both large: Rice saddle-point expansion (torch: _beta_grad_alpha_mid).  Same expression as
 // torch, algebraically regrouped so that it costs 2 logs, 2 rsqrt and a handful of divisions instead of
 // 3 logs, 2 pows, 4 sqrts and ~15 divisions:
@@ -181,17 +198,8 @@ __device__ __forceinline__ real beta_grad_alpha_mid(real x, real alpha, real bet
   const real mean = alpha * iT;
   const real dx = x - mean;
   // |x - mean| <= 0.1 std  <=>  dx^2 (T+1) T^2 <= 0.01 a b
-  if (dx * dx * (total + real(1)) * total * total <= real(0.01) * alpha * beta) {
-    const real b2 = beta * beta;
-    const real poly = real(47) * x * b2 * b2 +
-                      alpha * ((real(43) + real(20) * (real(16) + real(27) * beta) * x) * b2 * beta +
-                               alpha * (real(3) * (real(59) + real(180) * beta - real(90) * x) * b2 +
-                                        alpha * ((real(453) + real(1620) * beta * (real(1) - x) - real(455) * x) * beta +
-                                                 alpha * (real(8) * (real(1) - x) * (real(135) * beta - real(11))))));
-    const real pre_num = (real(1) + real(12) * alpha) * (real(1) + real(12) * beta) * iT * iT;
-    const real pre_den = real(12960) * alpha * alpha * alpha * beta * beta * (real(1) + real(12) * total);
-    return pre_num * poly / ((real(1) - x) * pre_den);
-  }
+  if (dx * dx * (total + real(1)) * total * total <= real(0.01) * alpha * beta)
+    return beta_grad_mid_near_mean(x, alpha, beta, iT);
   const real q = real(2) * alpha * beta * iT;
   const real rs = real(1) / Num<real>::sqrt(q);
   const real s = q * rs;
@@ -264,6 +272,61 @@ __device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real tota
 // out-of-line double evaluation: keeps the (register-hungry) double code out of the float kernels' bodies
 __device__ __noinline__ double dirichlet_grad_one_f64(double x, double alpha, double total) {
   return dirichlet_grad_one<double>(x, alpha, total);
+}
+
+// Both components of a two-allele draw at once: g0 = dirichlet_grad_one(x0, a, a + b), g1 = dirichlet_grad_one(x1, b, a + b).
+// When both land in the saddle-point regime (the common case once concentrations exceed 6) the two evaluations
+// share everything expensive: the roles of (alpha, L1) and (beta, L2) just swap, q = 2ab/T, the Stirling factor and
+// term4 = (b L2 + a L1)^-1.5 are symmetric.  Component 1 is evaluated at 1 - x0 throughout (x1 differs from it by one
+// rounding of the sample: a smooth perturbation of the argument, not amplified by the formula's cancellation).
+__device__ __noinline__ void dirichlet_grad_pair_f64(double x0, double x1, double a, double b, double& g0, double& g1) {
+  const double T = a + b;
+  const double bnd0 = T * x0 * (1.0 - x0), bnd1 = T * x1 * (1.0 - x1);
+  const bool big = a > 6.0 && b > 6.0;
+  const bool mid0 = big && !(x0 <= 0.5 && bnd0 < 2.5) && !(x0 >= 0.5 && bnd0 < 0.75);
+  const bool mid1 = big && !(x1 <= 0.5 && bnd1 < 2.5) && !(x1 >= 0.5 && bnd1 < 0.75);
+  const double iT = 1.0 / T;
+  const double m0 = a * iT, m1 = b * iT;
+  const double d0 = x0 - m0, d1 = x1 - m1;
+  if (!(mid0 && mid1)) {  // any other regime: the generic per-component evaluation
+    g0 = dirichlet_grad_one<double>(x0, a, T);
+    g1 = dirichlet_grad_one<double>(x1, b, T);
+    return;
+  }
+  // |x - mean| <= 0.1 std: torch switches to a polynomial there (8 % of draws, so nearly every warp has such a
+  // lane: keep it inside this path, per component, instead of diverging into the generic evaluation)
+  const double lim = 0.01 * a * b, w = (T + 1.0) * T * T;
+  const bool near0 = d0 * d0 * w <= lim, near1 = d1 * d1 * w <= lim;
+  const double q = 2.0 * a * b * iT;
+  const double rs = rsqrt(q);
+  const double s = q * rs;
+  const double a2 = a * a, b2 = b * b, t2 = T * T;
+  const double stirling = (288.0 * a2 + 24.0 * a + 1.0) * (288.0 * b2 + 24.0 * b + 1.0) * t2 /
+                          (288.0 * a2 * b2 * (288.0 * t2 + 24.0 * T + 1.0));
+  const double La = ::log(m0 / x0);          // component 0: L1, component 1: L2
+  const double Lb = ::log(m1 / (1.0 - x0));  // component 0: L2, component 1: L1
+  const double base = b * Lb + a * La;
+  const double rb = rsqrt(base);
+  const double term4 = rb * rb * rb;
+  const double k = rs * iT * iT;
+  {
+    const double xm1 = x0 - 1.0;
+    const double iax = 1.0 / (a * xm1 + b * x0);
+    const double term1 = (2.0 * a2 * xm1 + a * b * xm1 - x0 * b2) * b * k * iax * iax;
+    const double t = term1 + 0.5 * La * (2.0 * s * iax + (x0 < m0 ? term4 : -term4));
+    g0 = stirling * (-x0 * rs) * t;
+  }
+  {
+    // every x of component 1 must be the SAME number the shared logs saw (1 - x0): term1 and term2 * term4 cancel
+    // to O(1) from O((x - mean)^-2), and a sample rounded differently in the two would break that cancellation
+    const double y1 = 1.0 - x0, xm1 = -x0;
+    const double iax = 1.0 / (b * xm1 + a * y1);
+    const double term1 = (2.0 * b2 * xm1 + a * b * xm1 - y1 * a2) * a * k * iax * iax;
+    const double t = term1 + 0.5 * Lb * (2.0 * s * iax + (y1 < m1 ? term4 : -term4));
+    g1 = stirling * (-y1 * rs) * t;
+  }
+  if (near0) g0 = beta_grad_mid_near_mean(x0, a, b, iT);
+  if (near1) g1 = beta_grad_mid_near_mean(x1, b, a, iT);
 }
 
 }  // namespace bean

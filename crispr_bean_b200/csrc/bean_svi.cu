@@ -290,10 +290,11 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         // pathwise derivative of pi w.r.t. the guide concentration (torch _Dirichlet_backward)
         // evaluated in double even on the float path, as torch's CPU kernel does (accscalar_t = double):
         // the saddle-point branch cancels badly in float
-        const double tot = (double)cg[0] + (double)cg[1];
         const double gbar = (double)pi0 * (double)go0 + (double)pi1 * (double)go1;
-        dcg[0] += real(dirichlet_grad_one_f64((double)pi0, (double)cg[0], tot) * ((double)go0 - gbar));
-        dcg[1] += real(dirichlet_grad_one_f64((double)pi1, (double)cg[1], tot) * ((double)go1 - gbar));
+        double dg0, dg1;
+        dirichlet_grad_pair_f64((double)pi0, (double)pi1, (double)cg[0], (double)cg[1], dg0, dg1);
+        dcg[0] += real(dg0 * ((double)go0 - gbar));
+        dcg[1] += real(dg1 * ((double)go1 - gbar));
       } else {
 #pragma unroll
         for (int b = 0; b < NB; ++b) dP[b] += de[b];
