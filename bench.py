@@ -225,16 +225,35 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    # empirical FP32/SFU ceiling: the Dirichlet-Multinomial row maths alone, operands in registers
+    from crispr_bean_b200 import _lib as L_
+
+    sink = torch.empty((nv * gpv + 127) // 128, device=dev, dtype=torch.float32)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    for _ in range(3):
+        L_.check(L_.lib().bean_row_ceiling_f32(nv * gpv, R * L, B, sink.data_ptr(), st), "bean_row_ceiling_f32")
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(20):
+        L_.check(L_.lib().bean_row_ceiling_f32(nv * gpv, R * L, B, sink.data_ptr(), st), "bean_row_ceiling_f32")
+    c1.record()
+    torch.cuda.synchronize()
+    ms_ceiling = c0.elapsed_time(c1) / 20
     achieved = bytes_launch / (ms_guide * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "svi_guide_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": ms_guide,
                 "ms_per_launch_variant_kernel": ms_var,
+                "row_math_ceiling_ms": ms_ceiling, "frac_of_row_math_ceiling": ms_ceiling / ms_guide,
+                "row_math_ceiling_what": "register-only kernel evaluating the same Dirichlet-Multinomial row maths "
+                                         f"({R * L} rows x {B} bins per guide: {2 * B + 2} lgamma/digamma pairs + {2 * B} log1p per row) "
+                                         "with no memory traffic: the measured FP32/SFU floor of the step's row work",
                 "note": "the kernel is FP32/SFU-bound (lgamma/digamma/log1p series per cell), see DESIGN.md and profiles/"}
 
     # --- e2e: host-resident screen -> public API -> host-resident results ------------------------
     from crispr_bean_b200.device_pack import DeviceScreen
 
+    data.pin_memory()  # the contract's e2e starts from PINNED host memory; pinning itself is not timed
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)

@@ -95,6 +95,7 @@ _PROTOTYPES = {
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
     "bean_svi_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSviConfig),
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_row_ceiling_f32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -10,15 +10,23 @@
 
 namespace bean {
 
+// Library functions with long bodies are called through ONE out-of-line copy each: the SVI kernel is bound by
+// instruction issue AND by its instruction-cache footprint, and a call costs far less than a duplicated body.
+static __device__ __noinline__ float ool_logf(float x) { return logf(x); }
+static __device__ __noinline__ float ool_log1pf(float x) { return log1pf(x); }
+static __device__ __noinline__ float ool_powf(float x, float y) { return powf(x, y); }
+static __device__ __noinline__ float ool_erfcf(float x) { return erfcf(x); }
+static __device__ __noinline__ double ool_log(double x) { return ::log(x); }
+
 template <typename real> struct Num;
 template <> struct Num<float> {
-  static __device__ __forceinline__ float log(float x) { return logf(x); }
+  static __device__ __forceinline__ float log(float x) { return ool_logf(x); }
   static __device__ __forceinline__ float exp(float x) { return expf(x); }
   static __device__ __forceinline__ float erf(float x) { return erff(x); }
   static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
   static __device__ __forceinline__ float lgamma(float x) { return lgammaf(x); }
-  static __device__ __forceinline__ float pow(float x, float y) { return powf(x, y); }
-  static __device__ __forceinline__ float log1p(float x) { return log1pf(x); }
+  static __device__ __forceinline__ float pow(float x, float y) { return ool_powf(x, y); }
+  static __device__ __forceinline__ float log1p(float x) { return ool_log1pf(x); }
   static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }  // MUFU.RCP, ~1 ulp
@@ -28,7 +36,7 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float flog(float x) { return __logf(x); }
 };
 template <> struct Num<double> {
-  static __device__ __forceinline__ double log(double x) { return ::log(x); }
+  static __device__ __forceinline__ double log(double x) { return ool_log(x); }
   static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
   static __device__ __forceinline__ double erf(double x) { return ::erf(x); }
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
@@ -145,9 +153,9 @@ __device__ __forceinline__ void bin_prob_sorting(float thr_u, float thr_l, float
   const float zl = hl ? (thr_l - mu) * rs : -INFINITY;
   const float k = 0.70710678118654752440f;
   if (zl > 0.0f)
-    P = 0.5f * (erfcf(zl * k) - erfcf(zu * k));
+    P = 0.5f * (ool_erfcf(zl * k) - ool_erfcf(zu * k));
   else
-    P = 0.5f * (erfcf(-zu * k) - erfcf(-zl * k));
+    P = 0.5f * (ool_erfcf(-zu * k) - ool_erfcf(-zl * k));
   const float fu = hu ? std_normal_pdf(zu) : 0.0f, fl = hl ? std_normal_pdf(zl) : 0.0f;
   const float zfu = hu ? zu * fu : 0.0f, zfl = hl ? zl * fl : 0.0f;
   dP_dmu = -(fu - fl) * rs;

@@ -17,7 +17,7 @@
 
 namespace bean {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+static __device__ __noinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
@@ -144,6 +144,7 @@ __device__ __forceinline__ real beta_grad_alpha_small(real x, real alpha, real b
   const real factor = digamma_full(alpha) - digamma_full(alpha + beta) - Num<real>::log(x);
   real numer = real(1);
   real series = numer / alpha * (factor + real(1) / alpha);
+#pragma unroll 1
   for (int i = 1; i <= 10; ++i) {
     const real ci = real(i);
     numer *= (ci - beta) * x / ci;
@@ -159,6 +160,7 @@ template <typename real>
 __device__ __forceinline__ real beta_grad_beta_small(real x, real alpha, real beta) {
   const real factor = digamma_full(alpha + beta) - digamma_full(beta);
   real numer = real(1), betas = real(1), dbetas = real(0), series = factor / alpha;
+#pragma unroll 1
   for (int i = 1; i <= 8; ++i) {
     const real ci = real(i);
     numer *= -x / ci;
@@ -269,9 +271,19 @@ __device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real tota
   return p / q * approx;
 }
 
-// out-of-line double evaluation: keeps the (register-hungry) double code out of the float kernels' bodies
-__device__ __noinline__ double dirichlet_grad_one_f64(double x, double alpha, double total) {
+// Single out-of-line copies (code size: the SVI kernel lives or dies by its instruction-cache footprint -- with
+// these inlined per call site it reached 235 KB of SASS and stalled on instruction fetch once warps diverged):
+//   the full four-regime evaluation in double (double kernels),
+//   the three cancellation-free regimes in float (float kernels; the caller has excluded the saddle-point regime),
+//   the saddle-point regime alone in double.
+static __device__ __noinline__ double dirichlet_grad_one_f64(double x, double alpha, double total) {
   return dirichlet_grad_one<double>(x, alpha, total);
+}
+static __device__ __noinline__ float dirichlet_grad_tail_f32(float x, float alpha, float total) {
+  return dirichlet_grad_one<float>(x, alpha, total);
+}
+static __device__ __noinline__ double beta_grad_mid_f64(double x, double alpha, double beta) {
+  return beta_grad_alpha_mid<double>(x, alpha, beta);
 }
 
 // Both components of a two-allele draw at once: g0 = dirichlet_grad_one(x0, a, a + b), g1 = dirichlet_grad_one(x1, b, a + b).
@@ -279,7 +291,15 @@ __device__ __noinline__ double dirichlet_grad_one_f64(double x, double alpha, do
 // share everything expensive: the roles of (alpha, L1) and (beta, L2) just swap, q = 2ab/T, the Stirling factor and
 // term4 = (b L2 + a L1)^-1.5 are symmetric.  Component 1 is evaluated at 1 - x0 throughout (x1 differs from it by one
 // rounding of the sample: a smooth perturbation of the argument, not amplified by the formula's cancellation).
-__device__ __noinline__ void dirichlet_grad_pair_f64(double x0, double x1, double a, double b, double& g0, double& g1) {
+//
+// FLOAT_TAILS (the float kernels): the other three regimes of torch's approximation -- the two boundary series and
+// the rational correction -- carry no cancellation, so they are evaluated in float (1e-6 relative, against the
+// fp32 path's 2e-4 budget for this gradient).  They are the minority of draws but, being divergent, they would
+// otherwise dominate warp time: a double series of 10 terms with 2 divisions each, 2 digamma recurrences and a
+// double pow cost ~10x the saddle-point path, and 3 % of such guides already put one in 60 % of the warps
+// (measured: 1.3 -> 4.3 ms/step once alpha_pi has fitted the low editing rates).
+template <bool FLOAT_TAILS>
+__device__ __noinline__ void dirichlet_grad_pair(double x0, double x1, double a, double b, double& g0, double& g1) {
   const double T = a + b;
   const double bnd0 = T * x0 * (1.0 - x0), bnd1 = T * x1 * (1.0 - x1);
   const bool big = a > 6.0 && b > 6.0;
@@ -289,8 +309,13 @@ __device__ __noinline__ void dirichlet_grad_pair_f64(double x0, double x1, doubl
   const double m0 = a * iT, m1 = b * iT;
   const double d0 = x0 - m0, d1 = x1 - m1;
   if (!(mid0 && mid1)) {  // any other regime: the generic per-component evaluation
-    g0 = dirichlet_grad_one<double>(x0, a, T);
-    g1 = dirichlet_grad_one<double>(x1, b, T);
+    if (FLOAT_TAILS) {
+      g0 = mid0 ? beta_grad_mid_f64(x0, a, b) : (double)dirichlet_grad_tail_f32((float)x0, (float)a, (float)T);
+      g1 = mid1 ? beta_grad_mid_f64(x1, b, a) : (double)dirichlet_grad_tail_f32((float)x1, (float)b, (float)T);
+    } else {
+      g0 = dirichlet_grad_one_f64(x0, a, T);
+      g1 = dirichlet_grad_one_f64(x1, b, T);
+    }
     return;
   }
   // |x - mean| <= 0.1 std: torch switches to a polynomial there (8 % of draws, so nearly every warp has such a
@@ -303,8 +328,8 @@ __device__ __noinline__ void dirichlet_grad_pair_f64(double x0, double x1, doubl
   const double a2 = a * a, b2 = b * b, t2 = T * T;
   const double stirling = (288.0 * a2 + 24.0 * a + 1.0) * (288.0 * b2 + 24.0 * b + 1.0) * t2 /
                           (288.0 * a2 * b2 * (288.0 * t2 + 24.0 * T + 1.0));
-  const double La = ::log(m0 / x0);          // component 0: L1, component 1: L2
-  const double Lb = ::log(m1 / (1.0 - x0));  // component 0: L2, component 1: L1
+  const double La = ool_log(m0 / x0);          // component 0: L1, component 1: L2
+  const double Lb = ool_log(m1 / (1.0 - x0));  // component 0: L2, component 1: L1
   const double base = b * Lb + a * La;
   const double rb = rsqrt(base);
   const double term4 = rb * rb * rb;

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         // the saddle-point branch cancels badly in float
         const double gbar = (double)pi0 * (double)go0 + (double)pi1 * (double)go1;
         double dg0, dg1;
-        dirichlet_grad_pair_f64((double)pi0, (double)pi1, (double)cg[0], (double)cg[1], dg0, dg1);
+        dirichlet_grad_pair<sizeof(real) == 4>((double)pi0, (double)pi1, (double)cg[0], (double)cg[1], dg0, dg1);
         dcg[0] += real(dg0 * ((double)go0 - gbar));
         dcg[1] += real(dg1 * ((double)go1 - gbar));
       } else {

@@ -182,6 +182,15 @@ class ScreenData:
                    "a0_bcmatch": 0, "pi_a0": 0, "allele_counts_control": 2, "guide_accessibility": 0,
                    "allele_counts": 2}
 
+    def pin_memory(self):
+        """Page-lock every tensor of the tensorised screen (in place) so the upload to the GPU runs at full PCIe
+        rate and asynchronously; a no-op without CUDA."""
+        if torch.cuda.is_available():
+            for k, v in vars(self).items():
+                if torch.is_tensor(v) and not v.is_cuda and not v.is_pinned() and v.numel() > 0:
+                    setattr(self, k, v.contiguous().pin_memory())
+        return self
+
     def __getitem__(self, guide_idx):
         idx = torch.as_tensor(np.asarray(guide_idx)).long()
         nd = copy(self)

@@ -40,10 +40,11 @@ class DeviceScreen:
             layers.append((data.X_bcmatch_masked, data.size_factor_bcmatch, data.a0_bcmatch))
         self.n_guides, self.n_reps, self.n_bins, self.n_layers = G, R, B, len(layers)
         self.mask_thres = int(mask_thres)
-        # (R, B, G) -> (G, R, B), layers stacked in front
-        self.x = torch.stack([x.permute(2, 0, 1) for x, _, _ in layers]).to(device=self.device, dtype=dtype).contiguous()
+        # (R, B, G) -> (G, R, B), layers stacked in front; uploaded as they are (asynchronously when the host
+        # tensors are pinned, `data.pin_memory()`) and re-tiled on the device
+        self.x = torch.stack([x.to(self.device, non_blocking=True).permute(2, 0, 1) for x, _, _ in layers]).to(dtype).contiguous()
         self.a0 = torch.stack([torch.as_tensor(a) for _, _, a in layers]).to(device=self.device, dtype=dtype).contiguous()
-        self.row_mask = data.repguide_mask.T.to(torch.uint8).to(self.device).contiguous()  # (G, R)
+        self.row_mask = data.repguide_mask.to(self.device, non_blocking=True).T.to(torch.uint8).contiguous()  # (G, R)
         self._sf = np.ascontiguousarray(torch.stack([torch.as_tensor(s).double() for _, s, _ in layers]).numpy())
         self._smask = np.ascontiguousarray(data.sample_mask.double().numpy())
         if self.mode == _lib.MODE_SORTING:

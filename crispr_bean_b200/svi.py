@@ -64,7 +64,7 @@ class SviEngine:
             ac = data.allele_counts_control  # (R, C, G, 2); the model observes condition 0 of the control
             if ac.shape[1] != 1:
                 raise NotImplementedError("more than one control condition")
-            self.allele_counts = ac[:, 0].permute(1, 0, 2).to(**kw).contiguous()  # (G, R, 2)
+            self.allele_counts = ac.to(dev, non_blocking=True)[:, 0].permute(1, 0, 2).to(dtype).contiguous()  # (G, R, 2)
             self.pi_a0 = torch.as_tensor(data.pi_a0).to(**kw).contiguous()
             # data-only part of the Multinomial log-pmf, masked like the site (model.py:455, :470-474)
             a64 = self.allele_counts.double()

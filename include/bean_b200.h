@@ -224,6 +224,13 @@ int bean_svi_run_f32(const BeanScreen* screen, const BeanSviState* state, const 
 int bean_svi_run_f64(const BeanScreen* screen, const BeanSviState* state, const BeanSviConfig* cfg,
                      const BeanSviNoise* noise, int32_t first_step, int32_t n_steps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Measurement aid (no reference counterpart): register-only evaluation of the Dirichlet-Multinomial row
+ * maths of `n_rows_per_guide` rows of `n_bins` bins for `n_guides` guides -- the empirical FP32/SFU ceiling
+ * bench.py quotes next to the HBM roofline.  out: float [ceil(n_guides / 128)] (checksum sink).
+ * ---------------------------------------------------------------------------------------------- */
+int bean_row_ceiling_f32(int32_t n_guides, int32_t n_rows_per_guide, int32_t n_bins, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
