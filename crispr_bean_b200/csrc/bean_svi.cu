@@ -22,6 +22,9 @@ namespace bean {
 
 constexpr int SVI_THREADS = 128;
 constexpr int SVI_MIN_CTAS = 4;  // <= 128 registers: 16 warps/SM resident
+// ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
+// so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
+constexpr int SVI_WARP = 32;
 constexpr int VAR_THREADS = 256;
 constexpr int VAR_LANES = 8;  // lanes cooperating on one variant
 constexpr int VAR_PER_CTA = VAR_THREADS / VAR_LANES;
@@ -108,9 +111,8 @@ __device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, re
   sd_t = Num<real>::exp(log_sd);
 }
 
-template <typename real, int NB, bool MIXTURE>
+template <typename real, int NB, bool MIXTURE, bool ACC>
 __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
-  __shared__ double red[32];
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = p.B;
   const real eps = real(1e-5);
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
       }
     }
     // --scale-by-acc: per-guide logit-space noise (utils.py:133-178)
-    const bool acc = MIXTURE && p.acc_k != nullptr;
+    constexpr bool acc = MIXTURE && ACC;  // compiled out of the plain kernels (code size)
     const real PI_NOISE_SD = real(0.655);
     real kacc = real(1), n_eps = real(0), n_loc = real(0), n_scale = PI_NOISE_SD, n_val = real(0), dnoise = real(0);
     if (acc) {
@@ -357,8 +359,8 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
     }
     elbo = (double)elbo_g;
   }
-  const double tot = block_sum(elbo, red);
-  if (threadIdx.x == 0) p.partial[blockIdx.x] = tot;
+  const double tot = warp_sum(elbo);
+  if ((threadIdx.x & 31) == 0) p.partial[(blockIdx.x * SVI_THREADS + threadIdx.x) / SVI_WARP] = tot;
 }
 
 template <typename real>
@@ -451,15 +453,15 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
   }
 }
 
-template <typename real, bool MIXTURE>
+template <typename real, bool MIXTURE, bool ACC>
 static void launch_guide(const SviParams<real>& p, cudaStream_t st) {
   const int grid = (p.G + SVI_THREADS - 1) / SVI_THREADS;
   if (p.B <= 4)
-    svi_guide_kernel<real, 4, MIXTURE><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, 4, MIXTURE, ACC><<<grid, SVI_THREADS, 0, st>>>(p);
   else if (p.B == 5)
-    svi_guide_kernel<real, 5, MIXTURE><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, 5, MIXTURE, ACC><<<grid, SVI_THREADS, 0, st>>>(p);
   else
-    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC><<<grid, SVI_THREADS, 0, st>>>(p);
 }
 
 template <typename real>
@@ -519,7 +521,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.partial = state->partial;
   p.counter = state->counter;
   p.loss = state->loss;
-  p.n_partial_guide = (p.G + SVI_THREADS - 1) / SVI_THREADS;
+  p.n_partial_guide = (p.G + SVI_THREADS - 1) / SVI_THREADS * (SVI_THREADS / SVI_WARP);
   p.n_partial_var = (p.T + VAR_PER_CTA - 1) / VAR_PER_CTA;
   p.eps_mu = noise ? static_cast<const real*>(noise->eps_mu) : nullptr;
   p.eps_sd = noise ? static_cast<const real*>(noise->eps_sd) : nullptr;
@@ -548,7 +550,9 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
     const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
     p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
     if (cfg->phases != 2) {
-      if (mix) launch_guide<real, true>(p, st); else launch_guide<real, false>(p, st);
+      if (mix && p.acc_k) launch_guide<real, true, true>(p, st);
+      else if (mix) launch_guide<real, true, false>(p, st);
+      else launch_guide<real, false, false>(p, st);
     }
     if (cfg->phases != 1) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
   }
@@ -561,7 +565,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
 extern "C" {
 
 int bean_svi_num_partials(int32_t n_guides, int32_t n_variants) {
-  return (n_guides + bean::SVI_THREADS - 1) / bean::SVI_THREADS + (n_variants + bean::VAR_PER_CTA - 1) / bean::VAR_PER_CTA;
+  return (n_guides + bean::SVI_THREADS - 1) / bean::SVI_THREADS * (bean::SVI_THREADS / bean::SVI_WARP) + (n_variants + bean::VAR_PER_CTA - 1) / bean::VAR_PER_CTA;
 }
 int bean_svi_run_f32(const BeanScreen* s, const BeanSviState* st, const BeanSviConfig* c, const BeanSviNoise* n,
                      int32_t first_step, int32_t n_steps, void* stream) {
