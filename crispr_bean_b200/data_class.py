@@ -250,6 +250,73 @@ class VariantSortingReporterScreenData(SortingScreenData):
                          sample_mask_column=sample_mask_column, **kwargs)
 
 
+class SurvivalScreenData(ScreenData):
+    """Proliferation screens: conditions are timepoints (reference: data_class.py:1003-1122).
+
+    `time` is divided by its maximum (`timepoints` in [0, 1]); the control condition stays a selected condition
+    (`control_can_be_selected=True`, the reference default for survival) and `control_timepoint` holds its time."""
+
+    is_survival = True
+
+    def _assign_condition_ids(self, smp, selected):
+        tc = self.time_column
+        try:
+            t = smp[tc].astype(float)
+        except ValueError as exc:
+            raise ValueError(f"Invalid timepoint value({smp[tc]}) in screen.samples[{tc}]: check input.") from exc
+        smp[tc] = t / t.max()
+        if smp[tc].isnull().any():
+            raise ValueError(f"NaN values in time points provided in input: {smp[tc]}")
+        if not (smp.groupby(self.condition_column).size() == self.n_reps).all():
+            raise ValueError(
+                "Not all replicate share same timepoint definition. If you have missing bin data, add the sample and add "
+                "'mask' column in 'screen.samples', or run `bean-qc` that automatically handles this.")
+        times = np.sort(smp[tc].unique())
+        smp[f"{tc}_id"] = smp[tc].map({v: j for j, v in enumerate(times)}).astype(np.int64)
+        smp[f"{self.condition_column}_id"] = smp[f"{tc}_id"]  # samples are ordered by (replicate, time)
+        is_control = smp[self.condition_column].astype(str).isin(self.control_condition).to_numpy()
+        control_timepoint = smp.loc[is_control, tc].unique()
+        if len(control_timepoint) != len(self.control_condition):
+            raise ValueError(
+                "All samples with --control-condition should have the same --time-col column in "
+                "ReporterScreen.samples[time_col]. Check your input ReporterScreen object.")
+        self.control_timepoint = torch.tensor(control_timepoint)
+        self.timepoints = torch.as_tensor(np.sort(smp.loc[selected, tc].unique()))
+        self.n_timepoints = len(self.timepoints)
+
+    def _reporter_init(self, impute_pi_popt=False):
+        """+ `allele_counts (R, n_timepoints, G, 2)`: reporter alleles at every timepoint (data_class.py:347-362)."""
+        scr, tc = self.screen, self.time_column
+        per_time = []
+        for t in self.timepoints:
+            st = scr[:, (scr.samples[tc] == t.item()).to_numpy()]
+            edited = self.transform_data(st.layers["edits"], 1)
+            nonedited = (self.transform_data(st.layers["X_bcmatch"], 1) - edited).clamp(min=0)
+            per_time.append(torch.stack([nonedited, edited], axis=-1))
+        self.allele_counts = torch.cat(per_time, axis=1)
+        super()._reporter_init(impute_pi_popt)
+
+
+class VariantSurvivalScreenData(SurvivalScreenData):
+    """data_class.py:1358-1427: guide counts only (survival Normal / ControlNormal models)."""
+
+    def __init__(self, screen, *args, condition_column="condition", time_column="time", control_can_be_selected=True,
+                 sample_mask_column="mask", **kwargs):
+        super().__init__(screen, *args, condition_column=condition_column, time_column=time_column,
+                         control_can_be_selected=control_can_be_selected, sample_mask_column=sample_mask_column, **kwargs)
+
+
+class VariantSurvivalReporterScreenData(SurvivalScreenData):
+    """data_class.py:1430-1475: + barcode-matched counts and reporter edits (survival MixtureNormal)."""
+
+    is_reporter = True
+
+    def __init__(self, screen, *args, condition_column="condition", time_column="time", control_can_be_selected=True,
+                 sample_mask_column="mask", **kwargs):
+        super().__init__(screen, *args, condition_column=condition_column, time_column=time_column,
+                         control_can_be_selected=control_can_be_selected, sample_mask_column=sample_mask_column, **kwargs)
+
+
 class TilingSortingReporterScreenData(SortingScreenData):
     """data_class.py:536-872 + :1298-1355: tiling screens -- every guide has up to `n_max_alleles - 1` edited
     alleles, each a set of edits shared across guides (MultiMixtureNormal models).
@@ -342,5 +409,11 @@ DATACLASS_DICT = {
         "MultiMixtureNormal": TilingSortingReporterScreenData,
         "MultiMixtureNormal+Acc": TilingSortingReporterScreenData,
     },
-    "survival": {},
+    "survival": {
+        "Normal": VariantSurvivalScreenData,
+        "MixtureNormal": VariantSurvivalReporterScreenData,
+        "_MixtureNormal": VariantSurvivalReporterScreenData,
+        "MixtureNormal+Acc": VariantSurvivalReporterScreenData,
+        "_MixtureNormal+Acc": VariantSurvivalReporterScreenData,
+    },
 }

@@ -48,7 +48,68 @@ def _masked_sum(mask, lp):
     return torch.where(mask, lp, torch.zeros_like(lp)).sum()
 
 
-class TilingSviEngine:
+class AutogradSviEngine:
+    """Shared SVI plumbing of the models whose ELBO is assembled from torch CUDA ops around the C-ABI kernels:
+    unconstrained parameters (positive ones as log), ClippedAdam, device-side loss log."""
+
+    def _init_optim(self, theta, positive, num_steps, initial_lr, gamma, seed):
+        self.theta, self.positive = theta, set(positive)
+        for p in self.theta.values():
+            p.requires_grad_(True)
+        self.m = {k: torch.zeros_like(v) for k, v in self.theta.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in self.theta.items()}
+        self.lr0, self.lrd, self.num_steps = float(initial_lr), float(gamma) ** (1.0 / max(num_steps, 1)), int(num_steps)
+        self.step = 0
+        self.loss = torch.zeros(max(num_steps, 1), dtype=torch.float64, device=self.device)
+        self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
+
+    def _draw(self, noise, key, shape):
+        if noise is not None and key in noise:
+            return noise[key].to(device=self.device, dtype=self.dtype).reshape(shape)
+        return torch.randn(shape, generator=self.gen, device=self.device, dtype=self.dtype)
+
+    def _adam(self):
+        """pyro.optim.ClippedAdam on the unconstrained tensors (SURVEY App. A.6)."""
+        t = self.step + 1
+        lr = self.lr0 * self.lrd ** t
+        step_size = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        with torch.no_grad():
+            for k, p in self.theta.items():
+                if p.grad is None:
+                    continue
+                g = p.grad.clamp(-10.0, 10.0)
+                self.m[k].mul_(0.9).add_(g, alpha=0.1)
+                self.v[k].mul_(0.999).addcmul_(g, g, value=0.001)
+                p.addcdiv_(self.m[k], self.v[k].sqrt().add_(1e-8), value=-step_size)
+                p.grad = None
+
+    def run(self, n_steps: int, noise=None):
+        for _ in range(n_steps):
+            loss = self.elbo_loss(noise)
+            loss.backward()
+            self.loss[self.step] = loss.detach().double()
+            self._adam()
+            self.step += 1
+        return self.loss[self.step - n_steps:self.step]
+
+    def gradients(self, noise=None):
+        loss = self.elbo_loss(noise)
+        loss.backward()
+        out = {"loss": loss.detach().clone()}
+        for k, p in self.theta.items():
+            out[k] = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().clone()
+            p.grad = None
+        return out
+
+    def params(self):
+        """Constrained values under the reference's parameter names."""
+        return {k: (v.detach().exp() if k in self.positive else v.detach().clone()) for k, v in self.theta.items()}
+
+    def losses(self):
+        return self.loss[: self.step].cpu()
+
+
+class TilingSviEngine(AutogradSviEngine):
     """MultiMixtureNormal on one GPU.  Parameter names / shapes follow the pyro guide (model.py:893-937)."""
 
     def __init__(self, data, device="cuda", dtype=torch.float32, use_bcmatch=True, num_steps=2000, initial_lr=0.01,
@@ -70,17 +131,8 @@ class TilingSviEngine:
         a0[~self.allele_mask] = epsilon
         z = lambda *s: torch.zeros(s, **kw)
         # unconstrained parameters (positive ones as log), initial values of model.py:893-937
-        self.theta = {"mu_loc": z(self.E), "mu_scale": z(self.E), "sd_loc": z(self.E), "sd_scale": z(self.E),
-                       "alpha_pi": a0.log()}
-        self.positive = {"mu_scale", "sd_scale", "alpha_pi"}
-        for p in self.theta.values():
-            p.requires_grad_(True)
-        self.m = {k: torch.zeros_like(v) for k, v in self.theta.items()}
-        self.v = {k: torch.zeros_like(v) for k, v in self.theta.items()}
-        self.lr0, self.lrd, self.num_steps = float(initial_lr), float(gamma) ** (1.0 / max(num_steps, 1)), int(num_steps)
-        self.step = 0
-        self.loss = torch.zeros(max(num_steps, 1), dtype=torch.float64, device=self.device)
-        self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
+        theta = {"mu_loc": z(self.E), "mu_scale": z(self.E), "sd_loc": z(self.E), "sd_scale": z(self.E), "alpha_pi": a0.log()}
+        self._init_optim(theta, {"mu_scale", "sd_scale", "alpha_pi"}, num_steps, initial_lr, gamma, seed)
 
     # ---------------------------------------------------------------------------------------------
     def elbo_loss(self, noise: Optional[Dict[str, torch.Tensor]] = None):
@@ -126,41 +178,3 @@ class TilingSviEngine:
         pi_g = pi[:, 0].permute(1, 0, 2).contiguous()  # (G, R, A)
         model_lp = model_lp + count_log_likelihood(self.screen, mu_a, sd_a, pi_g, self.allele_mask_u8)
         return -(model_lp - guide_lp)
-
-    def _adam(self):
-        """pyro.optim.ClippedAdam on the unconstrained tensors (SURVEY App. A.6)."""
-        t = self.step + 1
-        lr = self.lr0 * self.lrd ** t
-        step_size = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
-        with torch.no_grad():
-            for k, p in self.theta.items():
-                g = p.grad.clamp(-10.0, 10.0)
-                self.m[k].mul_(0.9).add_(g, alpha=0.1)
-                self.v[k].mul_(0.999).addcmul_(g, g, value=0.001)
-                p.addcdiv_(self.m[k], self.v[k].sqrt().add_(1e-8), value=-step_size)
-                p.grad = None
-
-    def run(self, n_steps: int, noise=None):
-        for _ in range(n_steps):
-            loss = self.elbo_loss(noise)
-            loss.backward()
-            self.loss[self.step] = loss.detach().double()
-            self._adam()
-            self.step += 1
-        return self.loss[self.step - n_steps:self.step]
-
-    def gradients(self, noise=None):
-        loss = self.elbo_loss(noise)
-        loss.backward()
-        out = {"loss": loss.detach().clone()}
-        for k, p in self.theta.items():
-            out[k] = p.grad.detach().clone()
-            p.grad = None
-        return out
-
-    def params(self):
-        """Constrained values under the reference's names: mu_loc, mu_scale, sd_loc, sd_scale (E,), alpha_pi (G, A)."""
-        return {k: (v.detach().exp() if k in self.positive else v.detach().clone()) for k, v in self.theta.items()}
-
-    def losses(self):
-        return self.loss[: self.step].cpu()

@@ -18,8 +18,8 @@ from typing import Optional
 class _Program:
     """A named model or guide program plus the keyword arguments bound so far."""
 
-    def __init__(self, name: str, kind: str, defaults: dict):
-        self.bean_name, self.kind, self.defaults = name, kind, defaults
+    def __init__(self, name: str, kind: str, defaults: dict, selection: str = "sorting"):
+        self.bean_name, self.kind, self.defaults, self.selection = name, kind, defaults, selection
         self.__name__ = f"{name}{'Model' if kind == 'model' else 'Guide'}"
 
     def __call__(self, data, **kwargs):
@@ -37,6 +37,13 @@ def resolve(program):
     if not isinstance(program, _Program):
         raise TypeError(f"not a crispr_bean_b200 model/guide: {program!r}")
     return program.bean_name, {**program.defaults, **kwargs}
+
+
+def selection_of(program) -> str:
+    """"sorting" | "survival": which family (bean/model/model.py vs survival_model.py) a program belongs to."""
+    while isinstance(program, partial):
+        program = program.func
+    return program.selection
 
 
 # sorting models (bean/model/model.py:19, :168, :378, :550) and guides (:754, :785, :861, :878)

@@ -12,8 +12,9 @@ from logging import info
 import torch
 
 from . import model as sorting_model
+from . import survival_model
 from ._lib import BeanError
-from .model import resolve
+from .model import resolve, selection_of
 from .svi import SviEngine
 
 FUSED_MODELS = ("Normal", "ControlNormal", "MixtureNormal")
@@ -27,6 +28,19 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
         raise ValueError(f"model {name} and guide {gname} do not belong together")
     if not torch.cuda.is_available():
         raise BeanError("run_inference needs a CUDA device: crispr_bean_b200 has no CPU fallback")
+    if selection_of(model) != selection_of(guide):
+        raise ValueError("model and guide belong to different selections (sorting vs survival)")
+    if selection_of(model) == "survival":
+        if mkw.get("scale_by_accessibility"):
+            raise NotImplementedError("survival MixtureNormal+Acc is not built yet")
+        from .survival import SurvivalSviEngine
+
+        use_bcmatch = mkw.get("use_bcmatch", True)
+        use_bcmatch = True if isinstance(use_bcmatch, tuple) else bool(use_bcmatch)  # App. B2
+        extra = {"mu_negctrl": mkw["mu_negctrl"]} if name == "MixtureNormal" else {}
+        return SurvivalSviEngine(data, name, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps,
+                                 initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
+                                 mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"), **extra)
     if name == "MultiMixtureNormal":
         if mkw.get("scale_by_accessibility"):
             raise NotImplementedError("MultiMixtureNormal+Acc is not built yet")
@@ -65,11 +79,11 @@ def run_inference(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000
 
 
 def identify_model_guide(args):
-    """bean/model/run.py:399-457 for the sorting selection."""
-    if args.selection != "sorting":
-        raise NotImplementedError("survival models")
-    m = sorting_model
+    """bean/model/run.py:399-457."""
+    m = sorting_model if args.selection == "sorting" else survival_model
     if args.library_design == "tiling":
+        if args.selection != "sorting":
+            raise NotImplementedError("survival MultiMixtureNormal is not built yet")
         return (
             f"MultiMixtureNormal{'+Acc' if args.scale_by_acc else ''}",
             partial(m.MultiMixtureNormalModel, scale_by_accessibility=args.scale_by_acc, use_bcmatch=(not args.ignore_bcmatch,)),
@@ -89,4 +103,5 @@ def identify_model_guide(args):
 def identify_negctrl_model_guide(args, data_has_bcmatch):
     """bean/model/run.py:460-474."""
     use = (not args.ignore_bcmatch) and data_has_bcmatch
-    return partial(sorting_model.ControlNormalModel, use_bcmatch=use), partial(sorting_model.ControlNormalGuide, use_bcmatch=use)
+    m = sorting_model if getattr(args, "selection", "sorting") == "sorting" else survival_model
+    return partial(m.ControlNormalModel, use_bcmatch=use), partial(m.ControlNormalGuide, use_bcmatch=use)

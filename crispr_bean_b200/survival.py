@@ -1,0 +1,147 @@
+"""SVI engine for the proliferation / survival models (bean/model/survival_model.py): Normal, ControlNormal,
+MixtureNormal.
+
+Same split as the tiling engine: the count likelihood -- exp(mu t) allele masses, allele mixture, get_alpha and the
+Dirichlet-Multinomial rows of both count layers with their backward -- is the C-ABI kernel (`bean_ll_*` in survival
+mode); the Dirichlet-over-guides abundance sites, the editing-rate sites, priors and ClippedAdam are torch CUDA ops
+(plumbing).  Sites and quirks follow the reference:
+  * survival Normal  (survival_model.py:15-130, guide :629-650): `initial_guide_abundance ~ Dirichlet` over ALL
+    guides per replicate, e[r, b, g] = exp(mu_g t_b) q_0[r, g]; negative-control guides have mu := 0 (:58-60);
+  * ControlNormal    (:133-213, guide :742-757): one shared growth rate;
+  * MixtureNormal    (:215-424, guide :651-739): the guide samples `initial_abundance` although the model observes it,
+    `q0` is the guide's (G,) parameter, `mu_negctrl` is a model-only latent drawn from its prior every step.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributions as tdist
+
+from ._lib import BeanError
+from .device_pack import DeviceScreen
+from .generic import AutogradSviEngine, _DirichletRsample, _masked_sum
+from .ll_function import count_log_likelihood
+
+
+class SurvivalSviEngine(AutogradSviEngine):
+    def __init__(self, data, model: str = "MixtureNormal", device="cuda", dtype=torch.float32, use_bcmatch=True,
+                 num_steps=2000, initial_lr=0.01, gamma=0.1, seed=101, alpha_prior=1.0, mask_thres=10,
+                 prior_params: Optional[dict] = None, mu_negctrl=(0.0, 0.1)):
+        if model not in ("Normal", "ControlNormal", "MixtureNormal"):
+            raise ValueError(f"SurvivalSviEngine does not implement model {model!r}")
+        if not torch.cuda.is_available():
+            raise BeanError("SurvivalSviEngine needs a CUDA device: there is no CPU fallback")
+        if not getattr(data, "is_survival", False):
+            raise ValueError("SurvivalSviEngine needs a *SurvivalScreenData object")
+        self.model, self.device, self.dtype = model, torch.device(device), dtype
+        kw = dict(device=self.device, dtype=dtype)
+        use_bcmatch = bool(use_bcmatch) and getattr(data, "X_bcmatch_masked", None) is not None
+        self.screen = DeviceScreen(data, self.device, dtype=dtype, use_bcmatch=use_bcmatch, mask_thres=mask_thres)
+        G, R = data.n_guides, data.n_reps
+        self.G, self.R = G, R
+        self.prior_params = prior_params
+        z = lambda *s: torch.zeros(s, **kw)
+        if model == "ControlNormal":
+            self.T = 1
+            theta, positive = {"mu_loc": z(), "mu_scale": z()}, {"mu_scale"}
+        else:
+            self.T = int(data.n_targets)
+            self.target_lengths = data.target_lengths.to(self.device)
+            theta, positive = {"mu_loc": z(self.T, 1), "mu_scale": z(self.T, 1)}, {"mu_scale"}
+        uniform = torch.full((G,), 1.0 / G, **kw)
+        if model == "Normal":
+            theta["initial_abundance"] = uniform.log()
+            positive.add("initial_abundance")
+            self.prior_abundance = uniform if not (prior_params and "initial_abundance" in prior_params) else \
+                torch.as_tensor(prior_params["initial_abundance"]).to(**kw)
+            keep = torch.ones((G, 1), **kw)  # survival_model.py:58-60 (None indexes every guide, as in the reference)
+            if hasattr(data, "negctrl_guide_idx"):
+                if data.negctrl_guide_idx is None:
+                    keep.zero_()
+                else:
+                    keep[torch.as_tensor(data.negctrl_guide_idx).long().to(self.device)] = 0.0
+            self.keep = keep
+        if model == "MixtureNormal":
+            theta["q0"] = uniform.log()
+            theta["alpha_pi"] = torch.full((G, 2), float(alpha_prior), **kw).log()
+            positive |= {"q0", "alpha_pi"}
+            self.pi_a0 = torch.as_tensor(data.pi_a0).to(**kw)
+            self.allele_counts_control = data.allele_counts_control.to(**kw)  # (R, C, G, 2)
+            self.control_timepoint = data.control_timepoint.to(**kw)
+            self.rg_mask = data.repguide_mask.to(self.device).unsqueeze(1)  # (R, 1, G)
+            x0 = data.X[:, 0, :].to(**kw) + 1  # survival_model.py:306-311: observed initial abundance
+            self.obs_abundance = x0 / x0.sum(-1, keepdim=True)
+            self.mu_negctrl = (float(mu_negctrl[0]), float(mu_negctrl[1]))
+        self._init_optim(theta, positive, num_steps, initial_lr, gamma, seed)
+
+    # ---------------------------------------------------------------------------------------------
+    def _mu_prior(self):
+        kw = dict(device=self.device, dtype=self.dtype)
+        pp = self.prior_params or {}
+        if "mu_loc" in pp or "mu_scale" in pp:
+            return tdist.Normal(torch.as_tensor(pp.get("mu_loc", 0.0), **kw), torch.as_tensor(pp.get("mu_scale", 1.0), **kw))
+        return tdist.Laplace(torch.zeros((), **kw), torch.ones((), **kw))
+
+    def elbo_loss(self, noise: Optional[Dict[str, torch.Tensor]] = None):
+        """-ELBO of one particle (site lists: SURVEY App. A.8)."""
+        kw = dict(device=self.device, dtype=self.dtype)
+        G, R, T = self.G, self.R, self.T
+        P = self.theta
+        mu_loc, mu_scale = P["mu_loc"], P["mu_scale"].exp()
+        shape = () if self.model == "ControlNormal" else (T, 1)
+        mu_t = mu_loc + mu_scale * self._draw(noise, "eps_mu", shape)
+        guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_t).sum()
+        injected_q = noise["q0"].to(**kw) if (noise is not None and "q0" in noise) else None
+
+        if self.model == "ControlNormal":
+            one = torch.ones((), **kw)
+            model_lp = tdist.Normal(0 * one, one).log_prob(mu_t).sum()
+            mu_a = mu_t.reshape(1, 1).expand(G, 1)
+            ll = count_log_likelihood(self.screen, mu_a, torch.ones_like(mu_a), None, None)
+            return -(model_lp + ll - guide_lp)
+
+        model_lp = self._mu_prior().log_prob(mu_t).sum()
+        mu_g = torch.repeat_interleave(mu_t, self.target_lengths, dim=0)  # (G, 1)
+        if self.model == "Normal":
+            conc = P["initial_abundance"].exp().unsqueeze(0).expand(R, -1)
+            q_0 = _DirichletRsample.apply(conc, injected_q, self.gen)  # (R, G): one Dirichlet over all guides per replicate
+            guide_lp = guide_lp + tdist.Dirichlet(conc, validate_args=False).log_prob(q_0).sum()
+            model_lp = model_lp + tdist.Dirichlet(self.prior_abundance.unsqueeze(0).expand(R, -1),
+                                                  validate_args=False).log_prob(q_0).sum()
+            mu_a = mu_g * self.keep
+            ll = count_log_likelihood(self.screen, mu_a, torch.ones_like(mu_a), q_0.t().unsqueeze(-1).contiguous(), None)
+            return -(model_lp + ll - guide_lp)
+
+        # MixtureNormal
+        alpha_pi = P["alpha_pi"].exp()
+        conc_q = P["q0"].exp().unsqueeze(0).expand(R, -1)
+        ia = _DirichletRsample.apply(conc_q, injected_q, self.gen)  # guide-only draw (App. B8)
+        guide_lp = guide_lp + tdist.Dirichlet(conc_q, validate_args=False).log_prob(ia).sum()
+        m0, s0 = self.mu_negctrl
+        u = m0 + s0 * self._draw(noise, "eps_negctrl", (G,))  # model-only latent: fresh prior noise every step
+        model_lp = model_lp + tdist.Normal(torch.as_tensor(m0, **kw), torch.as_tensor(s0, **kw)).log_prob(u).sum()
+        mu = torch.cat([u.unsqueeze(-1), mu_g + u.unsqueeze(-1)], dim=-1)  # (G, 2)
+        model_lp = model_lp + tdist.Dirichlet(conc_q, validate_args=False).log_prob(self.obs_abundance).sum()
+        pi_a_scaled = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]
+        conc_g = pi_a_scaled.clamp(min=1e-5).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+        conc_m = pi_a_scaled.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+        injected = noise["pi"].to(**kw) if (noise is not None and "pi" in noise) else None
+        pi = _DirichletRsample.apply(conc_g, injected, self.gen)
+        guide_lp = guide_lp + tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi).sum()
+        model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
+        tc = self.control_timepoint
+        C = tc.shape[0]
+        expanded = pi.expand(-1, C, -1, -1) * torch.exp(mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1)
+                                                        * tc.reshape(1, C, 1, 1).expand(R, -1, G, 2))
+        lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(self.allele_counts_control)
+        model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
+        pi_g = pi[:, 0].permute(1, 0, 2).contiguous()  # (G, R, 2)
+        ll = count_log_likelihood(self.screen, mu, torch.ones_like(mu), pi_g, None)
+        return -(model_lp + ll - guide_lp)
+
+    def params(self):
+        out = super().params()
+        if self.model == "ControlNormal":
+            out = {k: v.reshape(()) for k, v in out.items()}
+        return out

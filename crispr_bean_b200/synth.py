@@ -186,3 +186,53 @@ def make_tiling_screen(n_guides: int = 200, window: int = 6, max_alleles: int = 
     scr = MiniScreen(flat(X), guides, samples, {"X_bcmatch": flat(Xbc), "edits": np.zeros((n_guides, len(samples)), dtype=np.float32)},
                      uns={"allele_counts": allele_df, "true_mu_edit": {f"{p}:A>G": float(mu_edit[p]) for p in range(n_pos)}})
     return scr
+
+
+def make_survival_screen(n_variants: int, guides_per_variant=5, n_reps: int = 3, times: Sequence[float] = (0.0, 7.0, 14.0),
+                         depth: float = 300.0, seed: int = 101, n_negctrl_guides: int = 0, frac_effect: float = 0.3,
+                         accessibility: bool = False) -> MiniScreen:
+    """Proliferation screen (c4 shape): samples = replicates x timepoints (`condition` D<t>, `time` t); a guide's
+    abundance grows as exp(mu t / max t) in its edited cells.  Same layers as the sorting screens."""
+    gen = torch.Generator().manual_seed(seed)
+    lengths = variant_lengths(n_variants, guides_per_variant, gen)
+    if n_negctrl_guides:
+        lengths = torch.cat([torch.tensor([n_negctrl_guides]), lengths])
+    T = len(lengths)
+    G = int(lengths.sum())
+    gv = torch.repeat_interleave(torch.arange(T), lengths)
+    mu_v = 0.8 * torch.randn(T, generator=gen) * (torch.rand(T, generator=gen) < frac_effect)
+    if n_negctrl_guides:
+        mu_v[0] = 0.0
+    g1 = torch._standard_gamma(torch.full((G,), 2.0), generator=gen)
+    g2 = torch._standard_gamma(torch.full((G,), 5.0), generator=gen)
+    pi_g = g1 / (g1 + g2)
+    n_g = torch.exp(math.log(depth) + 0.8 * torch.randn(G, generator=gen)).clamp(min=5.0)
+    tt = torch.tensor(times) / max(times)
+    S = len(times)
+    growth = (1 - pi_g)[None, :] + pi_g[None, :] * torch.exp(mu_v[gv][None, :] * tt[:, None])  # (S, G)
+    s_rb = 0.7 + 0.6 * torch.rand(n_reps, S, generator=gen)
+    over = torch._standard_gamma(torch.full((n_reps, S, G), 8.0), generator=gen) / 8.0  # overdispersion
+    X = torch.poisson(n_g[None, None, :] * s_rb[:, :, None] * growth[None] * over, generator=gen)
+    Xbc = torch.binomial(X, torch.full_like(X, 0.5), generator=gen)
+    p_edit = (pi_g[None, :] * torch.exp(mu_v[gv][None, :] * tt[:, None]) / growth)[None].expand_as(Xbc).contiguous()
+    edits = torch.binomial(Xbc, p_edit, generator=gen)
+    cond = [f"D{int(t)}" for t in times]
+    rows = [(f"rep{r}_{cond[j]}", f"rep{r}", cond[j], float(times[j]), 1) for r in range(n_reps) for j in range(S)]
+    samples = pd.DataFrame(rows, columns=["name", "replicate", "condition", "time", "mask"]).set_index("name")
+    width = max(6, len(str(T)))
+    tnames = np.char.add("v", np.char.zfill(np.arange(T).astype(str), width))
+    if n_negctrl_guides:
+        tnames[0] = "CONTROL"
+    guides = pd.DataFrame({
+        "target": tnames[gv.numpy()],
+        "target_group": np.where((gv.numpy() == 0) & (n_negctrl_guides > 0), "NegCtrl", "Variant"),
+    }, index=pd.Index(np.char.add("g", np.arange(G).astype(str)), name="name"))
+    guides["true_mu"] = mu_v[gv].numpy()
+    guides["true_pi"] = pi_g.numpy()
+    if accessibility:
+        guides["accessibility"] = torch.exp(1.0 + 0.8 * torch.randn(G, generator=gen)).numpy()
+
+    def flat(t):
+        return t.permute(2, 0, 1).reshape(G, -1).numpy().astype(np.float32)
+
+    return MiniScreen(flat(X), guides, samples, {"X_bcmatch": flat(Xbc), "edits": flat(edits)})

@@ -69,6 +69,30 @@ def sorting_cases(ns):
     ]
 
 
+def survival_cases(ns):
+    from crispr_bean_b200.synth import make_survival_screen
+
+    m, dc = ns.survival_model, ns.data_class
+    scr = make_survival_screen(10, 4, n_reps=3, seed=4, n_negctrl_guides=5, depth=150.0)
+    kw = dict(condition_column="condition", time_column="time", control_condition="D7")
+    negctrl = [0, 1, 2, 3, 4]  # what cli/run.py:98-101 passes as negctrl_guide_idx
+    return [
+        ("survival_normal", scr, dc.VariantSurvivalScreenData, dict(kw, negctrl_guide_idx=negctrl),
+         partial(m.NormalModel, use_bcmatch=False), m.NormalGuide, "Normal", dict(use_bcmatch=False)),
+        # without negctrl_guide_idx the reference's `mu[None, :] = 0.0` zeroes EVERY guide's growth rate (survival_model.py:59-60)
+        ("survival_normal_no_negctrl_idx", scr, dc.VariantSurvivalScreenData, kw,
+         partial(m.NormalModel, use_bcmatch=False), m.NormalGuide, "Normal", dict(use_bcmatch=False)),
+        ("survival_normal_bcmatch", scr, dc.VariantSurvivalScreenData, dict(kw, negctrl_guide_idx=negctrl, use_bcmatch=True),
+         partial(m.NormalModel, use_bcmatch=True), m.NormalGuide, "Normal", dict(use_bcmatch=True)),
+        ("survival_control_normal", scr, dc.VariantSurvivalScreenData, kw, partial(m.ControlNormalModel, use_bcmatch=False),
+         partial(m.ControlNormalGuide, use_bcmatch=False), "ControlNormal", dict(use_bcmatch=False)),
+        ("survival_mixture", scr, dc.VariantSurvivalReporterScreenData, kw, m.MixtureNormalModel, m.MixtureNormalGuide,
+         "MixtureNormal", {}),
+        ("survival_mixture_control_d0", scr, dc.VariantSurvivalReporterScreenData, dict(kw, control_condition="D0"),
+         m.MixtureNormalModel, m.MixtureNormalGuide, "MixtureNormal", {}),
+    ]
+
+
 def write_case(ns, name, screen, cls, data_kw, model, guide, oracle_model, oracle_kw, n_traj=0):
     data = cls(copy.deepcopy(screen), **data_kw)
     arrays = dict(G.screen_to_arrays(screen))
@@ -98,11 +122,17 @@ def trajectory(ns, model, guide, data, n_steps):
         tr = pyro.poutine.trace(guide).get_trace(d)  # inner trace: sees the same messages as SVI's own
         rec.append({k: v.double().numpy() for k, v in G.noise_from_guide_trace(pyro, tr).items()})
 
+    def recording_model(d):
+        tr = pyro.poutine.trace(model).get_trace(d)
+        site = tr.nodes.get("mu_negctrl")  # survival MixtureNormal: model-only latent, fresh prior draw every step
+        if site is not None and not site["is_observed"]:
+            rec[-1]["eps_negctrl"] = ((site["value"] - site["fn"].loc) / site["fn"].scale).detach().double().numpy()
+
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     try:
         torch.manual_seed(23)
-        store, hist = ns.run.run_inference(model, recording_guide, G.cast_floats(data, torch.float64), num_steps=n_steps)
+        store, hist = ns.run.run_inference(recording_model, recording_guide, G.cast_floats(data, torch.float64), num_steps=n_steps)
     finally:
         torch.set_default_dtype(old)
         torch.autograd.set_detect_anomaly(False)
@@ -116,8 +146,9 @@ def trajectory(ns, model, guide, data, n_steps):
 
 def main():
     ns = load_reference()
-    for case in sorting_cases(ns):
-        write_case(ns, *case, n_traj=6 if case[0] in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise") else 0)
+    traj = ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise", "survival_normal", "survival_mixture")
+    for case in sorting_cases(ns) + survival_cases(ns):
+        write_case(ns, *case, n_traj=6 if case[0] in traj else 0)
 
 
 if __name__ == "__main__":

@@ -66,6 +66,7 @@ def noise_from_guide_trace(pyro, gt):
     """Standardised reparameterisation noise behind the guide's draws (what the oracle / kernels inject)."""
     st = pyro.get_param_store()
     val = lambda k: gt.nodes[k]["value"].detach()
+    sampled = {k for k, site in gt.nodes.items() if site["type"] == "sample"}  # (param sites share the trace)
     noise = {}
     if "mu_targets" in gt:
         noise["eps_mu"] = (val("mu_targets") - st["mu_loc"].detach()) / st["mu_scale"].detach()
@@ -79,7 +80,7 @@ def noise_from_guide_trace(pyro, gt):
         else:
             noise["eps_noise"] = val("logit_pi_noise") / 0.655
     for k in ("initial_guide_abundance", "initial_abundance"):
-        if k in gt:
+        if k in sampled:
             noise["q0"] = val(k)
     return noise
 
@@ -110,6 +111,9 @@ def reference_loss_and_grads(pyro, model, guide, data, seed, dtype):
         for name, site in mt.nodes.items():  # model-only latents (drawn from the prior in the model)
             if site["type"] == "sample" and not site["is_observed"] and name not in gt:
                 noise[f"noise/model_only/{name}"] = site["value"].detach().double().numpy()
+                if name == "mu_negctrl":  # Normal(m0, s0) prior draw -> its standard-normal noise
+                    fn = site["fn"]
+                    noise["noise/eps_negctrl"] = ((site["value"] - fn.loc) / fn.scale).detach().double().numpy()
         return out, noise
     finally:
         torch.set_default_dtype(old)

@@ -10,10 +10,10 @@ import pytest
 import torch
 
 from crispr_bean_b200.svi import SviEngine
-from tests.test_reference_golden import SORTING, group, load_case
+from tests.test_reference_golden import PROGRAMS, SORTING, group, load_case
 
 pytestmark = pytest.mark.gpu
-FUSED = [c for c in SORTING]
+FUSED = list(PROGRAMS)  # sorting: fused SVI kernels; survival: bean_ll kernel inside the autograd engine
 
 
 def rel(got, ref):
@@ -25,6 +25,10 @@ def rel(got, ref):
 def make_engine(z, data, cuda_device, dtype, num_steps):
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     model = str(z["meta/oracle_model"])
+    if getattr(data, "is_survival", False):
+        from crispr_bean_b200.survival import SurvivalSviEngine
+
+        return SurvivalSviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True))
     return SviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True),
                      scale_by_accessibility=kw.get("scale_by_accessibility", False), fit_noise=kw.get("fit_noise", False),
                      prior_params=kw.get("prior_params"))
@@ -41,7 +45,7 @@ def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol
     noise = {k: torch.as_tensor(v) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
     got = eng.gradients(noise)
     ref_loss = float(z[f"{tag}/loss"])
-    if name == "control_normal_c1" and dtype == torch.float32:
+    if name in ("control_normal_c1", "survival_control_normal") and dtype == torch.float32:
         tol = 2e-4  # one global (mu, sd): its gradient is a 40x-cancelling sum of per-guide terms
     assert abs(got["loss"].item() - ref_loss) <= tol * abs(ref_loss), (got["loss"].item(), ref_loss)
     ref = group(z, f"{tag}/grad/")
@@ -53,7 +57,8 @@ def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol
         assert e <= (tol_alpha if k == "alpha_pi" else tol), f"{k}: {e:.3e}"
 
 
-@pytest.mark.parametrize("name", [c for c in FUSED if c in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise")])
+@pytest.mark.parametrize("name", [c for c in FUSED if c in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise",
+                                                              "survival_normal", "survival_mixture")])
 def test_fused_run_follows_reference_run_inference(cuda_device, name):
     z, data = load_case(name)
     n = int(z["traj/n_steps"])
@@ -62,6 +67,7 @@ def test_fused_run_follows_reference_run_inference(cuda_device, name):
     for t in range(n):
         eng.run(1, noise={k: torch.as_tensor(v[t]) for k, v in tn.items()})
     loss = eng.losses().numpy()
+    print(name, "traj loss err", np.abs(loss - z["traj/loss"]).max() / np.abs(z["traj/loss"]).max())
     assert np.abs(loss - z["traj/loss"]).max() <= 1e-9 * np.abs(z["traj/loss"]).max()
     params = eng.params()
     for k, v in group(z, "traj/param/").items():

@@ -15,6 +15,13 @@ from tests.refharness.golden import screen_from_arrays
 
 CASES = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
 SORTING = [c for c in CASES if not c.startswith(("survival", "tiling"))]
+SURVIVAL = [c for c in CASES if c.startswith("survival")]
+PROGRAMS = SORTING + SURVIVAL
+
+
+def elbo_fn(name, z):
+    table = O.SURVIVAL_ELBOS if name.startswith("survival") else O.SORTING_ELBOS
+    return table[str(z["meta/oracle_model"])]
 
 
 def load_case(name, reference_fits=True):
@@ -42,7 +49,7 @@ def rel(a, b):
 
 
 def test_golden_cases_exist():
-    assert len(CASES) >= 9
+    assert len(SORTING) >= 9 and len(SURVIVAL) >= 6
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -70,22 +77,22 @@ def test_tensoriser_equals_reference_data_class(name):
     assert not missing, f"tensors of the reference data class absent from the mirror: {missing}"
 
 
-def oracle_eval(z, data, tag, dtype):
+def oracle_eval(z, data, tag, dtype, name=""):
     noise = {k: torch.as_tensor(v).to(dtype) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     with default_dtype(dtype):
         d = cast_data(data, dtype) if dtype == torch.float64 else data
         ps = O.ParamStore()
-        loss, aux = O.SORTING_ELBOS[str(z["meta/oracle_model"])](d, ps, noise=noise, **kw)
+        loss, aux = elbo_fn(name, z)(d, ps, noise=noise, **kw)
         loss.backward()
     return float(loss.detach()), {k: v.grad.detach().double().numpy() for k, v in ps.unconstrained.items()}, ps
 
 
-@pytest.mark.parametrize("name", SORTING)
+@pytest.mark.parametrize("name", PROGRAMS)
 def test_oracle_equals_reference_programs_float64(name):
     """-ELBO and d(-ELBO)/d(unconstrained params) of the reference model/guide programs, float64, same noise."""
     z, data = load_case(name)
-    loss, grads, _ = oracle_eval(z, data, "f64", torch.float64)
+    loss, grads, _ = oracle_eval(z, data, "f64", torch.float64, name)
     assert abs(loss - float(z["f64/loss"])) <= 1e-11 * abs(float(z["f64/loss"]))
     ref_grads = group(z, "f64/grad/")
     assert set(grads) == set(ref_grads)
@@ -93,17 +100,17 @@ def test_oracle_equals_reference_programs_float64(name):
         assert rel(grads[k].reshape(g.shape), g) < 1e-9, k
 
 
-@pytest.mark.parametrize("name", SORTING)
+@pytest.mark.parametrize("name", PROGRAMS)
 def test_oracle_equals_reference_programs_native_precision(name):
     """Same in the reference's own mixed float32/float64 arithmetic (tolerance: float32 rounding)."""
     z, data = load_case(name)
-    loss, grads, _ = oracle_eval(z, data, "native", torch.float32)
+    loss, grads, _ = oracle_eval(z, data, "native", torch.float32, name)
     assert abs(loss - float(z["native/loss"])) <= 2e-6 * abs(float(z["native/loss"]))
     for k, g in group(z, "native/grad/").items():
         assert rel(grads[k].reshape(g.shape), g) < 2e-4, k
 
 
-@pytest.mark.parametrize("name", [c for c in SORTING if "traj/n_steps" in np.load(os.path.join(GOLDEN, f"ref_{c}.npz")).files])
+@pytest.mark.parametrize("name", [c for c in PROGRAMS if "traj/n_steps" in np.load(os.path.join(GOLDEN, f"ref_{c}.npz")).files])
 def test_oracle_run_inference_follows_reference_trajectory(name):
     """bean/model/run.py:run_inference (SVI + ClippedAdam, lr decay) for a few steps with the recorded draws."""
     z, data = load_case(name)
@@ -112,7 +119,7 @@ def test_oracle_run_inference_follows_reference_trajectory(name):
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     with default_dtype(torch.float64):
         d = cast_data(data, torch.float64)
-        ps, hist = O.run_inference(O.SORTING_ELBOS[str(z["meta/oracle_model"])], d, num_steps=n,
+        ps, hist = O.run_inference(elbo_fn(name, z), d, num_steps=n,
                                    noise_fn=lambda t: {k: torch.as_tensor(v[t]) for k, v in tn.items()}, **kw)
     assert rel(hist["loss"], z["traj/loss"]) < 1e-11
     for k, v in group(z, "traj/param/").items():
