@@ -317,13 +317,40 @@ class VariantSurvivalReporterScreenData(SurvivalScreenData):
                          control_can_be_selected=control_can_be_selected, sample_mask_column=sample_mask_column, **kwargs)
 
 
+_EDIT_RE = None
+_COMPLEMENT = {"A": "T", "C": "G", "T": "A", "G": "C", "-": "-"}
+
+
+def abs_edit_key(token: str) -> str:
+    """Identity of an edit across guides: the reference's `Edit.get_abs_edit()` (framework/Edit.py:75-87) computed
+    from the edit's string form `[chrom:]pos:rel_pos:strand:ref>alt` (optionally `uid!` in front): the sense-strand
+    base change at the absolute position -- the same edit seen from two overlapping guides has different `rel_pos`
+    but one key.  Tokens in any other format (e.g. amino-acid edits) are their own key."""
+    global _EDIT_RE
+    if _EDIT_RE is None:
+        import re
+
+        _EDIT_RE = re.compile(r"(?:(?P<uid>[\w*]+)!)?(?:(?P<chrom>(?:chr)?\w+|nan):)?(?P<pos>-?\d+):(?P<rel>-?\d+):(?P<strand>[+-]):"
+                              r"(?P<ref>[A-Z*-])>(?P<alt>[A-Z*-])")
+    m = _EDIT_RE.fullmatch(token)
+    if m is None:
+        return token
+    ref, alt = m["ref"], m["alt"]
+    if m["strand"] == "-":
+        ref, alt = _COMPLEMENT.get(ref, ref), _COMPLEMENT.get(alt, alt)
+    chrom = f"{m['chrom']}:" if m["chrom"] else ""
+    if m["uid"] is not None:
+        return f"{m['uid']}!{chrom}{int(m['rel'])}:{ref}>{alt}"
+    return f"{chrom}{int(m['pos'])}:{ref}>{alt}"
+
+
 class TilingSortingReporterScreenData(SortingScreenData):
     """data_class.py:536-872 + :1298-1355: tiling screens -- every guide has up to `n_max_alleles - 1` edited
     alleles, each a set of edits shared across guides (MultiMixtureNormal models).
 
     `screen.uns[allele_df_key]` is the filtered allele-count table `bean filter` writes: columns `guide`,
     `allele` | `aa_allele`, then one count column per sample.  An allele's edits are the comma-separated
-    tokens of `str(allele)` (the reference's `Allele.__str__`).  Emits the reference attributes
+    tokens of `str(allele)` (the reference's `Allele.__repr__`), identified across guides by `abs_edit_key`.  Emits the reference attributes
     (`n_edits, n_max_alleles, edit_index, allele_mask, allele_counts_control`, dense `allele_to_edit` on
     demand) plus the flat CSR `allele_ptr / allele_edit` the kernels use.  Vectorised: the reference's
     per-guide / per-allele Python loops (:696-698, :756-788, :868-871) are gone.
@@ -359,7 +386,7 @@ class TilingSortingReporterScreenData(SortingScreenData):
         aid = df.groupby("guide", sort=False).cumcount().to_numpy() + 1  # allele_id_for_guide, table order
         self.n_max_alleles = int(aid.max()) + 1 if len(aid) else 1
         A = self.n_max_alleles
-        tokens = [[t.strip() for t in str(a).split(",") if t.strip()] for a in df[col]]
+        tokens = [[abs_edit_key(t.strip()) for t in str(a).split(",") if t.strip()] for a in df[col]]
         self.edit_index = {}
         for ts in tokens:  # unique edits in order of first appearance (preprocessing/utils.py:149-173)
             for t in ts:
@@ -375,6 +402,7 @@ class TilingSortingReporterScreenData(SortingScreenData):
         np.maximum.at(n_valid, gi, aid)
         self.allele_mask = torch.as_tensor(np.arange(A)[None, :] <= n_valid[:, None])  # column 0 = WT always exists
         self.allele_counts_control = self._allele_tensor(self.screen_control, df, gi, aid, len(self.control_condition))
+        self.allele_counts = self._allele_tensor(self.screen_selected, df, gi, aid, self.n_condits)
 
     def _allele_tensor(self, scr, df, gi, aid, n_cond):
         """(R, n_cond, G, A) allele counts; WT = barcode-matched total minus the edited alleles, floored at 0."""

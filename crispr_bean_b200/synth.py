@@ -170,7 +170,8 @@ def make_tiling_screen(n_guides: int = 200, window: int = 6, max_alleles: int = 
         frac = frac_all[g]
         for j, pos in enumerate(alleles_of[g]):
             cnt = torch.binomial(Xbc[:, :, g], torch.full_like(Xbc[:, :, g], float(frac[j + 1])), generator=gen)  # (R, B+1)
-            table.append([f"g{g}", ",".join(f"{p}:A>G" for p in pos)] + cnt.reshape(-1).tolist())
+            # the reference's Edit string: "<abs pos>:<pos relative to the guide>:<strand>:<ref>><alt>" (framework/Edit.py:129-134)
+            table.append([f"g{g}", ",".join(f"{p}:{p - g}:+:A>G" for p in pos)] + cnt.reshape(-1).tolist())
     allele_df = pd.DataFrame(table, columns=["guide", "allele"] + sample_names)
     rows = []
     for r in range(n_reps):

@@ -93,9 +93,37 @@ def survival_cases(ns):
     ]
 
 
+def tiling_cases(ns):
+    from crispr_bean_b200.synth import make_tiling_screen
+
+    m, dc = ns.model, ns.data_class
+    out = []
+    for name, kw in (("tiling_small", dict(n_guides=40, n_reps=3, seed=2)), ("tiling_wide", dict(n_guides=30, n_reps=4, max_alleles=7, seed=6))):
+        scr = make_tiling_screen(**kw)
+        out.append((name, scr, dc.TilingSortingReporterScreenData, dict(control_can_be_selected=True, allele_df_key="allele_counts"),
+                    partial(m.MultiMixtureNormalModel, scale_by_accessibility=False, use_bcmatch=(True,)),
+                    partial(m.MultiMixtureNormalGuide, scale_by_accessibility=False, fit_noise=True), "MultiMixtureNormal", {}))
+    return out
+
+
+def with_allele_objects(ns, screen):
+    """The reference's tiling tensoriser works on `Allele` objects (bean/framework/Edit.py); the stored screen and
+    our tensoriser hold their string form."""
+    scr = copy.deepcopy(screen)
+    for key, tbl in scr.uns.items():
+        if hasattr(tbl, "columns") and "allele" in tbl.columns:
+            tbl = tbl.copy()
+            tbl["allele"] = tbl["allele"].map(ns.edit.Allele.from_str)
+            scr.uns[key] = tbl
+    return scr
+
+
 def write_case(ns, name, screen, cls, data_kw, model, guide, oracle_model, oracle_kw, n_traj=0):
-    data = cls(copy.deepcopy(screen), **data_kw)
+    data = cls(with_allele_objects(ns, screen), **data_kw)
     arrays = dict(G.screen_to_arrays(screen))
+    if hasattr(data, "edit_index"):  # set-iteration order of the reference: a labelling, stored so tests can align to it
+        keys = sorted(data.edit_index, key=data.edit_index.get)
+        arrays["meta/edit_index_keys"] = np.asarray(keys).astype(str)
     arrays.update({f"data/{k}": v for k, v in G.data_tensors(data).items()})
     arrays["meta/data_class"] = np.asarray(cls.__name__)
     arrays["meta/data_kwargs"] = np.asarray(repr(data_kw))
@@ -146,8 +174,9 @@ def trajectory(ns, model, guide, data, n_steps):
 
 def main():
     ns = load_reference()
-    traj = ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise", "survival_normal", "survival_mixture")
-    for case in sorting_cases(ns) + survival_cases(ns):
+    traj = ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise", "survival_normal", "survival_mixture",
+            "tiling_small")
+    for case in sorting_cases(ns) + survival_cases(ns) + tiling_cases(ns):
         write_case(ns, *case, n_traj=6 if case[0] in traj else 0)
 
 

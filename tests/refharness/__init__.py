@@ -4,7 +4,7 @@ for golden-vector generation and cross-checks.  TEST INFRASTRUCTURE ONLY; availa
 
 What is real and what is shimmed:
   real  (unmodified reference code): bean/model/{model,survival_model,utils,run,readwrite}.py,
-        bean/preprocessing/{data_class,get_alpha0,get_pi_alpha0,utils}.py
+        bean/preprocessing/{data_class,get_alpha0,get_pi_alpha0,utils}.py, bean/framework/Edit.py
   shim  pyro (tests/refharness/pyro: restated effect handlers, Trace_ELBO, ClippedAdam), `bean` top-level
         package (its __init__ imports anndata / perturb_tools, absent here), pyBigWig, bean.qc.guide_qc
 """
@@ -46,7 +46,7 @@ def load_reference():
     bean = pkg("bean", os.path.join(REFERENCE_ROOT, "bean"))
     bean.__refharness__ = True
     bean.ReporterScreen = object  # only used in annotations (data_class.py:38)
-    for sub in ("model", "preprocessing"):
+    for sub in ("model", "preprocessing", "framework", "utils"):
         setattr(bean, sub, pkg(f"bean.{sub}", os.path.join(REFERENCE_ROOT, "bean", sub)))
     qc = pkg("bean.qc", os.path.join(_HERE, "_absent"))
     gq = types.ModuleType("bean.qc.guide_qc")
@@ -60,7 +60,7 @@ def load_reference():
     for attr, mod in [("utils", "bean.model.utils"), ("data_class", "bean.preprocessing.data_class"),
                       ("get_alpha0", "bean.preprocessing.get_alpha0"), ("get_pi_alpha0", "bean.preprocessing.get_pi_alpha0"),
                       ("model", "bean.model.model"), ("survival_model", "bean.model.survival_model"),
-                      ("run", "bean.model.run"), ("readwrite", "bean.model.readwrite")]:
+                      ("run", "bean.model.run"), ("readwrite", "bean.model.readwrite"), ("edit", "bean.framework.Edit")]:
         setattr(ns, attr, importlib.import_module(mod))
     bean.__refharness_ns__ = ns
     return ns

@@ -27,6 +27,12 @@ def screen_to_arrays(scr, prefix="screen/"):
         for c in df.columns:
             col = df[c].to_numpy()
             out[f"{prefix}{tag}/col/{c}"] = col.astype(str) if col.dtype.kind in "OUS" else col
+    for key, tbl in scr.uns.items():  # per-allele count tables of tiling screens (values may be Allele objects -> str)
+        if isinstance(tbl, pd.DataFrame):
+            out[f"{prefix}uns/{key}/columns"] = np.asarray(list(tbl.columns)).astype(str)
+            for c in tbl.columns:
+                col = tbl[c].to_numpy()
+                out[f"{prefix}uns/{key}/col/{c}"] = np.asarray([str(v) for v in col]) if col.dtype.kind in "OUS" else col
     return out
 
 
@@ -39,7 +45,13 @@ def screen_from_arrays(z, prefix="screen/"):
         return pd.DataFrame({c: (v.astype(str) if v.dtype.kind in "US" else v) for c, v in cols.items()}, index=idx)
 
     layers = {k.split("layer/", 1)[1]: z[k] for k in z.files if k.startswith(prefix + "layer/")}
-    return MiniScreen(z[prefix + "X"], frame("guides"), frame("samples"), layers)
+    uns = {}
+    for k in z.files:
+        if k.startswith(prefix + "uns/") and k.endswith("/columns"):
+            key = k[len(prefix) + 4:-len("/columns")]
+            uns[key] = pd.DataFrame({c: (z[f"{prefix}uns/{key}/col/{c}"].astype(str) if z[f"{prefix}uns/{key}/col/{c}"].dtype.kind in "US"
+                                         else z[f"{prefix}uns/{key}/col/{c}"]) for c in z[k].astype(str)})
+    return MiniScreen(z[prefix + "X"], frame("guides"), frame("samples"), layers, uns)
 
 
 def data_tensors(data):

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from crispr_bean_b200.svi import SviEngine
-from tests.test_reference_golden import PROGRAMS, SORTING, group, load_case
+from tests.test_reference_golden import PROGRAMS, SORTING, edit_perm, group, load_case, to_ours
 
 pytestmark = pytest.mark.gpu
 FUSED = list(PROGRAMS)  # sorting: fused SVI kernels; survival: bean_ll kernel inside the autograd engine
@@ -25,6 +25,10 @@ def rel(got, ref):
 def make_engine(z, data, cuda_device, dtype, num_steps):
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     model = str(z["meta/oracle_model"])
+    if getattr(data, "is_tiling", False):
+        from crispr_bean_b200.generic import TilingSviEngine
+
+        return TilingSviEngine(data, cuda_device, dtype=dtype, num_steps=num_steps)
     if getattr(data, "is_survival", False):
         from crispr_bean_b200.survival import SurvivalSviEngine
 
@@ -42,7 +46,8 @@ def make_engine(z, data, cuda_device, dtype, num_steps):
 def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol, tol_alpha):
     z, data = load_case(name)
     eng = make_engine(z, data, cuda_device, dtype, 4)
-    noise = {k: torch.as_tensor(v) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
+    perm = edit_perm(z, data)
+    noise = {k: torch.as_tensor(to_ours(v, perm, k)) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
     got = eng.gradients(noise)
     ref_loss = float(z[f"{tag}/loss"])
     if name in ("control_normal_c1", "survival_control_normal") and dtype == torch.float32:
@@ -50,6 +55,7 @@ def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol
     assert abs(got["loss"].item() - ref_loss) <= tol * abs(ref_loss), (got["loss"].item(), ref_loss)
     ref = group(z, f"{tag}/grad/")
     assert set(ref) <= set(got), (sorted(ref), sorted(got))
+    ref = {k: to_ours(g, perm, k) for k, g in ref.items()}
     errs = {k: rel(got[k], g) for k, g in ref.items()}
     print(name, tag, "loss", abs(got["loss"].item() - ref_loss) / abs(ref_loss), errs)
     for k, g in ref.items():
@@ -58,12 +64,13 @@ def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol
 
 
 @pytest.mark.parametrize("name", [c for c in FUSED if c in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise",
-                                                              "survival_normal", "survival_mixture")])
+                                                              "survival_normal", "survival_mixture", "tiling_small")])
 def test_fused_run_follows_reference_run_inference(cuda_device, name):
     z, data = load_case(name)
     n = int(z["traj/n_steps"])
     eng = make_engine(z, data, cuda_device, torch.float64, n)
-    tn = group(z, "traj/noise/")
+    perm = edit_perm(z, data)
+    tn = {k: to_ours(v, perm, k) for k, v in group(z, "traj/noise/").items()}
     for t in range(n):
         eng.run(1, noise={k: torch.as_tensor(v[t]) for k, v in tn.items()})
     loss = eng.losses().numpy()
@@ -71,4 +78,4 @@ def test_fused_run_follows_reference_run_inference(cuda_device, name):
     assert np.abs(loss - z["traj/loss"]).max() <= 1e-9 * np.abs(z["traj/loss"]).max()
     params = eng.params()
     for k, v in group(z, "traj/param/").items():
-        assert rel(params[k], v) <= 1e-8, k
+        assert rel(params[k], to_ours(v, perm, k)) <= 1e-8, k

@@ -16,11 +16,13 @@ from tests.refharness.golden import screen_from_arrays
 CASES = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
 SORTING = [c for c in CASES if not c.startswith(("survival", "tiling"))]
 SURVIVAL = [c for c in CASES if c.startswith("survival")]
-PROGRAMS = SORTING + SURVIVAL
+TILING = [c for c in CASES if c.startswith("tiling")]
+PROGRAMS = SORTING + SURVIVAL + TILING
+EDIT_AXIS_KEYS = ("mu_loc", "mu_scale", "sd_loc", "sd_scale", "eps_mu", "eps_sd")  # (E,) arrays of the tiling model
 
 
 def elbo_fn(name, z):
-    table = O.SURVIVAL_ELBOS if name.startswith("survival") else O.SORTING_ELBOS
+    table = O.SURVIVAL_ELBOS if name.startswith("survival") else O.SORTING_ELBOS  # (tiling lives in SORTING_ELBOS)
     return table[str(z["meta/oracle_model"])]
 
 
@@ -37,6 +39,26 @@ def load_case(name, reference_fits=True):
             if f"data/{k}" in z.files and hasattr(data, k):
                 setattr(data, k, torch.as_tensor(z[f"data/{k}"]))
     return z, data
+
+
+def edit_perm(z, data):
+    """Tiling: position in OUR edit order of every edit of the reference's order.  The reference numbers edits in the
+    iteration order of Python sets of `Edit` objects (preprocessing/utils.py:149-173) -- a labelling that changes
+    from process to process -- so (E,) arrays are aligned through the edit keys before comparing."""
+    if "meta/edit_index_keys" not in z.files:
+        return None
+    keys = [str(k) for k in z["meta/edit_index_keys"]]
+    assert set(keys) == set(data.edit_index) and len(keys) == len(data.edit_index)
+    return np.asarray([data.edit_index[k] for k in keys])
+
+
+def to_ours(arr, perm, key):
+    """(E,)-shaped reference array (or a stack of them, E last) -> our edit order."""
+    if perm is None or key.split("/")[-1] not in EDIT_AXIS_KEYS:
+        return arr
+    out = np.empty_like(arr)
+    out[..., perm] = arr
+    return out
 
 
 def group(z, prefix):
@@ -67,6 +89,8 @@ def test_tensoriser_equals_reference_data_class(name):
             assert str(mine.dtype).replace("torch.", "") == str(v.dtype), (k, mine.dtype, v.dtype)
             if k in ("a0", "a0_bcmatch", "pi_a0"):  # closed-form OLS here vs curve_fit (ftol 1.5e-8) there
                 assert rel(mine.numpy(), v) < 1e-7, k
+            elif k == "allele_to_edit":
+                assert np.array_equal(mine.numpy()[:, :, edit_perm(z, data)], v), k
             else:
                 assert np.array_equal(mine.numpy(), v, equal_nan=True), k
         else:
@@ -78,7 +102,8 @@ def test_tensoriser_equals_reference_data_class(name):
 
 
 def oracle_eval(z, data, tag, dtype, name=""):
-    noise = {k: torch.as_tensor(v).to(dtype) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
+    perm = edit_perm(z, data)
+    noise = {k: torch.as_tensor(to_ours(v, perm, k)).to(dtype) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     with default_dtype(dtype):
         d = cast_data(data, dtype) if dtype == torch.float64 else data
@@ -96,8 +121,9 @@ def test_oracle_equals_reference_programs_float64(name):
     assert abs(loss - float(z["f64/loss"])) <= 1e-11 * abs(float(z["f64/loss"]))
     ref_grads = group(z, "f64/grad/")
     assert set(grads) == set(ref_grads)
+    perm = edit_perm(z, data)
     for k, g in ref_grads.items():
-        assert rel(grads[k].reshape(g.shape), g) < 1e-9, k
+        assert rel(grads[k].reshape(g.shape), to_ours(g, perm, k)) < 1e-9, k
 
 
 @pytest.mark.parametrize("name", PROGRAMS)
@@ -106,8 +132,9 @@ def test_oracle_equals_reference_programs_native_precision(name):
     z, data = load_case(name)
     loss, grads, _ = oracle_eval(z, data, "native", torch.float32, name)
     assert abs(loss - float(z["native/loss"])) <= 2e-6 * abs(float(z["native/loss"]))
+    perm = edit_perm(z, data)
     for k, g in group(z, "native/grad/").items():
-        assert rel(grads[k].reshape(g.shape), g) < 2e-4, k
+        assert rel(grads[k].reshape(g.shape), to_ours(g, perm, k)) < 2e-4, k
 
 
 @pytest.mark.parametrize("name", [c for c in PROGRAMS if "traj/n_steps" in np.load(os.path.join(GOLDEN, f"ref_{c}.npz")).files])
@@ -115,7 +142,8 @@ def test_oracle_run_inference_follows_reference_trajectory(name):
     """bean/model/run.py:run_inference (SVI + ClippedAdam, lr decay) for a few steps with the recorded draws."""
     z, data = load_case(name)
     n = int(z["traj/n_steps"])
-    tn = group(z, "traj/noise/")
+    perm = edit_perm(z, data)
+    tn = {k: to_ours(v, perm, k) for k, v in group(z, "traj/noise/").items()}
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     with default_dtype(torch.float64):
         d = cast_data(data, torch.float64)
@@ -123,7 +151,7 @@ def test_oracle_run_inference_follows_reference_trajectory(name):
                                    noise_fn=lambda t: {k: torch.as_tensor(v[t]) for k, v in tn.items()}, **kw)
     assert rel(hist["loss"], z["traj/loss"]) < 1e-11
     for k, v in group(z, "traj/param/").items():
-        assert rel(hist["params"][k].numpy().reshape(v.shape), v) < 1e-9, k
+        assert rel(hist["params"][k].numpy().reshape(v.shape), to_ours(v, perm, k)) < 1e-9, k
 
 
 def test_live_reference_matches_committed_vectors():
