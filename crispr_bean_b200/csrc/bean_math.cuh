@@ -104,7 +104,7 @@ __device__ __forceinline__ void gamma_corr(double z, double& cv, double& dl) {
 
 // full lgamma / digamma of one argument (off the hot row loop: Dirichlet normalisers)
 template <typename real>
-__device__ __forceinline__ void lgamma_digamma(real z, real& lg, real& dg) {
+__device__ __noinline__ void lgamma_digamma(real z, real& lg, real& dg) {
   real cv, dl;
   gamma_corr(z, cv, dl);
   const real lz = Num<real>::log(z);
@@ -145,7 +145,7 @@ __device__ __forceinline__ void bin_prob_sorting(double thr_u, double thr_l, dou
 // float: the same mass written with erfc on the tail side, Q(z) = erfc(z / sqrt 2) / 2, so that a bin far
 // in a tail keeps its RELATIVE accuracy (0.5 (1 + erf) in float loses it below ~1e-3 and that error is
 // amplified by a0 / sum(p) downstream).
-__device__ __forceinline__ void bin_prob_sorting(float thr_u, float thr_l, float mu, float sd, float& P,
+static __device__ __noinline__ void bin_prob_sorting(float thr_u, float thr_l, float mu, float sd, float& P,
                                                  float& dP_dmu, float& dP_dsd) {
   const float rs = 1.0f / sd;
   const bool hu = !isinf(thr_u), hl = !isinf(thr_l);

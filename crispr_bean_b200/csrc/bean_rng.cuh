@@ -286,40 +286,39 @@ static __device__ __noinline__ double beta_grad_mid_f64(double x, double alpha, 
   return beta_grad_alpha_mid<double>(x, alpha, beta);
 }
 
-// Both components of a two-allele draw at once: g0 = dirichlet_grad_one(x0, a, a + b), g1 = dirichlet_grad_one(x1, b, a + b).
-// When both land in the saddle-point regime (the common case once concentrations exceed 6) the two evaluations
-// share everything expensive: the roles of (alpha, L1) and (beta, L2) just swap, q = 2ab/T, the Stirling factor and
-// term4 = (b L2 + a L1)^-1.5 are symmetric.  Component 1 is evaluated at 1 - x0 throughout (x1 differs from it by one
-// rounding of the sample: a smooth perturbation of the argument, not amplified by the formula's cancellation).
+// ---- the two components of a two-allele (Beta) draw --------------------------------------------------------------
+// g0 = dirichlet_grad_one(x0, a, a + b), g1 = dirichlet_grad_one(x1, b, a + b).
 //
-// FLOAT_TAILS (the float kernels): the other three regimes of torch's approximation -- the two boundary series and
-// the rational correction -- carry no cancellation, so they are evaluated in float (1e-6 relative, against the
-// fp32 path's 2e-4 budget for this gradient).  They are the minority of draws but, being divergent, they would
-// otherwise dominate warp time: a double series of 10 terms with 2 divisions each, 2 digamma recurrences and a
-// double pow cost ~10x the saddle-point path, and 3 % of such guides already put one in 60 % of the warps
-// (measured: 1.3 -> 4.3 ms/step once alpha_pi has fitted the low editing rates).
-template <bool FLOAT_TAILS>
-__device__ __noinline__ void dirichlet_grad_pair(double x0, double x1, double a, double b, double& g0, double& g1) {
+// Regimes.  Once both concentrations exceed 6 nearly every draw lands in torch's saddle-point regime for BOTH
+// components; there the two evaluations share everything expensive (`dirichlet_pair_saddle_f64`).  The other three
+// regimes (two boundary series, the rational correction) are the minority of draws -- but a 3 % minority already puts
+// one in 60 % of the warps, and evaluated in place they cost 40 % of the step: 1-2 active lanes walk through ~1,000
+// instructions of cold code per replicate (measured: 1.84 vs 1.11 ms/step with the tails artificially skipped).  So
+// the SVI kernel does not evaluate them in place: `dirichlet_pair_is_saddle` routes a draw either to the shared
+// saddle-point evaluation or into a per-warp queue in shared memory (`TailQueue`), which is flushed with all lanes busy
+// when 32 requests have gathered and once after the replicate loop.
+
+// true  <=>  both components are in the saddle-point regime (torch's dirichlet_grad_one branch order)
+__device__ __forceinline__ bool dirichlet_pair_is_saddle(double x0, double x1, double a, double b) {
   const double T = a + b;
   const double bnd0 = T * x0 * (1.0 - x0), bnd1 = T * x1 * (1.0 - x1);
   const bool big = a > 6.0 && b > 6.0;
   const bool mid0 = big && !(x0 <= 0.5 && bnd0 < 2.5) && !(x0 >= 0.5 && bnd0 < 0.75);
   const bool mid1 = big && !(x1 <= 0.5 && bnd1 < 2.5) && !(x1 >= 0.5 && bnd1 < 0.75);
+  return mid0 && mid1;
+}
+
+// Both components in the saddle-point regime: the roles of (alpha, L1) and (beta, L2) just swap between them, and
+// q = 2ab/T, the Stirling factor and term4 = (b L2 + a L1)^-1.5 are symmetric.  Component 1 is evaluated at 1 - x0
+// throughout (x1 differs from it by one rounding of the sample: a smooth perturbation of the argument, not amplified by
+// the formula's cancellation).
+static __device__ __noinline__ void dirichlet_pair_saddle_f64(double x0, double x1, double a, double b, double& g0, double& g1) {
+  const double T = a + b;
   const double iT = 1.0 / T;
   const double m0 = a * iT, m1 = b * iT;
   const double d0 = x0 - m0, d1 = x1 - m1;
-  if (!(mid0 && mid1)) {  // any other regime: the generic per-component evaluation
-    if (FLOAT_TAILS) {
-      g0 = mid0 ? beta_grad_mid_f64(x0, a, b) : (double)dirichlet_grad_tail_f32((float)x0, (float)a, (float)T);
-      g1 = mid1 ? beta_grad_mid_f64(x1, b, a) : (double)dirichlet_grad_tail_f32((float)x1, (float)b, (float)T);
-    } else {
-      g0 = dirichlet_grad_one_f64(x0, a, T);
-      g1 = dirichlet_grad_one_f64(x1, b, T);
-    }
-    return;
-  }
   // |x - mean| <= 0.1 std: torch switches to a polynomial there (8 % of draws, so nearly every warp has such a
-  // lane: keep it inside this path, per component, instead of diverging into the generic evaluation)
+  // lane: it stays inside this path, per component)
   const double lim = 0.01 * a * b, w = (T + 1.0) * T * T;
   const bool near0 = d0 * d0 * w <= lim, near1 = d1 * d1 * w <= lim;
   const double q = 2.0 * a * b * iT;
@@ -352,6 +351,58 @@ __device__ __noinline__ void dirichlet_grad_pair(double x0, double x1, double a,
   }
   if (near0) g0 = beta_grad_mid_near_mean(x0, a, b, iT);
   if (near1) g1 = beta_grad_mid_near_mean(x1, b, a, iT);
+}
+
+// One component, any regime.  FLOAT_TAILS (the float kernels): the three regimes without cancellation are evaluated in
+// float (1e-6 relative, against the fp32 path's 2e-4 budget for this gradient); the saddle-point regime stays double.
+template <bool FLOAT_TAILS>
+__device__ __forceinline__ double dirichlet_grad_any(double x, double alpha, double beta) {
+  if (!FLOAT_TAILS) return dirichlet_grad_one_f64(x, alpha, alpha + beta);
+  const double T = alpha + beta, bnd = T * x * (1.0 - x);
+  const bool mid = alpha > 6.0 && beta > 6.0 && !(x <= 0.5 && bnd < 2.5) && !(x >= 0.5 && bnd < 0.75);
+  return mid ? beta_grad_mid_f64(x, alpha, beta) : (double)dirichlet_grad_tail_f32((float)x, (float)alpha, (float)T);
+}
+
+// Per-warp queue of deferred (non-saddle) draws.  Entry: the draw (x0, x1), the guide's concentrations (a, b), the
+// upstream weights (w0, w1) = (go - gbar) of the two components and the owning lane.  `flush` evaluates the requests
+// with every lane of the warp busy, then each owner adds its own results in queue order (deterministic).
+template <typename real>
+struct TailQueue {
+  static constexpr int CAP = 64;  // flushed as soon as it holds >= 32, a push adds <= 32
+  real x0[CAP], x1[CAP], a[CAP], b[CAP], w0[CAP], w1[CAP];
+  int owner[CAP];
+};
+
+template <typename real>
+__device__ __forceinline__ int tail_queue_push(TailQueue<real>& q, int count, unsigned wmask, int lane, bool need, real x0, real x1,
+                                               real a, real b, real w0, real w1) {
+  const unsigned m = __ballot_sync(wmask, need);
+  if (need) {
+    const int j = count + __popc(m & ((1u << lane) - 1u));
+    q.x0[j] = x0; q.x1[j] = x1; q.a[j] = a; q.b[j] = b; q.w0[j] = w0; q.w1[j] = w1;
+    q.owner[j] = lane;
+  }
+  return count + __popc(m);
+}
+
+template <typename real>
+static __device__ __noinline__ void tail_queue_flush(TailQueue<real>& q, int n, unsigned wmask, int lane, real& acc0, real& acc1) {
+  __syncwarp(wmask);
+  const int rank = __popc(wmask & ((1u << lane) - 1u)), width = __popc(wmask);
+  for (int j = rank; j < n; j += width) {
+    const double x0 = (double)q.x0[j], x1 = (double)q.x1[j], a = (double)q.a[j], b = (double)q.b[j];
+    const double g0 = dirichlet_grad_any<sizeof(real) == 4>(x0, a, b);
+    const double g1 = dirichlet_grad_any<sizeof(real) == 4>(x1, b, a);
+    q.w0[j] = real(g0 * (double)q.w0[j]);
+    q.w1[j] = real(g1 * (double)q.w1[j]);
+  }
+  __syncwarp(wmask);
+  for (int j = 0; j < n; ++j)
+    if (q.owner[j] == lane) {
+      acc0 += q.w0[j];
+      acc1 += q.w1[j];
+    }
+  __syncwarp(wmask);
 }
 
 }  // namespace bean

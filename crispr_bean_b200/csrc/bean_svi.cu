@@ -113,11 +113,16 @@ __device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, re
 
 template <typename real, int NB, bool MIXTURE, bool ACC>
 __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
+  __shared__ TailQueue<real> tail_queues[SVI_THREADS / SVI_WARP];
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = p.B;
   const real eps = real(1e-5);
   double elbo = 0.0;
+  const int lane = threadIdx.x & 31;
+  const unsigned wmask = __ballot_sync(0xffffffffu, g < p.G);  // lanes that own a guide: the warp-collective set below
   if (g < p.G) {
+    TailQueue<real>& tq = tail_queues[threadIdx.x / SVI_WARP];
+    int n_tail = 0;
     const int v = p.guide_variant[g];
     real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd;
     variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd);
@@ -293,15 +298,26 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         // evaluated in double even on the float path, as torch's CPU kernel does (accscalar_t = double):
         // the saddle-point branch cancels badly in float
         const double gbar = (double)pi0 * (double)go0 + (double)pi1 * (double)go1;
-        double dg0, dg1;
-        dirichlet_grad_pair<sizeof(real) == 4>((double)pi0, (double)pi1, (double)cg[0], (double)cg[1], dg0, dg1);
-        dcg[0] += real(dg0 * ((double)go0 - gbar));
-        dcg[1] += real(dg1 * ((double)go1 - gbar));
+        const double w0 = (double)go0 - gbar, w1 = (double)go1 - gbar;
+        const bool saddle = dirichlet_pair_is_saddle((double)pi0, (double)pi1, (double)cg[0], (double)cg[1]);
+        if (saddle) {
+          double dg0, dg1;
+          dirichlet_pair_saddle_f64((double)pi0, (double)pi1, (double)cg[0], (double)cg[1], dg0, dg1);
+          dcg[0] += real(dg0 * w0);
+          dcg[1] += real(dg1 * w1);
+        }
+        // every other regime is deferred: queued per warp, evaluated with all lanes busy (bean_rng.cuh, TailQueue)
+        n_tail = tail_queue_push(tq, n_tail, wmask, lane, !saddle, pi0, pi1, cg[0], cg[1], real(w0), real(w1));
+        if (n_tail >= 32) {
+          tail_queue_flush(tq, n_tail, wmask, lane, dcg[0], dcg[1]);
+          n_tail = 0;
+        }
       } else {
 #pragma unroll
         for (int b = 0; b < NB; ++b) dP[b] += de[b];
       }
     }
+    if (MIXTURE && n_tail > 0) tail_queue_flush(tq, n_tail, wmask, lane, dcg[0], dcg[1]);
     // per-guide gradient w.r.t. the edited allele's (mu, sd_targets); reduced per variant by the next kernel
     real dmu = real(0), dsg = real(0);
 #pragma unroll
