@@ -172,8 +172,21 @@ def trajectory(ns, model, guide, data, n_steps):
     return out
 
 
+def result_table_golden(ns):
+    """The reference's `write_result_table` (bean/model/readwrite.py, real code) on fixed synthetic parameters."""
+    import tempfile
+
+    from tests.test_result_table import CASES, run
+
+    with tempfile.TemporaryDirectory() as tmp:
+        table, _ = run(ns.readwrite.write_result_table, CASES[0], tmp)
+    table.to_csv(os.path.join(HERE, "ref_result_table.csv"), float_format="%.17g")
+    print("ref_result_table.csv", table.shape)
+
+
 def main():
     ns = load_reference()
+    result_table_golden(ns)
     traj = ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise", "survival_normal", "survival_mixture",
             "tiling_small")
     for case in sorting_cases(ns) + survival_cases(ns) + tiling_cases(ns):

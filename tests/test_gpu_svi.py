@@ -235,3 +235,41 @@ def test_sharded_run_reproduces_unsharded_run(cuda_device):
     assert torch.equal(torch.cat(mu), full.params()["mu_loc"])
     assert torch.equal(torch.cat(alpha), full.params()["alpha_pi"])
     torch.testing.assert_close(loss, full.losses(), rtol=1e-12, atol=0)
+
+
+def test_end_to_end_result_table_equals_oracle_run(cuda_device):
+    """North-star end-to-end check: `run_inference`-style run on the GPU with its OWN Philox draws (recorded per step),
+    replayed into the oracle's SVI loop -> posterior mu / sd within 1e-8 (fp64), and the `bean_element_result` table
+    built from both has the identical variant ranking and z-scores."""
+    import pandas as pd
+
+    from crispr_bean_b200.readwrite import write_result_table
+
+    data = H.make_small_mixture_data(n_variants=40, n_reps=3, seed=12)
+    steps = 60
+    eng = SviEngine(data, "MixtureNormal", cuda_device, dtype=torch.float64, num_steps=steps, seed=5)
+    draws = []
+    for _ in range(steps):
+        eng.run(1, noise={"record": True})
+        eps, pi = eng.eps_used.double().cpu(), eng.pi_used.double().cpu()
+        draws.append({"eps_mu": eps[0].reshape(-1, 1), "eps_sd": eps[1].reshape(-1, 1), "pi": pi.permute(1, 0, 2).unsqueeze(1)})
+    with H.default_dtype(torch.float64):
+        ps, hist = O.run_inference(O.elbo_mixture_normal, H.cast_data(data, torch.float64), num_steps=steps,
+                                   noise_fn=lambda t: draws[t])
+    got = {k: v.detach().cpu() for k, v in eng.params().items()}
+    assert max(abs(a - b) / abs(b) for a, b in zip(eng.losses().tolist(), hist["loss"])) <= 1e-9
+    for k, v in hist["params"].items():
+        assert rel_err(got[k], v) <= 1e-8, k
+    T = data.n_targets
+    info = pd.DataFrame({"n": range(T)}, index=pd.Index([f"v{i}" for i in range(T)], name="target"))
+    ginfo = pd.DataFrame({"x": range(data.n_guides)})
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        kw = dict(model_label="MixtureNormal", prefix=f"{tmp}/", adjust_confidence_by_negative_control=True,
+                  adjust_confidence_negatives=list(range(10)), return_result=True)
+        tab_gpu = write_result_table(info.copy(), ginfo.copy(), got, **kw)
+        tab_ref = write_result_table(info.copy(), ginfo.copy(), hist["params"], **kw)
+    assert list(tab_gpu["target"]) == list(tab_ref["target"])  # identical ranking
+    for c in ("mu", "mu_sd", "mu_z", "sd", "mu_z_adj"):
+        assert (tab_gpu[c] - tab_ref[c]).abs().max() <= 1e-7 * tab_ref[c].abs().max(), c
