@@ -321,11 +321,13 @@ _EDIT_RE = None
 _COMPLEMENT = {"A": "T", "C": "G", "T": "A", "G": "C", "-": "-"}
 
 
-def abs_edit_key(token: str) -> str:
+def abs_edit_key(token: str, uid: Optional[str] = None) -> str:
     """Identity of an edit across guides: the reference's `Edit.get_abs_edit()` (framework/Edit.py:75-87) computed
     from the edit's string form `[chrom:]pos:rel_pos:strand:ref>alt` (optionally `uid!` in front): the sense-strand
     base change at the absolute position -- the same edit seen from two overlapping guides has different `rel_pos`
-    but one key.  Tokens in any other format (e.g. amino-acid edits) are their own key."""
+    but one key.  With a `uid` (`control_guide_tag`: edits of control guides are made unique to their guide,
+    data_class.py:604-614) the key is guide-relative instead.  Tokens in any other format (e.g. amino-acid edits) are
+    their own key."""
     global _EDIT_RE
     if _EDIT_RE is None:
         import re
@@ -339,13 +341,14 @@ def abs_edit_key(token: str) -> str:
     if m["strand"] == "-":
         ref, alt = _COMPLEMENT.get(ref, ref), _COMPLEMENT.get(alt, alt)
     chrom = f"{m['chrom']}:" if m["chrom"] else ""
-    if m["uid"] is not None:
-        return f"{m['uid']}!{chrom}{int(m['rel'])}:{ref}>{alt}"
+    uid = uid if uid is not None else m["uid"]
+    if uid is not None:
+        return f"{uid}!{chrom}{int(m['rel'])}:{ref}>{alt}"
     return f"{chrom}{int(m['pos'])}:{ref}>{alt}"
 
 
-class TilingSortingReporterScreenData(SortingScreenData):
-    """data_class.py:536-872 + :1298-1355: tiling screens -- every guide has up to `n_max_alleles - 1` edited
+class _TilingReporterMixin:
+    """data_class.py:536-872 + :1298-1355 / :1487-1537: tiling screens -- every guide has up to `n_max_alleles - 1` edited
     alleles, each a set of edits shared across guides (MultiMixtureNormal models).
 
     `screen.uns[allele_df_key]` is the filtered allele-count table `bean filter` writes: columns `guide`,
@@ -359,13 +362,11 @@ class TilingSortingReporterScreenData(SortingScreenData):
     is_reporter = True
     is_tiling = True
 
-    def __init__(self, screen, *args, condition_column="bin", sample_mask_column="mask", allele_df_key=None,
-                 allele_col=None, control_guide_tag=None, **kwargs):
+    def _tiling_args(self, allele_df_key, allele_col, control_guide_tag, kwargs):
         if allele_df_key is None:
             raise ValueError("tiling screens need allele_df_key (a table in screen.uns)")
-        self._allele_df_key, self._allele_col = allele_df_key, allele_col
+        self._allele_df_key, self._allele_col, self._control_guide_tag = allele_df_key, allele_col, control_guide_tag
         kwargs["target_col"] = None
-        super().__init__(screen, *args, condition_column=condition_column, sample_mask_column=sample_mask_column, **kwargs)
 
     def _reporter_init(self, impute_pi_popt=False):
         self._tiling_init()
@@ -386,7 +387,11 @@ class TilingSortingReporterScreenData(SortingScreenData):
         aid = df.groupby("guide", sort=False).cumcount().to_numpy() + 1  # allele_id_for_guide, table order
         self.n_max_alleles = int(aid.max()) + 1 if len(aid) else 1
         A = self.n_max_alleles
-        tokens = [[abs_edit_key(t.strip()) for t in str(a).split(",") if t.strip()] for a in df[col]]
+        tag = self._control_guide_tag
+        uids = [g if (tag is not None and tag in str(g)) else None for g in df["guide"]]
+        if tag is not None and not any(u is not None for u in uids):
+            raise AssertionError("uid not assinged.")  # the reference's check (data_class.py:611-613)
+        tokens = [[abs_edit_key(t.strip(), u) for t in str(a).split(",") if t.strip()] for a, u in zip(df[col], uids)]
         self.edit_index = {}
         for ts in tokens:  # unique edits in order of first appearance (preprocessing/utils.py:149-173)
             for t in ts:
@@ -426,6 +431,25 @@ class TilingSortingReporterScreenData(SortingScreenData):
         raise NotImplementedError("guide subsetting of tiling screens")
 
 
+class TilingSortingReporterScreenData(_TilingReporterMixin, SortingScreenData):
+    """Tiling sorting screens (data_class.py:1298-1355)."""
+
+    def __init__(self, screen, *args, condition_column="bin", sample_mask_column="mask", allele_df_key=None,
+                 allele_col=None, control_guide_tag=None, **kwargs):
+        self._tiling_args(allele_df_key, allele_col, control_guide_tag, kwargs)
+        super().__init__(screen, *args, condition_column=condition_column, sample_mask_column=sample_mask_column, **kwargs)
+
+
+class TilingSurvivalReporterScreenData(_TilingReporterMixin, SurvivalScreenData):
+    """Tiling proliferation screens (data_class.py:1487-1537)."""
+
+    def __init__(self, screen, *args, condition_column="condition", time_column="time", control_can_be_selected=True,
+                 sample_mask_column="mask", allele_df_key=None, allele_col=None, control_guide_tag=None, **kwargs):
+        self._tiling_args(allele_df_key, allele_col, control_guide_tag, kwargs)
+        super().__init__(screen, *args, condition_column=condition_column, time_column=time_column,
+                         control_can_be_selected=control_can_be_selected, sample_mask_column=sample_mask_column, **kwargs)
+
+
 DATACLASS_DICT = {
     "sorting": {
         "Normal": VariantSortingScreenData,
@@ -443,5 +467,7 @@ DATACLASS_DICT = {
         "_MixtureNormal": VariantSurvivalReporterScreenData,
         "MixtureNormal+Acc": VariantSurvivalReporterScreenData,
         "_MixtureNormal+Acc": VariantSurvivalReporterScreenData,
+        "MultiMixtureNormal": TilingSurvivalReporterScreenData,
+        "MultiMixtureNormal+Acc": TilingSurvivalReporterScreenData,
     },
 }

@@ -32,6 +32,7 @@ class _DirichletRsample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, concentration, injected, generator):
         x = injected.to(concentration.dtype) if injected is not None else torch._sample_dirichlet(concentration.contiguous(), generator)
+        x = x.to(concentration.device)
         ctx.save_for_backward(x, concentration)
         return x.clone()
 
@@ -67,6 +68,45 @@ class AutogradSviEngine:
         if noise is not None and key in noise:
             return noise[key].to(device=self.device, dtype=self.dtype).reshape(shape)
         return torch.randn(shape, generator=self.gen, device=self.device, dtype=self.dtype)
+
+    # -- --scale-by-acc (bean/model/utils.py:79-178) ---------------------------------------------------
+    def _acc_init(self, data, theta, positive, fit_noise):
+        """Accessibility factor exp(b) acc^a (a = 0.2513, b = -1.9458) and, with fit_noise, the guide's
+        (noise_loc, noise_scale) parameters of the logit-space noise site (initial values utils.py:146-151)."""
+        if getattr(data, "guide_accessibility", None) is None:
+            raise ValueError("scale_by_accessibility needs data.guide_accessibility (accessibility_col)")
+        acc = torch.as_tensor(data.guide_accessibility).double()
+        self.acc_k = (math.exp(-1.9458) * acc.pow(0.2513)).to(device=self.device, dtype=self.dtype)
+        self.fit_noise = bool(fit_noise)
+        if self.fit_noise:
+            G = acc.numel()
+            theta["noise_loc"] = torch.zeros(G, device=self.device, dtype=self.dtype)
+            theta["noise_scale"] = torch.full((G,), PI_NOISE_SD, dtype=torch.float64).log().to(device=self.device, dtype=self.dtype)
+            positive.add("noise_scale")
+
+    def _acc_apply(self, pi, noise):
+        """pi (R, 1, G, A) -> accessibility-scaled, logit-noised pi; returns (pi, model_lp, guide_lp) of the
+        `logit_pi_noise` site.  The model never receives fit_noise: its density is the prior."""
+        kw = dict(device=self.device, dtype=self.dtype)
+        G = pi.shape[2]
+        eps = self._draw(noise, "eps_noise", (G,))
+        prior = tdist.Normal(torch.zeros((), **kw), torch.full((), PI_NOISE_SD, **kw))
+        if self.fit_noise:
+            loc, scale = self.theta["noise_loc"], self.theta["noise_scale"].exp()
+            val = loc + scale * eps
+            guide_lp = tdist.Normal(loc, scale).log_prob(val).sum()
+        else:
+            val = PI_NOISE_SD * eps
+            guide_lp = prior.log_prob(val).sum()
+        model_lp = prior.log_prob(val).sum()
+        scaled = pi[..., 1:] * self.acc_k.reshape(1, 1, G, 1)                       # _scale_edited_pi
+        full = torch.cat([(1 - scaled.sum(-1)).unsqueeze(-1), scaled], dim=-1)
+        full = full / full.sum(-1).clamp(min=1.0).unsqueeze(-1)                      # only if the edited rates exceed 1
+        logit = torch.logit(full[..., 1:].clamp(min=1e-3, max=1 - 1e-3)) + val.reshape(1, 1, G, 1)   # add_noise_to_pi
+        ex = torch.exp(logit)
+        noised = (ex / (1 + ex)).clamp(min=1e-3, max=1 - 1e-3)
+        out = torch.cat([(1 - noised.sum(-1)).unsqueeze(-1), noised], dim=-1)       # WT may go negative (App. B10)
+        return out, model_lp, guide_lp
 
     def _adam(self):
         """pyro.optim.ClippedAdam on the unconstrained tensors."""
@@ -113,7 +153,8 @@ class TilingSviEngine(AutogradSviEngine):
     """MultiMixtureNormal on one GPU.  Parameter names / shapes follow the pyro guide (model.py:893-937)."""
 
     def __init__(self, data, device="cuda", dtype=torch.float32, use_bcmatch=True, num_steps=2000, initial_lr=0.01,
-                 gamma=0.1, seed=101, alpha_prior=1.0, sd_scale=0.01, epsilon=EPS, prior_params: Optional[dict] = None):
+                 gamma=0.1, seed=101, alpha_prior=1.0, sd_scale=0.01, epsilon=EPS, prior_params: Optional[dict] = None,
+                 scale_by_accessibility: bool = False, fit_noise: bool = False):
         if not torch.cuda.is_available():
             raise BeanError("TilingSviEngine needs a CUDA device: there is no CPU fallback")
         self.device, self.dtype = torch.device(device), dtype
@@ -123,7 +164,9 @@ class TilingSviEngine(AutogradSviEngine):
         self.amap = AlleleMap(data.allele_ptr.numpy(), data.allele_edit.numpy(), self.G, self.A, self.E, self.device)
         self.allele_mask = data.allele_mask.to(self.device)
         self.allele_mask_u8 = self.allele_mask.to(torch.uint8).contiguous()
-        self.pi_a0 = torch.as_tensor(data.pi_a0).to(**kw)
+        # pi_a0 keeps its own dtype (float64 out of the a0 fit): as in the reference, the editing-rate concentrations and
+        # the pi draws are then float64 even on the float32 path (draws of non-existent alleles underflow float32)
+        self.pi_a0 = torch.as_tensor(data.pi_a0).to(self.device)
         self.allele_counts_control = data.allele_counts_control.to(**kw)  # (R, C, G, A)
         self.rg_mask = data.repguide_mask.to(self.device).unsqueeze(1)  # (R, 1, G)
         self.epsilon, self.sd_scale, self.prior_params = epsilon, sd_scale, prior_params
@@ -132,7 +175,11 @@ class TilingSviEngine(AutogradSviEngine):
         z = lambda *s: torch.zeros(s, **kw)
         # unconstrained parameters (positive ones as log), initial values of model.py:893-937
         theta = {"mu_loc": z(self.E), "mu_scale": z(self.E), "sd_loc": z(self.E), "sd_scale": z(self.E), "alpha_pi": a0.log()}
-        self._init_optim(theta, {"mu_scale", "sd_scale", "alpha_pi"}, num_steps, initial_lr, gamma, seed)
+        positive = {"mu_scale", "sd_scale", "alpha_pi"}
+        self.acc = bool(scale_by_accessibility)
+        if self.acc:
+            self._acc_init(data, theta, positive, fit_noise)
+        self._init_optim(theta, positive, num_steps, initial_lr, gamma, seed)
 
     # ---------------------------------------------------------------------------------------------
     def elbo_loss(self, noise: Optional[Dict[str, torch.Tensor]] = None):
@@ -145,13 +192,8 @@ class TilingSviEngine(AutogradSviEngine):
         mu_scale, sd_scale_q, alpha_pi = P["mu_scale"].exp(), P["sd_scale"].exp(), P["alpha_pi"].exp()
         alpha_pi = torch.where(self.allele_mask, alpha_pi, torch.full_like(alpha_pi, eps))  # model.py:645 / :937
 
-        def draw(key, shape):
-            if noise is not None and key in noise:
-                return noise[key].to(**kw).reshape(shape)
-            return torch.randn(shape, generator=self.gen, **kw)
-
-        mu_e = mu_loc + mu_scale * draw("eps_mu", (E,))
-        sd_e = torch.exp(sd_loc + sd_scale_q * draw("eps_sd", (E,)))
+        mu_e = mu_loc + mu_scale * self._draw(noise, "eps_mu", (E,))
+        sd_e = torch.exp(sd_loc + sd_scale_q * self._draw(noise, "eps_sd", (E,)))
         guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_e).sum() + tdist.LogNormal(sd_loc, sd_scale_q).log_prob(sd_e).sum()
         pp = self.prior_params or {}
         mu_prior = (tdist.Normal(torch.as_tensor(pp.get("mu_loc", 0.0), **kw), torch.as_tensor(pp.get("mu_scale", 1.0), **kw))
@@ -167,13 +209,16 @@ class TilingSviEngine(AutogradSviEngine):
         conc_g = (alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
         conc_m = (alpha_pi + eps / A) / (alpha_pi.sum(-1, keepdim=True) + eps) * self.pi_a0[:, None]
         conc_m = torch.where(conc_m < eps, torch.full_like(conc_m, eps), conc_m).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
-        injected = noise["pi"].to(**kw) if (noise is not None and "pi" in noise) else None
+        injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None  # cast to the concentration's dtype
         pi = _DirichletRsample.apply(conc_g, injected, self.gen)
         guide_lp = guide_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi))
         model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
         lp_mult = tdist.Multinomial(probs=pi, validate_args=False).log_prob(self.allele_counts_control)
         model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
 
+        if self.acc:
+            pi, m_lp, g_lp = self._acc_apply(pi, noise)
+            model_lp, guide_lp = model_lp + m_lp, guide_lp + g_lp
         # count likelihood of both layers (CUDA): bin masses, mixture, get_alpha, Dirichlet-Multinomial
         pi_g = pi[:, 0].permute(1, 0, 2).contiguous()  # (G, R, A)
         model_lp = model_lp + count_log_likelihood(self.screen, mu_a, sd_a, pi_g, self.allele_mask_u8)

@@ -31,25 +31,28 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
     if selection_of(model) != selection_of(guide):
         raise ValueError("model and guide belong to different selections (sorting vs survival)")
     if selection_of(model) == "survival":
-        if mkw.get("scale_by_accessibility"):
-            raise NotImplementedError("survival MixtureNormal+Acc is not built yet")
         from .survival import SurvivalSviEngine
 
         use_bcmatch = mkw.get("use_bcmatch", True)
         use_bcmatch = True if isinstance(use_bcmatch, tuple) else bool(use_bcmatch)  # App. B2
-        extra = {"mu_negctrl": mkw["mu_negctrl"]} if name == "MixtureNormal" else {}
+        extra = {}
+        if name in ("MixtureNormal", "MultiMixtureNormal"):
+            extra = dict(mu_negctrl=mkw["mu_negctrl"], scale_by_accessibility=bool(mkw.get("scale_by_accessibility", False)),
+                         fit_noise=bool(gkw.get("fit_noise", False)))
+        if name == "MultiMixtureNormal":
+            extra["epsilon"] = float(mkw.get("epsilon", 1e-5))
         return SurvivalSviEngine(data, name, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps,
                                  initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
                                  mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"), **extra)
     if name == "MultiMixtureNormal":
-        if mkw.get("scale_by_accessibility"):
-            raise NotImplementedError("MultiMixtureNormal+Acc is not built yet")
         from .generic import TilingSviEngine
 
         return TilingSviEngine(data, device=device, dtype=dtype, use_bcmatch=True, num_steps=num_steps, initial_lr=initial_lr,
                                gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
                                sd_scale=float(mkw.get("sd_scale", 0.01)), epsilon=float(mkw.get("epsilon", 1e-5)),
-                               prior_params=mkw.get("prior_params"))
+                               prior_params=mkw.get("prior_params"),
+                               scale_by_accessibility=bool(mkw.get("scale_by_accessibility", False)),
+                               fit_noise=bool(gkw.get("fit_noise", False)))
     if name not in FUSED_MODELS:
         raise NotImplementedError(f"model {name} is not built yet")
     use_bcmatch = mkw.get("use_bcmatch", True)
@@ -82,8 +85,6 @@ def identify_model_guide(args):
     """bean/model/run.py:399-457."""
     m = sorting_model if args.selection == "sorting" else survival_model
     if args.library_design == "tiling":
-        if args.selection != "sorting":
-            raise NotImplementedError("survival MultiMixtureNormal is not built yet")
         return (
             f"MultiMixtureNormal{'+Acc' if args.scale_by_acc else ''}",
             partial(m.MultiMixtureNormalModel, scale_by_accessibility=args.scale_by_acc, use_bcmatch=(not args.ignore_bcmatch,)),

@@ -1,5 +1,5 @@
 """SVI engine for the proliferation / survival models (bean/model/survival_model.py): Normal, ControlNormal,
-MixtureNormal.
+MixtureNormal (+ accessibility scaling) and the tiling MultiMixtureNormal (+ accessibility scaling).
 
 Same split as the tiling engine: the count likelihood -- exp(mu t) allele masses, allele mixture, get_alpha and the
 Dirichlet-Multinomial rows of both count layers with their backward -- is the C-ABI kernel (`bean_ll_*` in survival
@@ -9,7 +9,10 @@ mode); the Dirichlet-over-guides abundance sites, the editing-rate sites, priors
     guides per replicate, e[r, b, g] = exp(mu_g t_b) q_0[r, g]; negative-control guides have mu := 0 (:58-60);
   * ControlNormal    (:133-213, guide :742-757): one shared growth rate;
   * MixtureNormal    (:215-424, guide :651-739): the guide samples `initial_abundance` although the model observes it,
-    `q0` is the guide's (G,) parameter, `mu_negctrl` is a model-only latent drawn from its prior every step.
+    `q0` is the guide's (G,) parameter, `mu_negctrl` is a model-only latent drawn from its prior every step;
+  * MultiMixtureNormal (:427-626, guide :759-833): tiling screens -- allele growth rate = mu_negctrl + sum of its
+    edits' rates (CSR gather kernel), non-existent alleles multiplied by 0; the guide's `initial_abundance`
+    parameter is declared but unused.
 """
 from __future__ import annotations
 
@@ -20,15 +23,17 @@ import torch.distributions as tdist
 
 from ._lib import BeanError
 from .device_pack import DeviceScreen
-from .generic import AutogradSviEngine, _DirichletRsample, _masked_sum
+from .generic import EPS, AutogradSviEngine, _DirichletRsample, _masked_sum
 from .ll_function import count_log_likelihood
+from .tiling import AlleleMap, allele_gather
 
 
 class SurvivalSviEngine(AutogradSviEngine):
     def __init__(self, data, model: str = "MixtureNormal", device="cuda", dtype=torch.float32, use_bcmatch=True,
                  num_steps=2000, initial_lr=0.01, gamma=0.1, seed=101, alpha_prior=1.0, mask_thres=10,
-                 prior_params: Optional[dict] = None, mu_negctrl=(0.0, 0.1)):
-        if model not in ("Normal", "ControlNormal", "MixtureNormal"):
+                 prior_params: Optional[dict] = None, mu_negctrl=(0.0, 0.1), scale_by_accessibility: bool = False,
+                 fit_noise: bool = False, epsilon: float = EPS):
+        if model not in ("Normal", "ControlNormal", "MixtureNormal", "MultiMixtureNormal"):
             raise ValueError(f"SurvivalSviEngine does not implement model {model!r}")
         if not torch.cuda.is_available():
             raise BeanError("SurvivalSviEngine needs a CUDA device: there is no CPU fallback")
@@ -42,9 +47,21 @@ class SurvivalSviEngine(AutogradSviEngine):
         self.G, self.R = G, R
         self.prior_params = prior_params
         z = lambda *s: torch.zeros(s, **kw)
+        self.acc = bool(scale_by_accessibility) and model in ("MixtureNormal", "MultiMixtureNormal")
         if model == "ControlNormal":
             self.T = 1
             theta, positive = {"mu_loc": z(), "mu_scale": z()}, {"mu_scale"}
+        elif model == "MultiMixtureNormal":
+            self.E, self.A, self.epsilon = int(data.n_edits), int(data.n_max_alleles), float(epsilon)
+            self.T = self.E
+            self.amap = AlleleMap(data.allele_ptr.numpy(), data.allele_edit.numpy(), G, self.A, self.E, self.device)
+            self.allele_mask = data.allele_mask.to(self.device)
+            self.allele_mask_u8 = self.allele_mask.to(torch.uint8).contiguous()
+            a0 = torch.full((G, self.A), float(alpha_prior), **kw)
+            a0[~self.allele_mask] = self.epsilon
+            theta = {"initial_abundance": torch.full((G,), 1.0 / G, **kw).log(), "mu_loc": z(self.E), "mu_scale": z(self.E),
+                     "alpha_pi": a0.log()}
+            positive = {"initial_abundance", "mu_scale", "alpha_pi"}
         else:
             self.T = int(data.n_targets)
             self.target_lengths = data.target_lengths.to(self.device)
@@ -66,13 +83,16 @@ class SurvivalSviEngine(AutogradSviEngine):
             theta["q0"] = uniform.log()
             theta["alpha_pi"] = torch.full((G, 2), float(alpha_prior), **kw).log()
             positive |= {"q0", "alpha_pi"}
-            self.pi_a0 = torch.as_tensor(data.pi_a0).to(**kw)
+        if model in ("MixtureNormal", "MultiMixtureNormal"):
+            self.pi_a0 = torch.as_tensor(data.pi_a0).to(self.device)  # own dtype (float64), see generic.TilingSviEngine
             self.allele_counts_control = data.allele_counts_control.to(**kw)  # (R, C, G, 2)
             self.control_timepoint = data.control_timepoint.to(**kw)
             self.rg_mask = data.repguide_mask.to(self.device).unsqueeze(1)  # (R, 1, G)
             x0 = data.X[:, 0, :].to(**kw) + 1  # survival_model.py:306-311: observed initial abundance
             self.obs_abundance = x0 / x0.sum(-1, keepdim=True)
             self.mu_negctrl = (float(mu_negctrl[0]), float(mu_negctrl[1]))
+        if self.acc:
+            self._acc_init(data, theta, positive, fit_noise)
         self._init_optim(theta, positive, num_steps, initial_lr, gamma, seed)
 
     # ---------------------------------------------------------------------------------------------
@@ -89,7 +109,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         G, R, T = self.G, self.R, self.T
         P = self.theta
         mu_loc, mu_scale = P["mu_loc"], P["mu_scale"].exp()
-        shape = () if self.model == "ControlNormal" else (T, 1)
+        shape = () if self.model == "ControlNormal" else ((T,) if self.model == "MultiMixtureNormal" else (T, 1))
         mu_t = mu_loc + mu_scale * self._draw(noise, "eps_mu", shape)
         guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_t).sum()
         injected_q = noise["q0"].to(**kw) if (noise is not None and "q0" in noise) else None
@@ -102,6 +122,8 @@ class SurvivalSviEngine(AutogradSviEngine):
             return -(model_lp + ll - guide_lp)
 
         model_lp = self._mu_prior().log_prob(mu_t).sum()
+        if self.model == "MultiMixtureNormal":
+            return self._elbo_tiling(mu_t, model_lp, guide_lp, noise)
         mu_g = torch.repeat_interleave(mu_t, self.target_lengths, dim=0)  # (G, 1)
         if self.model == "Normal":
             conc = P["initial_abundance"].exp().unsqueeze(0).expand(R, -1)
@@ -126,7 +148,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         pi_a_scaled = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]
         conc_g = pi_a_scaled.clamp(min=1e-5).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
         conc_m = pi_a_scaled.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
-        injected = noise["pi"].to(**kw) if (noise is not None and "pi" in noise) else None
+        injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None
         pi = _DirichletRsample.apply(conc_g, injected, self.gen)
         guide_lp = guide_lp + tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi).sum()
         model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
@@ -136,8 +158,43 @@ class SurvivalSviEngine(AutogradSviEngine):
                                                         * tc.reshape(1, C, 1, 1).expand(R, -1, G, 2))
         lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(self.allele_counts_control)
         model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
+        if self.acc:  # survival_model.py:347-351
+            pi, m_lp, g_lp = self._acc_apply(pi, noise)
+            model_lp, guide_lp = model_lp + m_lp, guide_lp + g_lp
         pi_g = pi[:, 0].permute(1, 0, 2).contiguous()  # (G, R, 2)
         ll = count_log_likelihood(self.screen, mu, torch.ones_like(mu), pi_g, None)
+        return -(model_lp + ll - guide_lp)
+
+    def _elbo_tiling(self, mu_e, model_lp, guide_lp, noise):
+        """MultiMixtureNormal: everything after the `mu_targets` site (survival_model.py:469-626, guide :790-833)."""
+        kw = dict(device=self.device, dtype=self.dtype)
+        G, R, A, eps = self.G, self.R, self.A, self.epsilon
+        alpha_pi = self.theta["alpha_pi"].exp()
+        alpha_pi = torch.where(self.allele_mask, alpha_pi, torch.full_like(alpha_pi, eps))  # in-place overwrite in the reference
+        m0, s0 = self.mu_negctrl
+        u = m0 + s0 * self._draw(noise, "eps_negctrl", (G,))
+        model_lp = model_lp + tdist.Normal(torch.as_tensor(m0, **kw), torch.as_tensor(s0, **kw)).log_prob(u).sum()
+        mu_targets, _ = allele_gather(mu_e, torch.ones_like(mu_e), self.amap)  # (G, A): column 0 = 0, column j = sum of edit rates
+        mu = u.unsqueeze(-1) + mu_targets
+        conc_g = (alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]).clamp(min=1e-5)
+        conc_m = (alpha_pi + eps / A) / (alpha_pi.sum(-1, keepdim=True) + eps) * self.pi_a0[:, None]
+        conc_m = torch.where(conc_m < eps, torch.full_like(conc_m, eps), conc_m)
+        conc_g = conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+        conc_m = conc_m.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+        injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None
+        pi = _DirichletRsample.apply(conc_g, injected, self.gen)
+        guide_lp = guide_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi))
+        model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
+        tc = self.control_timepoint
+        C = tc.shape[0]
+        expanded = pi * torch.exp(mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1) * tc.reshape(1, C, 1, 1).expand(R, -1, G, A))
+        lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(self.allele_counts_control)
+        model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
+        if self.acc:
+            pi, m_lp, g_lp = self._acc_apply(pi, noise)
+            model_lp, guide_lp = model_lp + m_lp, guide_lp + g_lp
+        pi_g = pi[:, 0].permute(1, 0, 2).contiguous()  # (G, R, A)
+        ll = count_log_likelihood(self.screen, mu, torch.ones_like(mu), pi_g, self.allele_mask_u8)
         return -(model_lp + ll - guide_lp)
 
     def params(self):

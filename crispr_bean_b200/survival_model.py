@@ -15,3 +15,8 @@ NormalGuide = _Program("Normal", "guide", {}, selection="survival")
 ControlNormalGuide = _Program("ControlNormal", "guide", dict(mask_thres=10, use_bcmatch=True), selection="survival")
 MixtureNormalGuide = _Program("MixtureNormal", "guide", dict(
     alpha_prior=1, use_bcmatch=True, scale_by_accessibility=False, fit_noise=False), selection="survival")
+MultiMixtureNormalModel = _Program("MultiMixtureNormal", "model", dict(
+    alpha_prior=1, use_bcmatch=True, use_all_timepoints_for_pi=True, sd_scale=0.01, norm_pi=False, scale_by_accessibility=False,
+    fit_noise=False, prior_params=None, epsilon=1e-5, mu_negctrl=(0.0, 0.1)), selection="survival")
+MultiMixtureNormalGuide = _Program("MultiMixtureNormal", "guide", dict(
+    alpha_prior=1, use_bcmatch=True, epsilon=1e-5, scale_by_accessibility=False, fit_noise=False), selection="survival")

@@ -121,7 +121,7 @@ def make_config(name: str, seed: int = 101, **override) -> MiniScreen:
 
 def make_tiling_screen(n_guides: int = 200, window: int = 6, max_alleles: int = 5, n_reps: int = 3,
                        bins: Sequence[Tuple[float, float]] = DEFAULT_BINS, depth: float = 400.0, seed: int = 101,
-                       frac_effect: float = 0.2) -> MiniScreen:
+                       frac_effect: float = 0.2, accessibility: bool = False, as_survival: bool = False) -> MiniScreen:
     """Tiling screen (c3 shape): guide g can edit positions [g, g + window); each of its 1..max_alleles-1 edited
     alleles is a small subset of those positions, so edits are shared by overlapping guides.
     `uns["allele_counts"]` holds the per-sample allele-count table `bean filter` would write."""
@@ -180,6 +180,12 @@ def make_tiling_screen(n_guides: int = 200, window: int = 6, max_alleles: int = 
             rows.append((f"rep{r}_{cond_names[j]}", f"rep{r}", cond_names[j], lo, hi, 1))
     samples = pd.DataFrame(rows, columns=["name", "replicate", "bin", "lower_quantile", "upper_quantile", "mask"]).set_index("name")
     guides = pd.DataFrame({"start_pos": np.arange(n_guides)}, index=pd.Index([f"g{g}" for g in range(n_guides)], name="name"))
+    if accessibility:
+        guides["accessibility"] = torch.exp(1.0 + 0.8 * torch.randn(n_guides, generator=gen)).numpy()
+    if as_survival:  # the same counts read as a time course: condition D<7j>, time 7j (shape / parity tests of the survival tiling model)
+        samples["condition"] = [f"D{7 * j}" for _ in range(n_reps) for j in range(B + 1)]
+        samples["time"] = [7.0 * j for _ in range(n_reps) for j in range(B + 1)]
+        samples = samples.drop(columns=["bin", "lower_quantile", "upper_quantile"])
 
     def flat(t):
         return t.permute(2, 0, 1).reshape(n_guides, -1).numpy().astype(np.float32)

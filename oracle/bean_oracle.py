@@ -566,8 +566,8 @@ def elbo_survival_control_normal(data, ps: ParamStore, noise=None, mask_thres=10
 
 
 def elbo_survival_mixture_normal(data, ps: ParamStore, noise=None, alpha_prior=1.0, use_bcmatch=True, mask_thres=10,
-                                 prior_params=None, mu_negctrl=(0.0, 0.1)):
-    """survival MixtureNormalModel / Guide (survival_model.py:215-424, :651-739), without accessibility scaling."""
+                                 prior_params=None, mu_negctrl=(0.0, 0.1), scale_by_accessibility=False, fit_noise=False):
+    """survival MixtureNormalModel / Guide (survival_model.py:215-424, :651-739)."""
     T, G, R = data.n_targets, data.n_guides, data.n_reps
     out = {}
     q0 = ps.param("q0", torch.ones(G) / G, positive=True)
@@ -601,9 +601,67 @@ def elbo_survival_mixture_normal(data, ps: ParamStore, noise=None, alpha_prior=1
         mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1) * tc.unsqueeze(0).unsqueeze(-1).unsqueeze(-1).expand(R, -1, G, 2))
     lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(data.allele_counts_control)
     model_lp = model_lp + _masked_sum(rg_mask.expand(lp_mult.shape), lp_mult)
+    if scale_by_accessibility:  # survival_model.py:347-351
+        val, m_lp, g_lp = _noise_sites(data, ps, noise, fit_noise)
+        model_lp, guide_lp = model_lp + m_lp, guide_lp + g_lp
+        pi = scale_pi_by_accessibility(pi, data.guide_accessibility, val)
     P = _survival_p(mu, data.timepoints)  # (B, G, 2)
     e = (pi.expand(-1, data.n_condits, -1, -1) * P[None]).sum(axis=-1)
     model_lp = model_lp + _count_sites(data, e, use_bcmatch, mask_thres, out)
+    out["model_lp"], out["guide_lp"] = model_lp, guide_lp
+    return -(model_lp - guide_lp), out
+
+
+def elbo_survival_multi_mixture_normal(data, ps: ParamStore, noise=None, alpha_prior=1.0, use_bcmatch=True, prior_params=None,
+                                       epsilon=EPS, mu_negctrl=(0.0, 0.1), scale_by_accessibility=False, fit_noise=False):
+    """survival MultiMixtureNormalModel / Guide (survival_model.py:427-626, :759-833): tiling proliferation screens.
+
+    Guide: mu_targets (E,), pi ~ Dirichlet(clamp(alpha/sum * pi_a0, 1e-5)) masked by repguide_mask; its
+    `initial_abundance` parameter is declared but unused.  Model: mu_negctrl (G,) model-only latent; pi concentration
+    epsilon-regularised as in the sorting tiling model; control allele counts ~ Multinomial(pi exp(mu t_control))."""
+    E, G, A, R = data.n_edits, data.n_guides, data.n_max_alleles, data.n_reps
+    out = {}
+    ps.param("initial_abundance", torch.ones(G) / G, positive=True)  # declared by the guide, never used (no gradient)
+    mu_loc = ps.param("mu_loc", torch.zeros((E,)))
+    mu_scale = ps.param("mu_scale", torch.ones((E,)), positive=True)
+    alpha_pi0 = torch.ones((G, A)) * alpha_prior
+    alpha_pi0[~data.allele_mask] = epsilon
+    alpha_pi = ps.param("alpha_pi", alpha_pi0, positive=True)
+    alpha_pi = torch.where(data.allele_mask, alpha_pi, torch.full_like(alpha_pi, epsilon))
+    mu_e = mu_loc + mu_scale * _draw(noise, "eps_mu", (E,))
+    guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_e).sum()
+    mu_dist = tdist.Laplace(0.0, 1.0)
+    if prior_params is not None and ("mu_loc" in prior_params or "mu_scale" in prior_params):
+        mu_dist = tdist.Normal(prior_params.get("mu_loc", 0.0), prior_params.get("mu_scale", 1.0))
+    model_lp = mu_dist.log_prob(mu_e).sum()
+    mu_targets = torch.matmul(data.allele_to_edit, mu_e)  # (G, A-1)
+    u = mu_negctrl[0] + mu_negctrl[1] * _draw(noise, "eps_negctrl", (G,))
+    model_lp = model_lp + tdist.Normal(mu_negctrl[0], mu_negctrl[1]).log_prob(u).sum()
+    mu = torch.cat([u.unsqueeze(-1), u.unsqueeze(-1) + mu_targets], axis=1)  # (G, A)
+    conc_guide = (alpha_pi / alpha_pi.sum(axis=-1)[:, None] * data.pi_a0[:, None]).clamp(1e-5)
+    pi_a_scaled = (alpha_pi + epsilon / A) / (alpha_pi.sum(axis=-1)[:, None] + epsilon) * data.pi_a0[:, None]
+    pi_a_scaled = torch.where(pi_a_scaled < epsilon, torch.full_like(pi_a_scaled, epsilon), pi_a_scaled)
+    rg_mask = data.repguide_mask.unsqueeze(1)
+    conc_g = conc_guide.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+    pi = dirichlet_rsample(conc_g, noise.get("pi") if noise is not None else None)
+    guide_lp = guide_lp + _masked_sum(rg_mask, tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi))
+    conc_m = pi_a_scaled.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+    model_lp = model_lp + _masked_sum(rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
+    tc = data.control_timepoint
+    C = tc.shape[0]
+    expanded = pi * torch.exp(mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1)
+                              * tc.unsqueeze(0).unsqueeze(-1).unsqueeze(-1).expand(R, -1, G, A))
+    lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(data.allele_counts_control)
+    model_lp = model_lp + _masked_sum(rg_mask.expand(lp_mult.shape), lp_mult)
+    if scale_by_accessibility:
+        val, m_lp, g_lp = _noise_sites(data, ps, noise, fit_noise)
+        model_lp, guide_lp = model_lp + m_lp, guide_lp + g_lp
+        pi = scale_pi_by_accessibility(pi, data.guide_accessibility, val)
+    B = data.n_condits
+    P = torch.exp(data.timepoints.unsqueeze(-1).unsqueeze(-1).expand((-1, G, 1)) * mu.unsqueeze(0).expand((B, -1, -1)))
+    P = P * data.allele_mask.unsqueeze(0).expand((B, -1, -1))  # survival_model.py:566-567
+    e = (pi.expand(R, B, -1, -1) * P[None]).sum(axis=-1)
+    model_lp = model_lp + _count_sites(data, e, use_bcmatch, 10, out)
     out["model_lp"], out["guide_lp"] = model_lp, guide_lp
     return -(model_lp - guide_lp), out
 
@@ -612,4 +670,5 @@ SURVIVAL_ELBOS = {
     "Normal": elbo_survival_normal,
     "ControlNormal": elbo_survival_control_normal,
     "MixtureNormal": elbo_survival_mixture_normal,
+    "MultiMixtureNormal": elbo_survival_multi_mixture_normal,
 }

@@ -5,8 +5,8 @@
 TAG=${1:-r1}
 set -x
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:svi_guide_kernel -s 4 -c 1 -f -o gpurun_out/prof_${TAG}_guide \
+ncu --set full --clock-control none --import-source on -k regex:svi_guide_kernel -s 306 -c 1 -f -o gpurun_out/prof_${TAG}_guide \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2_$TAG.log 2>&1
 ls -la gpurun_out/

@@ -90,6 +90,10 @@ def survival_cases(ns):
          "MixtureNormal", {}),
         ("survival_mixture_control_d0", scr, dc.VariantSurvivalReporterScreenData, dict(kw, control_condition="D0"),
          m.MixtureNormalModel, m.MixtureNormalGuide, "MixtureNormal", {}),
+        ("survival_mixture_acc", make_survival_screen(10, 4, n_reps=3, seed=4, n_negctrl_guides=5, depth=150.0, accessibility=True),
+         dc.VariantSurvivalReporterScreenData, dict(kw, accessibility_col="accessibility"),
+         partial(m.MixtureNormalModel, scale_by_accessibility=True), partial(m.MixtureNormalGuide, scale_by_accessibility=True, fit_noise=True),
+         "MixtureNormal", dict(scale_by_accessibility=True, fit_noise=True)),
     ]
 
 
@@ -103,6 +107,23 @@ def tiling_cases(ns):
         out.append((name, scr, dc.TilingSortingReporterScreenData, dict(control_can_be_selected=True, allele_df_key="allele_counts"),
                     partial(m.MultiMixtureNormalModel, scale_by_accessibility=False, use_bcmatch=(True,)),
                     partial(m.MultiMixtureNormalGuide, scale_by_accessibility=False, fit_noise=True), "MultiMixtureNormal", {}))
+    acc = make_tiling_screen(n_guides=36, n_reps=3, seed=9, accessibility=True)
+    out.append(("tiling_acc", acc, dc.TilingSortingReporterScreenData,
+                dict(control_can_be_selected=True, allele_df_key="allele_counts", accessibility_col="accessibility"),
+                partial(m.MultiMixtureNormalModel, scale_by_accessibility=True, use_bcmatch=(True,)),
+                partial(m.MultiMixtureNormalGuide, scale_by_accessibility=True, fit_noise=True), "MultiMixtureNormal",
+                dict(scale_by_accessibility=True, fit_noise=True)))
+    # survival tiling (survival_model.py:427-626 / :759-833)
+    sm = ns.survival_model
+    surv = make_tiling_screen(n_guides=36, n_reps=3, seed=10, accessibility=True, as_survival=True)
+    skw = dict(condition_column="condition", time_column="time", control_condition="D0", allele_df_key="allele_counts")
+    out.append(("survival_tiling", surv, dc.TilingSurvivalReporterScreenData, skw,
+                partial(sm.MultiMixtureNormalModel, use_bcmatch=(True,)), partial(sm.MultiMixtureNormalGuide, fit_noise=True),
+                "MultiMixtureNormal", {}))
+    out.append(("survival_tiling_acc", surv, dc.TilingSurvivalReporterScreenData, dict(skw, accessibility_col="accessibility"),
+                partial(sm.MultiMixtureNormalModel, scale_by_accessibility=True, use_bcmatch=(True,)),
+                partial(sm.MultiMixtureNormalGuide, scale_by_accessibility=True, fit_noise=True), "MultiMixtureNormal",
+                dict(scale_by_accessibility=True, fit_noise=True)))
     return out
 
 
@@ -185,10 +206,14 @@ def result_table_golden(ns):
 
 
 def main():
+    if os.environ.get("PYTHONHASHSEED") != "0":
+        # the reference numbers tiling edits in set-iteration order (string hashes): pin it so the vectors are reproducible
+        os.environ["PYTHONHASHSEED"] = "0"
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     ns = load_reference()
     result_table_golden(ns)
     traj = ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise", "survival_normal", "survival_mixture",
-            "tiling_small")
+            "tiling_small", "survival_tiling_acc")
     for case in sorting_cases(ns) + survival_cases(ns) + tiling_cases(ns):
         write_case(ns, *case, n_traj=6 if case[0] in traj else 0)
 

@@ -119,7 +119,7 @@ def reference_loss_and_grads(pyro, model, guide, data, seed, dtype):
             for name, site in tr.nodes.items():
                 if site["type"] == "sample":
                     out[f"site/{tag}/{name}"] = np.asarray(float(site["log_prob_sum"].detach()))
-        noise = {f"noise/{k}": v.double().numpy() for k, v in noise_from_guide_trace(pyro, gt).items()}
+        noise = {f"noise/{k}": v.numpy() for k, v in noise_from_guide_trace(pyro, gt).items()}  # in the run's own dtypes
         for name, site in mt.nodes.items():  # model-only latents (drawn from the prior in the model)
             if site["type"] == "sample" and not site["is_observed"] and name not in gt:
                 noise[f"noise/model_only/{name}"] = site["value"].detach().double().numpy()

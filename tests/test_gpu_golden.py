@@ -25,14 +25,16 @@ def rel(got, ref):
 def make_engine(z, data, cuda_device, dtype, num_steps):
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     model = str(z["meta/oracle_model"])
-    if getattr(data, "is_tiling", False):
-        from crispr_bean_b200.generic import TilingSviEngine
-
-        return TilingSviEngine(data, cuda_device, dtype=dtype, num_steps=num_steps)
+    acc = dict(scale_by_accessibility=kw.get("scale_by_accessibility", False), fit_noise=kw.get("fit_noise", False))
     if getattr(data, "is_survival", False):
         from crispr_bean_b200.survival import SurvivalSviEngine
 
-        return SurvivalSviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True))
+        extra = acc if model in ("MixtureNormal", "MultiMixtureNormal") else {}
+        return SurvivalSviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True), **extra)
+    if getattr(data, "is_tiling", False):
+        from crispr_bean_b200.generic import TilingSviEngine
+
+        return TilingSviEngine(data, cuda_device, dtype=dtype, num_steps=num_steps, **acc)
     return SviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True),
                      scale_by_accessibility=kw.get("scale_by_accessibility", False), fit_noise=kw.get("fit_noise", False),
                      prior_params=kw.get("prior_params"))
@@ -64,7 +66,7 @@ def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol
 
 
 @pytest.mark.parametrize("name", [c for c in FUSED if c in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise",
-                                                              "survival_normal", "survival_mixture", "tiling_small")])
+                                                              "survival_normal", "survival_mixture", "tiling_small", "survival_tiling_acc")])
 def test_fused_run_follows_reference_run_inference(cuda_device, name):
     z, data = load_case(name)
     n = int(z["traj/n_steps"])

@@ -22,7 +22,7 @@ EDIT_AXIS_KEYS = ("mu_loc", "mu_scale", "sd_loc", "sd_scale", "eps_mu", "eps_sd"
 
 
 def elbo_fn(name, z):
-    table = O.SURVIVAL_ELBOS if name.startswith("survival") else O.SORTING_ELBOS  # (tiling lives in SORTING_ELBOS)
+    table = O.SURVIVAL_ELBOS if name.startswith("survival") else O.SORTING_ELBOS  # (sorting tiling lives in SORTING_ELBOS)
     return table[str(z["meta/oracle_model"])]
 
 
@@ -103,14 +103,16 @@ def test_tensoriser_equals_reference_data_class(name):
 
 def oracle_eval(z, data, tag, dtype, name=""):
     perm = edit_perm(z, data)
-    noise = {k: torch.as_tensor(to_ours(v, perm, k)).to(dtype) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
+    # draws keep the dtype the reference produced them in (native run: pi is float64 because pi_a0 is)
+    noise = {k: torch.as_tensor(to_ours(v, perm, k)) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
     kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
     with default_dtype(dtype):
         d = cast_data(data, dtype) if dtype == torch.float64 else data
         ps = O.ParamStore()
         loss, aux = elbo_fn(name, z)(d, ps, noise=noise, **kw)
         loss.backward()
-    return float(loss.detach()), {k: v.grad.detach().double().numpy() for k, v in ps.unconstrained.items()}, ps
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)).detach().double().numpy() for k, v in ps.unconstrained.items()}
+    return float(loss.detach()), grads, ps
 
 
 @pytest.mark.parametrize("name", PROGRAMS)
