@@ -63,6 +63,7 @@ class BeanSviState(C.Structure):
         ("partial", C.c_void_p), ("counter", C.c_void_p), ("loss", C.c_void_p),
         ("acc_k", C.c_void_p), ("noise_u", C.c_void_p), ("noise_m", C.c_void_p), ("noise_v", C.c_void_p),
         ("noise_grad", C.c_void_p),
+        ("mu_prior_loc_v", C.c_void_p), ("mu_prior_scale_v", C.c_void_p), ("sd_prior_loc_v", C.c_void_p), ("sd_prior_scale_v", C.c_void_p),
     ]
 
 
@@ -77,6 +78,7 @@ class BeanAlleleMap(C.Structure):
 
 
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
+ABI_VERSION = 2  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -119,6 +121,9 @@ def lib() -> C.CDLL:
         for name, (res, args) in _PROTOTYPES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
+        if handle.bean_abi_version() != ABI_VERSION:
+            raise BeanError(f"{LIB_PATH} has ABI version {handle.bean_abi_version()}, expected {ABI_VERSION}: rebuild it "
+                            "(python -m crispr_bean_b200.build --force)")
         _lib = handle
     return _lib
 

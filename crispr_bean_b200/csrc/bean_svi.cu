@@ -73,6 +73,10 @@ struct SviParams {
   real* pi_out;
   // priors / optimiser scalars of this step
   real mu_prior_loc, mu_prior_scale, sd_prior_loc, sd_prior_scale;
+  const real* mu_prior_loc_v;
+  const real* mu_prior_scale_v;
+  const real* sd_prior_loc_v;
+  const real* sd_prior_scale_v;
   real step_size, beta1, beta2, adam_eps, clip;
   double ll_const;
   real p_wt[BEAN_MAX_BINS];  // bin masses of the wild-type allele N(0, 1)
@@ -412,16 +416,20 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
     // model priors (model.py:41-65 / :405-428; ControlNormal :178-179)
     real lp_mu, dlp_mu;
     if (p.mu_prior_normal) {
-      const real z = (mu_t - p.mu_prior_loc) / p.mu_prior_scale;
-      lp_mu = -Num<real>::log(p.mu_prior_scale) - HL2PI - real(0.5) * z * z;
-      dlp_mu = -z / p.mu_prior_scale;
+      const real loc = p.mu_prior_loc_v ? p.mu_prior_loc_v[v] : p.mu_prior_loc;
+      const real scale = p.mu_prior_scale_v ? p.mu_prior_scale_v[v] : p.mu_prior_scale;
+      const real z = (mu_t - loc) / scale;
+      lp_mu = -Num<real>::log(scale) - HL2PI - real(0.5) * z * z;
+      dlp_mu = -z / scale;
     } else {  // Laplace(0, 1)
       lp_mu = -real(0.69314718055994530942) - (mu_t < real(0) ? -mu_t : mu_t);
       dlp_mu = mu_t > real(0) ? real(-1) : (mu_t < real(0) ? real(1) : real(0));
     }
-    const real zs = (y - p.sd_prior_loc) / p.sd_prior_scale;
-    const real lp_sd = -y - Num<real>::log(p.sd_prior_scale) - HL2PI - real(0.5) * zs * zs;
-    const real dlp_sd = (-real(1) - zs / p.sd_prior_scale) / sd_t;
+    const real sloc = p.sd_prior_loc_v ? p.sd_prior_loc_v[v] : p.sd_prior_loc;
+    const real sscale = p.sd_prior_scale_v ? p.sd_prior_scale_v[v] : p.sd_prior_scale;
+    const real zs = (y - sloc) / sscale;
+    const real lp_sd = -y - Num<real>::log(sscale) - HL2PI - real(0.5) * zs * zs;
+    const real dlp_sd = (-real(1) - zs / sscale) / sd_t;
     // guide densities (entropy side)
     const real lq_mu = -Num<real>::log(mu_scale) - HL2PI - real(0.5) * e_mu * e_mu;
     const real lq_sd = -y - Num<real>::log(sd_scale) - HL2PI - real(0.5) * e_sd * e_sd;
@@ -547,6 +555,10 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.pi_out = noise ? static_cast<real*>(noise->pi_out) : nullptr;
   p.mu_prior_loc = real(cfg->mu_prior_loc); p.mu_prior_scale = real(cfg->mu_prior_scale);
   p.sd_prior_loc = real(cfg->sd_prior_loc); p.sd_prior_scale = real(cfg->sd_prior_scale);
+  p.mu_prior_loc_v = static_cast<const real*>(state->mu_prior_loc_v);
+  p.mu_prior_scale_v = static_cast<const real*>(state->mu_prior_scale_v);
+  p.sd_prior_loc_v = static_cast<const real*>(state->sd_prior_loc_v);
+  p.sd_prior_scale_v = static_cast<const real*>(state->sd_prior_scale_v);
   p.beta1 = real(cfg->beta1); p.beta2 = real(cfg->beta2); p.adam_eps = real(cfg->adam_eps); p.clip = real(cfg->clip);
   p.ll_const = cfg->ll_const;
   fill_tables(s, p.t);

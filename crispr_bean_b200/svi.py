@@ -93,15 +93,27 @@ class SviEngine:
         c.fit_noise = 1 if self.fit_noise else 0
         c.mu_prior_normal, c.mu_prior_loc, c.mu_prior_scale = 0, 0.0, 1.0
         c.sd_prior_loc, c.sd_prior_scale = 0.0, (1.0 if model == "ControlNormal" else float(sd_scale))
+        self._prior_v = {}
         if prior_params:
-            if any(torch.is_tensor(v) and v.numel() > 1 for v in prior_params.values()):
-                raise NotImplementedError("per-variant prior_params tensors")
+            # scalars or per-variant tensors (T,) / (T, 1), as `bean build-prior` writes them (run.py:480-542)
+            def put(key, field):
+                val = prior_params[key]
+                if torch.is_tensor(val) and val.numel() > 1:
+                    if val.numel() != T:
+                        raise ValueError(f"prior_params[{key!r}] has {val.numel()} entries for {T} variants")
+                    self._prior_v[key] = val.detach().reshape(-1).to(**kw).contiguous()
+                else:
+                    setattr(c, field, float(val))
+
             if "mu_loc" in prior_params or "mu_scale" in prior_params:
                 c.mu_prior_normal = 1
-                c.mu_prior_loc = float(prior_params.get("mu_loc", 0.0))
-                c.mu_prior_scale = float(prior_params.get("mu_scale", 1.0))
-            c.sd_prior_loc = float(prior_params.get("sd_loc", c.sd_prior_loc))
-            c.sd_prior_scale = float(prior_params.get("sd_scale", c.sd_prior_scale))
+                c.mu_prior_loc, c.mu_prior_scale = 0.0, 1.0
+                for key in ("mu_loc", "mu_scale"):
+                    if key in prior_params:
+                        put(key, f"mu_prior_{key[3:]}")
+            for key in ("sd_loc", "sd_scale"):
+                if key in prior_params:
+                    put(key, f"sd_prior_{key[3:]}")
         c.lr0, c.lrd = float(initial_lr), float(gamma) ** (1.0 / max(self.num_steps, 1))
         c.beta1, c.beta2, c.adam_eps, c.clip = 0.9, 0.999, 1e-8, 10.0
         c.ll_const, c.seed = ll_const, int(seed)
@@ -118,6 +130,10 @@ class SviEngine:
         s.var_params, s.var_m, s.var_v = self.var_params.data_ptr(), self.var_m.data_ptr(), self.var_v.data_ptr()
         s.d_guide, s.var_grad = self.d_guide.data_ptr(), self.var_grad.data_ptr()
         s.partial, s.counter, s.loss = self.partial.data_ptr(), self.counter.data_ptr(), self.loss.data_ptr()
+        for key, field in (("mu_loc", "mu_prior_loc_v"), ("mu_scale", "mu_prior_scale_v"), ("sd_loc", "sd_prior_loc_v"),
+                           ("sd_scale", "sd_prior_scale_v")):
+            if key in self._prior_v:
+                setattr(s, field, self._prior_v[key].data_ptr())
         if self.acc:
             s.acc_k = self.acc_k.data_ptr()
             s.noise_u, s.noise_m, s.noise_v = self.noise_u.data_ptr(), self.noise_m.data_ptr(), self.noise_v.data_ptr()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 1
+#define BEAN_ABI_VERSION 2
 
 enum {
   BEAN_OK = 0,
@@ -207,6 +207,12 @@ typedef struct BeanSviState {
   void* noise_m;
   void* noise_v;
   void* noise_grad;              /* real [2][G] out or NULL                                             */
+  /* per-variant priors (`bean run --prior-params`, bean/model/run.py:480-542: tensors written by `bean build-prior`);
+     each may be NULL -> the scalar of BeanSviConfig applies.  mu_prior_* are read only when mu_prior_normal = 1.  */
+  const void* mu_prior_loc_v;    /* real [T] */
+  const void* mu_prior_scale_v;  /* real [T] */
+  const void* sd_prior_loc_v;    /* real [T] */
+  const void* sd_prior_scale_v;  /* real [T] */
 } BeanSviState;
 
 typedef struct BeanSviNoise {    /* all optional (NULL = draw with Philox) */

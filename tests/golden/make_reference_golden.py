@@ -64,6 +64,8 @@ def sorting_cases(ns):
         ("mixture_prior_params", small, dc.VariantSortingReporterScreenData, rep_kw,
          partial(m.MixtureNormalModel, prior_params={"mu_loc": 0.1, "mu_scale": 2.0}), m.MixtureNormalGuide,
          "MixtureNormal", dict(prior_params={"mu_loc": 0.1, "mu_scale": 2.0})),
+        ("mixture_prior_tensors", small, dc.VariantSortingReporterScreenData, rep_kw, "PRIOR_TENSORS", m.MixtureNormalGuide,
+         "MixtureNormal", "PRIOR_TENSORS"),
         ("normal_bcmatch", small, dc.VariantSortingScreenData, dict(rep_kw, use_bcmatch=True),
          partial(m.NormalModel, use_bcmatch=True), m.NormalGuide, "Normal", dict(use_bcmatch=True)),
     ]
@@ -142,6 +144,17 @@ def with_allele_objects(ns, screen):
 def write_case(ns, name, screen, cls, data_kw, model, guide, oracle_model, oracle_kw, n_traj=0):
     data = cls(with_allele_objects(ns, screen), **data_kw)
     arrays = dict(G.screen_to_arrays(screen))
+    if isinstance(model, str) and model == "PRIOR_TENSORS":
+        # per-variant priors as `bean build-prior` writes them and run.py:_check_prior_params reshapes them: (T, 1) tensors
+        g = torch.Generator().manual_seed(77)
+        T = data.n_targets
+        prior = {"mu_loc": 0.3 * torch.randn((T, 1), generator=g, dtype=torch.float64),
+                 "mu_scale": 0.5 + torch.rand((T, 1), generator=g, dtype=torch.float64),
+                 "sd_loc": 0.05 * torch.randn((T, 1), generator=g, dtype=torch.float64),
+                 "sd_scale": 0.01 + 0.05 * torch.rand((T, 1), generator=g, dtype=torch.float64)}
+        model = partial(ns.model.MixtureNormalModel, prior_params=prior)
+        oracle_kw = {"prior_params": "FROM_FIXTURE"}
+        arrays.update({f"prior/{k}": v.numpy() for k, v in prior.items()})
     if hasattr(data, "edit_index"):  # set-iteration order of the reference: a labelling, stored so tests can align to it
         keys = sorted(data.edit_index, key=data.edit_index.get)
         arrays["meta/edit_index_keys"] = np.asarray(keys).astype(str)

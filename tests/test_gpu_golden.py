@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from crispr_bean_b200.svi import SviEngine
-from tests.test_reference_golden import PROGRAMS, SORTING, edit_perm, group, load_case, to_ours
+from tests.test_reference_golden import PROGRAMS, SORTING, edit_perm, group, load_case, oracle_kwargs, to_ours
 
 pytestmark = pytest.mark.gpu
 FUSED = list(PROGRAMS)  # sorting: fused SVI kernels; survival: bean_ll kernel inside the autograd engine
@@ -23,7 +23,7 @@ def rel(got, ref):
 
 
 def make_engine(z, data, cuda_device, dtype, num_steps):
-    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    kw = oracle_kwargs(z)
     model = str(z["meta/oracle_model"])
     acc = dict(scale_by_accessibility=kw.get("scale_by_accessibility", False), fit_noise=kw.get("fit_noise", False))
     if getattr(data, "is_survival", False):

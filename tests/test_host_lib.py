@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/bean_b200.h but not exported"
     assert sorted(_lib.exported_symbols()) == names, "ctypes prototypes out of sync with the header"
-    assert _lib.lib().bean_abi_version() == 1
+    assert _lib.lib().bean_abi_version() == _lib.ABI_VERSION
 
 
 def test_argument_validation_without_gpu():

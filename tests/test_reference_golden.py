@@ -101,11 +101,18 @@ def test_tensoriser_equals_reference_data_class(name):
     assert not missing, f"tensors of the reference data class absent from the mirror: {missing}"
 
 
+def oracle_kwargs(z, dtype=torch.float64):
+    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    if kw.get("prior_params") == "FROM_FIXTURE":  # per-variant prior tensors stored in the fixture
+        kw["prior_params"] = {k: torch.as_tensor(v) for k, v in group(z, "prior/").items()}
+    return kw
+
+
 def oracle_eval(z, data, tag, dtype, name=""):
     perm = edit_perm(z, data)
     # draws keep the dtype the reference produced them in (native run: pi is float64 because pi_a0 is)
     noise = {k: torch.as_tensor(to_ours(v, perm, k)) for k, v in group(z, f"{tag}/noise/").items() if "/" not in k}
-    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    kw = oracle_kwargs(z)
     with default_dtype(dtype):
         d = cast_data(data, dtype) if dtype == torch.float64 else data
         ps = O.ParamStore()
@@ -146,7 +153,7 @@ def test_oracle_run_inference_follows_reference_trajectory(name):
     n = int(z["traj/n_steps"])
     perm = edit_perm(z, data)
     tn = {k: to_ours(v, perm, k) for k, v in group(z, "traj/noise/").items()}
-    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    kw = oracle_kwargs(z)
     with default_dtype(torch.float64):
         d = cast_data(data, torch.float64)
         ps, hist = O.run_inference(elbo_fn(name, z), d, num_steps=n,
