@@ -1,4 +1,15 @@
-import sys, time; sys.path.insert(0, '.')
+"""Per-step time of the c5 workload over a long run, in blocks of 100 steps (CUDA events).
+
+    python profiles/steady_state.py [n_steps]
+
+A step gets slower over the first ~300 steps (alpha_pi fits the low editing rates and more Dirichlet draws leave the
+saddle-point regime); bench.py therefore burns in before timing.  Also the target of the steady-state ncu capture
+(profiles/capture.sh).
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import build_data
 from crispr_bean_b200.svi import SviEngine
