@@ -47,7 +47,7 @@ class BeanSviConfig(C.Structure):
         ("sd_prior_loc", C.c_double), ("sd_prior_scale", C.c_double),
         ("lr0", C.c_double), ("lrd", C.c_double),
         ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double), ("clip", C.c_double),
-        ("ll_const", C.c_double), ("seed", C.c_uint64),
+        ("ll_const", C.c_double), ("prob_clamp_eps", C.c_double), ("seed", C.c_uint64),
         ("guide_offset", C.c_uint32), ("variant_offset", C.c_uint32),
     ]
 

@@ -138,18 +138,22 @@ __device__ __forceinline__ real digamma_full(real z) {
 template <>
 __device__ __forceinline__ double digamma_full<double>(double z) { return digamma_f64(z); }  // no lgamma needed
 
-// x near 0: Taylor series in x (torch: _beta_grad_alpha_small)
+// x near 0: Taylor series in x (torch: _beta_grad_alpha_small).  torch's `factor + 1/alpha` with
+// factor = psi(alpha) - psi(alpha + beta) - ln x cancels from O(1/alpha) to O(1) for small alpha (4 digits lost in
+// float at alpha = 3e-4); psi(alpha) + 1/alpha = psi(alpha + 1) removes the cancellation, the series is unchanged:
+//   factor + 1/(alpha + i) = f1 - i / (alpha (alpha + i)),   f1 = psi(alpha + 1) - psi(alpha + beta) - ln x.
 template <typename real>
 __device__ __forceinline__ real beta_grad_alpha_small(real x, real alpha, real beta) {
-  const real factor = digamma_full(alpha) - digamma_full(alpha + beta) - Num<real>::log(x);
+  const real f1 = digamma_full(alpha + real(1)) - digamma_full(alpha + beta) - Num<real>::log(x);
+  const real ialpha = real(1) / alpha;
   real numer = real(1);
-  real series = numer / alpha * (factor + real(1) / alpha);
+  real series = numer * ialpha * f1;
 #pragma unroll 1
   for (int i = 1; i <= 10; ++i) {
     const real ci = real(i);
     numer *= (ci - beta) * x / ci;
-    const real denom = alpha + ci;
-    series += numer / denom * (factor + real(1) / denom);
+    const real idenom = real(1) / (alpha + ci);
+    series += numer * idenom * (f1 - ci * ialpha * idenom);
   }
   const real result = x * Num<real>::pow(real(1) - x, -beta) * series;
   return isnan(result) ? real(0) : result;

@@ -77,7 +77,7 @@ struct SviParams {
   const real* mu_prior_scale_v;
   const real* sd_prior_loc_v;
   const real* sd_prior_scale_v;
-  real step_size, beta1, beta2, adam_eps, clip;
+  real step_size, beta1, beta2, adam_eps, clip, prob_eps;
   double ll_const;
   real p_wt[BEAN_MAX_BINS];  // bin masses of the wild-type allele N(0, 1)
   SampleTables<real> t;
@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
           dcm[1] += dg_cm[2] - dg_cm[1] + lp1;
           const real x0 = p.allele_counts[((size_t)g * R + r) * 2], x1 = p.allele_counts[((size_t)g * R + r) * 2 + 1];
           const real Sp = pi0 + pi1, iSp = Num<real>::rcp(Sp), pn0 = pi0 * iSp, pn1 = pi1 * iSp;
-          const real lo = Lim<real>::eps(), hi = real(1) - Lim<real>::eps();
+          // torch clamps Multinomial probs to [eps, 1 - eps] of THEIR dtype; in the reference pi inherits pi_a0's dtype
+          // (float64 out of the fit even on the float32 path): the host passes the eps that applies (BeanSviConfig)
+          const real lo = p.prob_eps, hi = real(1) - p.prob_eps;
           const real c0 = Num<real>::fmin(Num<real>::fmax(pn0, lo), hi), c1 = Num<real>::fmin(Num<real>::fmax(pn1, lo), hi);
           elbo_g += x0 * Num<real>::log(c0) + x1 * Num<real>::log(c1);
           const real h0 = (pn0 >= lo && pn0 <= hi) ? Num<real>::div(x0, c0) : real(0), h1 = (pn1 >= lo && pn1 <= hi) ? Num<real>::div(x1, c1) : real(0);
@@ -561,6 +563,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.sd_prior_scale_v = static_cast<const real*>(state->sd_prior_scale_v);
   p.beta1 = real(cfg->beta1); p.beta2 = real(cfg->beta2); p.adam_eps = real(cfg->adam_eps); p.clip = real(cfg->clip);
   p.ll_const = cfg->ll_const;
+  p.prob_eps = cfg->prob_clamp_eps > 0.0 ? real(cfg->prob_clamp_eps) : Lim<real>::eps();
   fill_tables(s, p.t);
   for (int b = 0; b < BEAN_MAX_BINS; ++b) {
     double m = 0.0;

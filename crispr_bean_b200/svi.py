@@ -117,6 +117,10 @@ class SviEngine:
         c.lr0, c.lrd = float(initial_lr), float(gamma) ** (1.0 / max(self.num_steps, 1))
         c.beta1, c.beta2, c.adam_eps, c.clip = 0.9, 0.999, 1e-8, 10.0
         c.ll_const, c.seed = ll_const, int(seed)
+        # Multinomial prob clamp: eps of the dtype pi has in the reference = dtype of pi_a0 (float64 out of the fit)
+        pa0 = getattr(data, "pi_a0", None)
+        ref_dtype = torch.float64 if (dtype == torch.float64 or pa0 is None or not torch.is_tensor(pa0)) else pa0.dtype
+        c.prob_clamp_eps = float(torch.finfo(ref_dtype).eps)
         c.guide_offset, c.variant_offset = int(guide_offset), int(variant_offset)
         self.cfg = c
 

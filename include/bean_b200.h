@@ -177,6 +177,9 @@ typedef struct BeanSviConfig {
   double lr0, lrd;          /* ClippedAdam: lr_t = lr0 * lrd^t, lrd = gamma^(1/num_steps) (run.py:367) */
   double beta1, beta2, adam_eps, clip;
   double ll_const;          /* data-only part of the ELBO (sum of masked lgamma(1+N) - sum lgamma(1+x)) */
+  double prob_clamp_eps;    /* torch.distributions.Multinomial clamps probs to [eps, 1 - eps] of THEIR dtype; in the reference
+                               pi inherits pi_a0's dtype (float64 from the fit, float32 with the fallback coefficients,
+                               get_pi_alpha0.py:109-143): 2.2e-16 or 1.19e-7.  0 selects the eps of the entry point's real */
   uint64_t seed;
   uint32_t guide_offset;    /* global index of this shard's first guide / variant: the Philox counters   */
   uint32_t variant_offset;  /* use GLOBAL ids, so a variant-sharded run draws exactly the unsharded noise */
