@@ -47,6 +47,10 @@ def shard_data(data, rank: int, world: int):
     if ge == gb:
         raise ValueError(f"rank {rank} of {world} received no variants")
     sub = data[np.arange(gb, ge)] if (gb, ge) != (0, data.n_guides) else data
+    idx = getattr(data, "negctrl_guide_idx", None)
+    if idx is not None and sub is not data:  # global guide indices -> this shard's local ones
+        idx = np.asarray(idx)
+        sub.negctrl_guide_idx = idx[(idx >= gb) & (idx < ge)] - gb
     return sub, {"variant_offset": vb, "guide_offset": gb, "n_variants": ve - vb, "n_guides": ge - gb}
 
 

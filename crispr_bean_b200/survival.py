@@ -22,6 +22,7 @@ import torch
 import torch.distributions as tdist
 
 from ._lib import BeanError
+from .collective import ShardedDirichletRsample, global_sum, sharded_dirichlet_log_prob
 from .device_pack import DeviceScreen
 from .generic import EPS, AutogradSviEngine, _DirichletRsample, _masked_sum
 from .ll_function import count_log_likelihood
@@ -32,7 +33,10 @@ class SurvivalSviEngine(AutogradSviEngine):
     def __init__(self, data, model: str = "MixtureNormal", device="cuda", dtype=torch.float32, use_bcmatch=True,
                  num_steps=2000, initial_lr=0.01, gamma=0.1, seed=101, alpha_prior=1.0, mask_thres=10,
                  prior_params: Optional[dict] = None, mu_negctrl=(0.0, 0.1), scale_by_accessibility: bool = False,
-                 fit_noise: bool = False, epsilon: float = EPS):
+                 fit_noise: bool = False, epsilon: float = EPS, group=None):
+        """`group`: torch.distributed process group over which the guides are sharded (variant blocks, `dist.shard_data`);
+        the default (None) is the WORLD group when torch.distributed is initialised, otherwise a single rank.  The
+        Dirichlet over all guides is then evaluated with one all-reduce of n_reps numbers per sum (collective.py)."""
         if model not in ("Normal", "ControlNormal", "MixtureNormal", "MultiMixtureNormal"):
             raise ValueError(f"SurvivalSviEngine does not implement model {model!r}")
         if not torch.cuda.is_available():
@@ -44,7 +48,8 @@ class SurvivalSviEngine(AutogradSviEngine):
         use_bcmatch = bool(use_bcmatch) and getattr(data, "X_bcmatch_masked", None) is not None
         self.screen = DeviceScreen(data, self.device, dtype=dtype, use_bcmatch=use_bcmatch, mask_thres=mask_thres)
         G, R = data.n_guides, data.n_reps
-        self.G, self.R = G, R
+        self.G, self.R, self.group = G, R, group
+        self.G_total = int(global_sum(torch.tensor([float(G)], device=self.device), group).item())  # guides of ALL shards
         self.prior_params = prior_params
         z = lambda *s: torch.zeros(s, **kw)
         self.acc = bool(scale_by_accessibility) and model in ("MixtureNormal", "MultiMixtureNormal")
@@ -59,14 +64,14 @@ class SurvivalSviEngine(AutogradSviEngine):
             self.allele_mask_u8 = self.allele_mask.to(torch.uint8).contiguous()
             a0 = torch.full((G, self.A), float(alpha_prior), **kw)
             a0[~self.allele_mask] = self.epsilon
-            theta = {"initial_abundance": torch.full((G,), 1.0 / G, **kw).log(), "mu_loc": z(self.E), "mu_scale": z(self.E),
+            theta = {"initial_abundance": torch.full((G,), 1.0 / self.G_total, **kw).log(), "mu_loc": z(self.E), "mu_scale": z(self.E),
                      "alpha_pi": a0.log()}
             positive = {"initial_abundance", "mu_scale", "alpha_pi"}
         else:
             self.T = int(data.n_targets)
             self.target_lengths = data.target_lengths.to(self.device)
             theta, positive = {"mu_loc": z(self.T, 1), "mu_scale": z(self.T, 1)}, {"mu_scale"}
-        uniform = torch.full((G,), 1.0 / G, **kw)
+        uniform = torch.full((G,), 1.0 / self.G_total, **kw)
         if model == "Normal":
             theta["initial_abundance"] = uniform.log()
             positive.add("initial_abundance")
@@ -89,7 +94,7 @@ class SurvivalSviEngine(AutogradSviEngine):
             self.control_timepoint = data.control_timepoint.to(**kw)
             self.rg_mask = data.repguide_mask.to(self.device).unsqueeze(1)  # (R, 1, G)
             x0 = data.X[:, 0, :].to(**kw) + 1  # survival_model.py:306-311: observed initial abundance
-            self.obs_abundance = x0 / x0.sum(-1, keepdim=True)
+            self.obs_abundance = x0 / global_sum(x0.sum(-1, keepdim=True), group)
             self.mu_negctrl = (float(mu_negctrl[0]), float(mu_negctrl[1]))
         if self.acc:
             self._acc_init(data, theta, positive, fit_noise)
@@ -127,10 +132,10 @@ class SurvivalSviEngine(AutogradSviEngine):
         mu_g = torch.repeat_interleave(mu_t, self.target_lengths, dim=0)  # (G, 1)
         if self.model == "Normal":
             conc = P["initial_abundance"].exp().unsqueeze(0).expand(R, -1)
-            q_0 = _DirichletRsample.apply(conc, injected_q, self.gen)  # (R, G): one Dirichlet over all guides per replicate
-            guide_lp = guide_lp + tdist.Dirichlet(conc, validate_args=False).log_prob(q_0).sum()
-            model_lp = model_lp + tdist.Dirichlet(self.prior_abundance.unsqueeze(0).expand(R, -1),
-                                                  validate_args=False).log_prob(q_0).sum()
+            # (R, G): one Dirichlet over ALL guides per replicate -> the exchange step when guides are sharded
+            q_0 = ShardedDirichletRsample.apply(conc, injected_q, self.gen, self.group)
+            guide_lp = guide_lp + sharded_dirichlet_log_prob(conc, q_0, self.group)
+            model_lp = model_lp + sharded_dirichlet_log_prob(self.prior_abundance.unsqueeze(0).expand(R, -1), q_0, self.group)
             mu_a = mu_g * self.keep
             ll = count_log_likelihood(self.screen, mu_a, torch.ones_like(mu_a), q_0.t().unsqueeze(-1).contiguous(), None)
             return -(model_lp + ll - guide_lp)
@@ -138,13 +143,13 @@ class SurvivalSviEngine(AutogradSviEngine):
         # MixtureNormal
         alpha_pi = P["alpha_pi"].exp()
         conc_q = P["q0"].exp().unsqueeze(0).expand(R, -1)
-        ia = _DirichletRsample.apply(conc_q, injected_q, self.gen)  # guide-only draw (App. B8)
-        guide_lp = guide_lp + tdist.Dirichlet(conc_q, validate_args=False).log_prob(ia).sum()
+        ia = ShardedDirichletRsample.apply(conc_q, injected_q, self.gen, self.group)  # guide-only draw (App. B8)
+        guide_lp = guide_lp + sharded_dirichlet_log_prob(conc_q, ia, self.group)
         m0, s0 = self.mu_negctrl
         u = m0 + s0 * self._draw(noise, "eps_negctrl", (G,))  # model-only latent: fresh prior noise every step
         model_lp = model_lp + tdist.Normal(torch.as_tensor(m0, **kw), torch.as_tensor(s0, **kw)).log_prob(u).sum()
         mu = torch.cat([u.unsqueeze(-1), mu_g + u.unsqueeze(-1)], dim=-1)  # (G, 2)
-        model_lp = model_lp + tdist.Dirichlet(conc_q, validate_args=False).log_prob(self.obs_abundance).sum()
+        model_lp = model_lp + sharded_dirichlet_log_prob(conc_q, self.obs_abundance.expand_as(conc_q), self.group)
         pi_a_scaled = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]
         conc_g = pi_a_scaled.clamp(min=1e-5).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
         conc_m = pi_a_scaled.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)

@@ -1,0 +1,85 @@
+"""Multi-GPU tests (need >= 2 GPUs; skipped on a single-GPU box): the survival models' exchange step over NCCL.
+
+Guides of a proliferation screen are sharded across 2 ranks in variant blocks (`dist.shard_data`); the Dirichlet over
+ALL guides of the initial abundance sites is evaluated with `collective` all-reduces.  The sharded loss (sum over ranks)
+and every gradient must equal the single-GPU engine's on the same injected draws.
+Run by hand on a 2-GPU box:  gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -q
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _noise(data, seed):
+    g = torch.Generator().manual_seed(seed)
+    G, R, T = data.n_guides, data.n_reps, data.n_targets
+    gam = torch._standard_gamma(torch.full((R, G), 1.3, dtype=torch.float64), generator=g)
+    pig = torch._standard_gamma(torch.full((R, 1, G, 2), 1.5, dtype=torch.float64), generator=g)
+    return {"eps_mu": torch.randn((T, 1), generator=g, dtype=torch.float64), "q0": gam / gam.sum(-1, keepdim=True),
+            "pi": pig / pig.sum(-1, keepdim=True), "eps_negctrl": torch.randn((G,), generator=g, dtype=torch.float64)}
+
+
+def _data(model):
+    from crispr_bean_b200.data_class import VariantSurvivalReporterScreenData, VariantSurvivalScreenData
+    from crispr_bean_b200.synth import make_survival_screen
+
+    scr = make_survival_screen(40, "lognormal", n_reps=3, seed=11, n_negctrl_guides=7)
+    if model == "Normal":
+        return VariantSurvivalScreenData(scr, control_condition="D7", negctrl_guide_idx=list(range(7)))
+    return VariantSurvivalReporterScreenData(scr, control_condition="D7")
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from crispr_bean_b200.dist import shard_data
+    from crispr_bean_b200.survival import SurvivalSviEngine
+
+    solo = dist.new_group([rank], use_local_synchronization=True)  # a single-rank group = the unsharded engine
+    res = {}
+    for model in ("Normal", "MixtureNormal"):
+        data = _data(model)
+        noise = _noise(data, 3)
+        sub, off = shard_data(data, rank, world)
+        gb, ge = off["guide_offset"], off["guide_offset"] + off["n_guides"]
+        vb, ve = off["variant_offset"], off["variant_offset"] + off["n_variants"]
+        part = {"eps_mu": noise["eps_mu"][vb:ve], "q0": noise["q0"][:, gb:ge], "pi": noise["pi"][:, :, gb:ge],
+                "eps_negctrl": noise["eps_negctrl"][gb:ge]}
+        for dtype in (torch.float64, torch.float32):
+            eng = SurvivalSviEngine(sub, model, f"cuda:{rank}", dtype=dtype, num_steps=4)  # WORLD group: sharded
+            got = eng.gradients(part)
+            loss = got["loss"].double().clone()
+            dist.all_reduce(loss)
+            # 3 sharded steps with fresh (non-injected) draws must run: the gamma normaliser is all-reduced
+            eng.run(3)
+            assert torch.isfinite(eng.losses()).all()
+            full = SurvivalSviEngine(data, model, f"cuda:{rank}", dtype=dtype, num_steps=4, group=solo).gradients(noise)
+            res[(model, str(dtype))] = {"loss": loss.cpu(), "full_loss": full["loss"].double().cpu(), "slices": (gb, ge, vb, ve),
+                                        "got": {k: v.cpu() for k, v in got.items() if k != "loss"},
+                                        "full": {k: v.cpu() for k, v in full.items() if k != "loss"}}
+    torch.save(res, f"{out_dir}/r{rank}.pt")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_survival_models_sharded_over_two_gpus_equal_single_gpu(tmp_path):
+    port = 29700 + os.getpid() % 200
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        res = torch.load(f"{tmp_path}/r{rank}.pt")
+        for (model, dtype), r in res.items():
+            tol = 1e-10 if "64" in dtype else 2e-5
+            assert abs(r["loss"].item() - r["full_loss"].item()) <= tol * abs(r["full_loss"].item()), (model, dtype)
+            gb, ge, vb, ve = r["slices"]
+            for k, g in r["got"].items():
+                f = r["full"][k]
+                ref = f[vb:ve] if f.shape[0] == (r["full"]["mu_loc"].shape[0]) and k.startswith("mu_") else f[gb:ge]
+                scale = f.abs().mean().item() + 1e-300
+                assert (g.double() - ref.double()).abs().max().item() <= tol * 50 * scale, (model, dtype, k)
