@@ -5,6 +5,10 @@ their backward (`bean_ll_*`), and the allele <- edit contraction (`bean_allele_g
 C-ABI kernels; the O(G A) Dirichlet / Multinomial editing-rate sites, the priors and ClippedAdam are
 ordinary torch CUDA ops (plumbing).  Mirrors bean/model/model.py:550-751 (model) and :878-962 (guide);
 one `step()` = one `svi.step` of bean/model/run.py:376-380 with the loss kept on the device.
+
+A step is ~200 small kernels (forward, backward, Adam); launched one by one from Python it is launch-bound (4.5 ms at
+c3 / c4 size), so `run()` captures ONE step into a CUDA graph and replays it: the step counter, the ClippedAdam step
+size of every step and the loss log live on the device, the generator is registered with the graph.
 """
 from __future__ import annotations
 
@@ -45,6 +49,16 @@ class _DirichletRsample(torch.autograd.Function):
         return grad * (grad_output - (x * grad_output).sum(-1, True)), None, None
 
 
+def _multinomial_log_prob(probs, value):
+    """torch.distributions.Multinomial(probs=probs).log_prob(value) (probs normalised over the last axis and clamped to
+    [eps, 1 - eps] of their dtype, then logged), written out because the distribution's constructor builds a Binomial
+    from the python scalar total_count -- a host-to-device copy, which cannot be captured into a CUDA graph."""
+    eps = torch.finfo(probs.dtype).eps
+    logits = (probs / probs.sum(-1, keepdim=True)).clamp(min=eps, max=1 - eps).log()
+    value = value.to(logits.dtype)
+    return torch.lgamma(value.sum(-1) + 1) - torch.lgamma(value + 1).sum(-1) + (logits * value).sum(-1)
+
+
 def _masked_sum(mask, lp):
     return torch.where(mask, lp, torch.zeros_like(lp)).sum()
 
@@ -63,6 +77,29 @@ class AutogradSviEngine:
         self.step = 0
         self.loss = torch.zeros(max(num_steps, 1), dtype=torch.float64, device=self.device)
         self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
+        # device-side step counter and the ClippedAdam step size of every step: a captured step reads
+        # step_sizes[t] and writes loss[t], then increments t -- nothing about a step depends on the host
+        t = torch.arange(1, max(num_steps, 1) + 1, dtype=torch.float64)
+        self._step_sizes = (self.lr0 * self.lrd ** t * torch.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)).to(self.device)
+        self._t = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._graph, self._graph_noise, self.use_graph = None, None, True
+        self._const = {}
+
+    def _prior_t(self, value):
+        """A prior hyper-parameter (python scalar or tensor) as a device tensor, converted once."""
+        if not torch.is_tensor(value):
+            return self._c(value)
+        key = ("t", id(value))
+        if key not in self._const:
+            self._const[key] = value.detach().to(device=self.device, dtype=self.dtype)
+        return self._const[key]
+
+    def _c(self, value):
+        """A python scalar as a cached 0-dim device tensor (no host-to-device copy inside a step: not capturable)."""
+        key = float(value)
+        if key not in self._const:
+            self._const[key] = torch.full((), key, device=self.device, dtype=self.dtype)
+        return self._const[key]
 
     def _draw(self, noise, key, shape):
         if noise is not None and key in noise:
@@ -90,7 +127,7 @@ class AutogradSviEngine:
         kw = dict(device=self.device, dtype=self.dtype)
         G = pi.shape[2]
         eps = self._draw(noise, "eps_noise", (G,))
-        prior = tdist.Normal(torch.zeros((), **kw), torch.full((), PI_NOISE_SD, **kw))
+        prior = tdist.Normal(self._c(0.0), self._c(PI_NOISE_SD))
         if self.fit_noise:
             loc, scale = self.theta["noise_loc"], self.theta["noise_scale"].exp()
             val = loc + scale * eps
@@ -109,30 +146,90 @@ class AutogradSviEngine:
         return out, model_lp, guide_lp
 
     def _adam(self):
-        """pyro.optim.ClippedAdam on the unconstrained tensors."""
-        t = self.step + 1
-        lr = self.lr0 * self.lrd ** t
-        step_size = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        """pyro.optim.ClippedAdam on the unconstrained tensors, step size read from the device."""
         with torch.no_grad():
+            step_size = self._step_sizes.index_select(0, self._t.clamp(max=self._step_sizes.numel() - 1)).reshape(())
             for k, p in self.theta.items():
                 if p.grad is None:
                     continue
                 g = p.grad.clamp(-10.0, 10.0)
                 self.m[k].mul_(0.9).add_(g, alpha=0.1)
                 self.v[k].mul_(0.999).addcmul_(g, g, value=0.001)
-                p.addcdiv_(self.m[k], self.v[k].sqrt().add_(1e-8), value=-step_size)
-                p.grad = None
+                p.sub_((step_size * self.m[k] / (self.v[k].sqrt() + 1e-8)).to(p.dtype))
 
-    def run(self, n_steps: int, noise=None):
-        for _ in range(n_steps):
+    def _step_once(self, noise):
+        """One SVI step, entirely on the device (capturable)."""
+        prev = tdist.Distribution._validate_args
+        tdist.Distribution.set_default_validate_args(False)  # argument validation synchronises with the host
+        try:
             loss = self.elbo_loss(noise)
             loss.backward()
-            self.loss[self.step] = loss.detach().double()
-            self._adam()
-            self.step += 1
+        finally:
+            tdist.Distribution.set_default_validate_args(prev)
+        with torch.no_grad():
+            self.loss.index_copy_(0, self._t.clamp(max=self.loss.numel() - 1), loss.detach().double().reshape(1))
+        self._adam()
+        self._t.add_(1)
+
+    def _capture(self, noise):
+        """Capture one step into a CUDA graph (torch.cuda.graph: side-stream warm-up, private memory pool, generator
+        registered).  Warm-up steps run for real, so the optimiser state is snapshotted and restored around them."""
+        keep = [(t, t.detach().clone()) for t in list(self.theta.values()) + list(self.m.values()) + list(self.v.values())
+                + [self._t, self.loss]]
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                for p in self.theta.values():
+                    p.grad = None
+                self._step_once(noise)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        for p in self.theta.values():
+            p.grad = None  # the captured backward allocates the gradients inside the graph's pool
+        graph = torch.cuda.CUDAGraph()
+        graph.register_generator_state(self.gen)
+        with torch.cuda.graph(graph):
+            self._step_once(noise)
+        with torch.no_grad():
+            for t, saved in keep:
+                t.copy_(saved)
+        self._graph, self._graph_noise = graph, noise
+
+    def _graph_ok(self, n_steps):
+        if not (self.use_graph and self.device.type == "cuda" and n_steps >= 4):
+            return False
+        import torch.distributed as dist
+
+        return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)  # collectives stay eager
+
+    def run(self, n_steps: int, noise=None, use_graph: Optional[bool] = None):
+        """Advance `n_steps` SVI steps; `noise` (parity runs) is injected into every one of them."""
+        if self.step + n_steps > self.loss.numel():
+            raise ValueError("loss buffer exhausted: construct the engine with a larger num_steps")
+        if noise is not None:
+            noise = {k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in noise.items()}
+        graph = self._graph_ok(n_steps) if use_graph is None else use_graph
+        if graph:
+            if self._graph is None or self._graph_noise is not noise:
+                if noise is not None and self._graph is not None and self._graph_noise is not None \
+                        and set(noise) == set(self._graph_noise):
+                    for k, v in noise.items():  # same keys: refill the captured buffers instead of re-capturing
+                        self._graph_noise[k].copy_(v)
+                else:
+                    self._capture(noise)
+            for _ in range(n_steps):
+                self._graph.replay()
+        else:
+            for _ in range(n_steps):
+                for p in self.theta.values():
+                    p.grad = None
+                self._step_once(noise)
+        self.step += n_steps
         return self.loss[self.step - n_steps:self.step]
 
     def gradients(self, noise=None):
+        for p in self.theta.values():
+            p.grad = None
         loss = self.elbo_loss(noise)
         loss.backward()
         out = {"loss": loss.detach().clone()}
@@ -196,10 +293,9 @@ class TilingSviEngine(AutogradSviEngine):
         sd_e = torch.exp(sd_loc + sd_scale_q * self._draw(noise, "eps_sd", (E,)))
         guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_e).sum() + tdist.LogNormal(sd_loc, sd_scale_q).log_prob(sd_e).sum()
         pp = self.prior_params or {}
-        mu_prior = (tdist.Normal(torch.as_tensor(pp.get("mu_loc", 0.0), **kw), torch.as_tensor(pp.get("mu_scale", 1.0), **kw))
-                    if ("mu_loc" in pp or "mu_scale" in pp) else tdist.Laplace(torch.zeros((), **kw), torch.ones((), **kw)))
-        sd_prior = tdist.LogNormal(torch.as_tensor(pp.get("sd_loc", torch.zeros(E, **kw)), **kw),
-                                   torch.as_tensor(pp.get("sd_scale", torch.full((E,), self.sd_scale, **kw)), **kw))
+        mu_prior = (tdist.Normal(self._prior_t(pp.get("mu_loc", 0.0)), self._prior_t(pp.get("mu_scale", 1.0)))
+                    if ("mu_loc" in pp or "mu_scale" in pp) else tdist.Laplace(self._c(0.0), self._c(1.0)))
+        sd_prior = tdist.LogNormal(self._prior_t(pp.get("sd_loc", 0.0)), self._prior_t(pp.get("sd_scale", self.sd_scale)))
         model_lp = mu_prior.log_prob(mu_e).sum() + sd_prior.log_prob(sd_e).sum()
 
         # allele <- edit contraction (CUDA CSR gather / CSC scatter), WT column (0, 1)
@@ -213,7 +309,7 @@ class TilingSviEngine(AutogradSviEngine):
         pi = _DirichletRsample.apply(conc_g, injected, self.gen)
         guide_lp = guide_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi))
         model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
-        lp_mult = tdist.Multinomial(probs=pi, validate_args=False).log_prob(self.allele_counts_control)
+        lp_mult = _multinomial_log_prob(pi, self.allele_counts_control)
         model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
 
         if self.acc:

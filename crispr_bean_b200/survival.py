@@ -24,7 +24,7 @@ import torch.distributions as tdist
 from ._lib import BeanError
 from .collective import ShardedDirichletRsample, global_sum, sharded_dirichlet_log_prob
 from .device_pack import DeviceScreen
-from .generic import EPS, AutogradSviEngine, _DirichletRsample, _masked_sum
+from .generic import EPS, AutogradSviEngine, _DirichletRsample, _masked_sum, _multinomial_log_prob
 from .ll_function import count_log_likelihood
 from .tiling import AlleleMap, allele_gather
 
@@ -105,8 +105,8 @@ class SurvivalSviEngine(AutogradSviEngine):
         kw = dict(device=self.device, dtype=self.dtype)
         pp = self.prior_params or {}
         if "mu_loc" in pp or "mu_scale" in pp:
-            return tdist.Normal(torch.as_tensor(pp.get("mu_loc", 0.0), **kw), torch.as_tensor(pp.get("mu_scale", 1.0), **kw))
-        return tdist.Laplace(torch.zeros((), **kw), torch.ones((), **kw))
+            return tdist.Normal(self._prior_t(pp.get("mu_loc", 0.0)), self._prior_t(pp.get("mu_scale", 1.0)))
+        return tdist.Laplace(self._c(0.0), self._c(1.0))
 
     def elbo_loss(self, noise: Optional[Dict[str, torch.Tensor]] = None):
         """-ELBO of one particle (site lists: SURVEY App. A.8)."""
@@ -120,8 +120,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         injected_q = noise["q0"].to(**kw) if (noise is not None and "q0" in noise) else None
 
         if self.model == "ControlNormal":
-            one = torch.ones((), **kw)
-            model_lp = tdist.Normal(0 * one, one).log_prob(mu_t).sum()
+            model_lp = tdist.Normal(self._c(0.0), self._c(1.0)).log_prob(mu_t).sum()
             mu_a = mu_t.reshape(1, 1).expand(G, 1)
             ll = count_log_likelihood(self.screen, mu_a, torch.ones_like(mu_a), None, None)
             return -(model_lp + ll - guide_lp)
@@ -129,7 +128,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         model_lp = self._mu_prior().log_prob(mu_t).sum()
         if self.model == "MultiMixtureNormal":
             return self._elbo_tiling(mu_t, model_lp, guide_lp, noise)
-        mu_g = torch.repeat_interleave(mu_t, self.target_lengths, dim=0)  # (G, 1)
+        mu_g = torch.repeat_interleave(mu_t, self.target_lengths, dim=0, output_size=self.G)  # (G, 1); output_size: no host sync
         if self.model == "Normal":
             conc = P["initial_abundance"].exp().unsqueeze(0).expand(R, -1)
             # (R, G): one Dirichlet over ALL guides per replicate -> the exchange step when guides are sharded
@@ -147,7 +146,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         guide_lp = guide_lp + sharded_dirichlet_log_prob(conc_q, ia, self.group)
         m0, s0 = self.mu_negctrl
         u = m0 + s0 * self._draw(noise, "eps_negctrl", (G,))  # model-only latent: fresh prior noise every step
-        model_lp = model_lp + tdist.Normal(torch.as_tensor(m0, **kw), torch.as_tensor(s0, **kw)).log_prob(u).sum()
+        model_lp = model_lp + tdist.Normal(self._c(m0), self._c(s0)).log_prob(u).sum()
         mu = torch.cat([u.unsqueeze(-1), mu_g + u.unsqueeze(-1)], dim=-1)  # (G, 2)
         model_lp = model_lp + sharded_dirichlet_log_prob(conc_q, self.obs_abundance.expand_as(conc_q), self.group)
         pi_a_scaled = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]
@@ -161,7 +160,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         C = tc.shape[0]
         expanded = pi.expand(-1, C, -1, -1) * torch.exp(mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1)
                                                         * tc.reshape(1, C, 1, 1).expand(R, -1, G, 2))
-        lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(self.allele_counts_control)
+        lp_mult = _multinomial_log_prob(expanded, self.allele_counts_control)
         model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
         if self.acc:  # survival_model.py:347-351
             pi, m_lp, g_lp = self._acc_apply(pi, noise)
@@ -178,7 +177,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         alpha_pi = torch.where(self.allele_mask, alpha_pi, torch.full_like(alpha_pi, eps))  # in-place overwrite in the reference
         m0, s0 = self.mu_negctrl
         u = m0 + s0 * self._draw(noise, "eps_negctrl", (G,))
-        model_lp = model_lp + tdist.Normal(torch.as_tensor(m0, **kw), torch.as_tensor(s0, **kw)).log_prob(u).sum()
+        model_lp = model_lp + tdist.Normal(self._c(m0), self._c(s0)).log_prob(u).sum()
         mu_targets, _ = allele_gather(mu_e, torch.ones_like(mu_e), self.amap)  # (G, A): column 0 = 0, column j = sum of edit rates
         mu = u.unsqueeze(-1) + mu_targets
         conc_g = (alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]).clamp(min=1e-5)
@@ -193,7 +192,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         tc = self.control_timepoint
         C = tc.shape[0]
         expanded = pi * torch.exp(mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1) * tc.reshape(1, C, 1, 1).expand(R, -1, G, A))
-        lp_mult = tdist.Multinomial(probs=expanded, validate_args=False).log_prob(self.allele_counts_control)
+        lp_mult = _multinomial_log_prob(expanded, self.allele_counts_control)
         model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
         if self.acc:
             pi, m_lp, g_lp = self._acc_apply(pi, noise)
