@@ -27,6 +27,7 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float lgamma(float x) { return lgammaf(x); }
   static __device__ __forceinline__ float pow(float x, float y) { return ool_powf(x, y); }
   static __device__ __forceinline__ float log1p(float x) { return ool_log1pf(x); }
+  static __device__ __forceinline__ float log1p_inl(float x) { return log1pf(x); }
   static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }  // MUFU.RCP, ~1 ulp
@@ -43,6 +44,7 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double lgamma(double x) { return ::lgamma(x); }
   static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
   static __device__ __forceinline__ double log1p(double x) { return ::log1p(x); }
+  static __device__ __forceinline__ double log1p_inl(double x) { return ::log1p(x); }
   static __device__ __forceinline__ double fmax(double a, double b) { return ::fmax(a, b); }
   static __device__ __forceinline__ double fmin(double a, double b) { return ::fmin(a, b); }
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }

@@ -34,8 +34,9 @@ __device__ __noinline__ typename Vec4<real>::type dm_bin_terms(real x, real a, r
   const real e = fma(a, N, -p);
   const real num = fma(x, A, -p) - e;
   const real t = num * rU;
-  const real L2 = Num<real>::log1p(Num<real>::div(t, a));
-  const real L1 = x > real(0) ? Num<real>::log1p(Num<real>::div(-t, x)) : real(0);
+  // log1p inlined here (its only hot call site): two fewer calls per bin than through the shared out-of-line copy
+  const real L2 = Num<real>::log1p_inl(Num<real>::div(t, a));
+  const real L1 = x > real(0) ? Num<real>::log1p_inl(Num<real>::div(-t, x)) : real(0);
   typename Vec4<real>::type out;
   out.x = x * L1 + a * L2;
   out.y = L2;
