@@ -65,6 +65,13 @@ class ScreenData:
 
         screen = screen.copy()
         smp = screen.samples
+        covs = screen.uns.get("sample_covariates")
+        if covs is not None:
+            # sample covariates (data_class.py:75-92): a "replicate" becomes a (replicate, covariates...) combination
+            self.sample_covariates = list(covs)
+            self.n_sample_covariates = len(self.sample_covariates)
+            smp["_rc"] = [".".join(map(str, row)) for row in smp[[replicate_column] + self.sample_covariates].values.tolist()]
+            replicate_column = self.replicate_column = "_rc"
         smp["size_factor"] = get_size_factor(screen.X)  # all samples incl. control (data_class.py:63)
         if "X_bcmatch" in screen.layers:
             smp["size_factor_bcmatch"] = get_size_factor(screen.layers["X_bcmatch"])
@@ -82,6 +89,9 @@ class ScreenData:
         screen = screen[:, order]
         selected, is_control = selected[order], is_control[order]
         self.screen = screen
+        if covs is not None:  # 0/1 design of the covariates per (sorted) replicate combination (data_class.py:973-980)
+            self.rep_by_cov = torch.as_tensor(screen.samples[["_rc"] + self.sample_covariates].drop_duplicates()
+                                              .set_index("_rc").values.astype(int))
         self.screen_selected = screen[:, selected]
         self.screen_control = screen[:, is_control]
         self.n_condits = len(self.screen_selected.samples[condition_column].unique())

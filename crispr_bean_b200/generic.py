@@ -319,3 +319,55 @@ class TilingSviEngine(AutogradSviEngine):
         pi_g = pi[:, 0].permute(1, 0, 2).contiguous()  # (G, R, A)
         model_lp = model_lp + count_log_likelihood(self.screen, mu_a, sd_a, pi_g, self.allele_mask_u8)
         return -(model_lp - guide_lp)
+
+
+class CovariateNormalEngine(AutogradSviEngine):
+    """Sorting `Normal` model with sample covariates (`screen.uns["sample_covariates"]`; model.py:73-91, guide :771-782).
+
+    The covariate shifts the phenotype mean per REPLICATE, mu[r, g] = mu_targets[v(g)] + rep_by_cov[r, 0] * mu_cov[0]
+    (only the first column of rep_by_cov * mu_cov is used, as in the reference).  The likelihood kernel takes one mean
+    per (guide, allele), so the R replicate-specific means are passed as R "alleles" with a one-hot pi[g, r, :] = e_r:
+    e[r, b, g] = sum_a pi[g, r, a] P[b, g, a] = P[b, g, r] -- one `bean_ll` launch, gradients per replicate come back in
+    d_mu / d_sd.  sigma = sqrt(sd_targets)."""
+
+    def __init__(self, data, device="cuda", dtype=torch.float32, use_bcmatch=True, num_steps=2000, initial_lr=0.01,
+                 gamma=0.1, seed=101, sd_scale=0.01, mask_thres=10, prior_params: Optional[dict] = None):
+        if not torch.cuda.is_available():
+            raise BeanError("CovariateNormalEngine needs a CUDA device: there is no CPU fallback")
+        self.device, self.dtype = torch.device(device), dtype
+        kw = dict(device=self.device, dtype=dtype)
+        use_bcmatch = bool(use_bcmatch) and getattr(data, "X_bcmatch_masked", None) is not None
+        self.screen = DeviceScreen(data, self.device, dtype=dtype, use_bcmatch=use_bcmatch, mask_thres=mask_thres)
+        self.G, self.R, self.T, self.C = data.n_guides, data.n_reps, int(data.n_targets), int(data.n_sample_covariates)
+        self.target_lengths = data.target_lengths.to(self.device)
+        self.rep_by_cov = data.rep_by_cov.to(**kw)  # (R, C)
+        self.onehot = torch.eye(self.R, **kw).unsqueeze(0).expand(self.G, -1, -1).contiguous()  # pi[g, r, a] = [a == r]
+        self.sd_scale, self.prior_params = sd_scale, prior_params
+        z = lambda *s: torch.zeros(s, **kw)
+        theta = {"mu_loc": z(self.T, 1), "mu_scale": z(self.T, 1), "sd_loc": z(self.T, 1), "sd_scale": z(self.T, 1),
+                 "mu_cov_loc": z(self.C), "mu_cov_scale": z(self.C)}
+        self._init_optim(theta, {"mu_scale", "sd_scale", "mu_cov_scale"}, num_steps, initial_lr, gamma, seed)
+
+    def elbo_loss(self, noise: Optional[Dict[str, torch.Tensor]] = None):
+        T, G, R = self.T, self.G, self.R
+        P = self.theta
+        mu_loc, sd_loc, cov_loc = P["mu_loc"], P["sd_loc"], P["mu_cov_loc"]
+        mu_scale, sd_scale_q, cov_scale = P["mu_scale"].exp(), P["sd_scale"].exp(), P["mu_cov_scale"].exp()
+        mu_t = mu_loc + mu_scale * self._draw(noise, "eps_mu", (T, 1))
+        sd_t = torch.exp(sd_loc + sd_scale_q * self._draw(noise, "eps_sd", (T, 1)))
+        mu_cov = cov_loc + cov_scale * self._draw(noise, "eps_cov", (self.C,))
+        guide_lp = (tdist.Normal(mu_loc, mu_scale).log_prob(mu_t).sum() + tdist.LogNormal(sd_loc, sd_scale_q).log_prob(sd_t).sum()
+                    + tdist.Normal(cov_loc, cov_scale).log_prob(mu_cov).sum())
+        pp = self.prior_params or {}
+        mu_prior = (tdist.Normal(self._prior_t(pp.get("mu_loc", 0.0)), self._prior_t(pp.get("mu_scale", 1.0)))
+                    if ("mu_loc" in pp or "mu_scale" in pp) else tdist.Laplace(self._c(0.0), self._c(1.0)))
+        sd_prior = tdist.LogNormal(self._prior_t(pp.get("sd_loc", 0.0)), self._prior_t(pp.get("sd_scale", self.sd_scale)))
+        model_lp = (mu_prior.log_prob(mu_t).sum() + sd_prior.log_prob(sd_t).sum()
+                    + tdist.Normal(self._c(0.0), self._c(1.0)).log_prob(mu_cov).sum())
+        mu_g = torch.repeat_interleave(mu_t, self.target_lengths, dim=0, output_size=G)  # (G, 1)
+        sd_g = torch.repeat_interleave(sd_t, self.target_lengths, dim=0, output_size=G)
+        shift = (self.rep_by_cov * mu_cov)[:, 0]  # (R,)
+        mu_a = mu_g + shift.unsqueeze(0)  # (G, R): replicate-specific means as "alleles"
+        sd_a = torch.sqrt(sd_g).expand(G, R)
+        ll = count_log_likelihood(self.screen, mu_a, sd_a, self.onehot, None)
+        return -(model_lp + ll - guide_lp)

@@ -53,6 +53,13 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
                                prior_params=mkw.get("prior_params"),
                                scale_by_accessibility=bool(mkw.get("scale_by_accessibility", False)),
                                fit_noise=bool(gkw.get("fit_noise", False)))
+    if name == "Normal" and getattr(data, "sample_covariates", None) is not None:
+        from .generic import CovariateNormalEngine  # replicate-specific means: not in the fused kernel
+
+        return CovariateNormalEngine(data, device=device, dtype=dtype, use_bcmatch=bool(mkw.get("use_bcmatch", True)),
+                                     num_steps=num_steps, initial_lr=initial_lr, gamma=gamma, seed=seed,
+                                     sd_scale=float(mkw.get("sd_scale", 0.01)), mask_thres=int(mkw.get("mask_thres", 10)),
+                                     prior_params=mkw.get("prior_params"))
     if name not in FUSED_MODELS:
         raise NotImplementedError(f"model {name} is not built yet")
     use_bcmatch = mkw.get("use_bcmatch", True)

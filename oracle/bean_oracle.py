@@ -269,6 +269,16 @@ def elbo_normal(data, ps: ParamStore, noise=None, mask_thres=10, use_bcmatch=Tru
     uq = data.upper_bounds.unsqueeze(0).unsqueeze(-1).unsqueeze(-1).expand((R, -1, G, 1))
     lq = data.lower_bounds.unsqueeze(0).unsqueeze(-1).unsqueeze(-1).expand((R, -1, G, 1))
     mu4 = mu.unsqueeze(0).unsqueeze(0).expand((R, B, -1, -1))
+    if hasattr(data, "sample_covariates"):
+        # model.py:73-91 / guide :771-782: mu_cov ~ Normal(mu_cov_loc, mu_cov_scale) vs prior Normal(0, 1); only the FIRST
+        # column of rep_by_cov * mu_cov shifts the replicate's mean (`[:, 0]`, as the reference does)
+        C = data.n_sample_covariates
+        cov_loc = ps.param("mu_cov_loc", torch.zeros((C,)))
+        cov_scale = ps.param("mu_cov_scale", torch.ones((C,)), positive=True)
+        mu_cov = cov_loc + cov_scale * _draw(noise, "eps_cov", (C,))
+        guide_lp = guide_lp + tdist.Normal(cov_loc, cov_scale).log_prob(mu_cov).sum()
+        model_lp = model_lp + tdist.Normal(0.0, 1.0).log_prob(mu_cov).sum()
+        mu4 = mu4 + (data.rep_by_cov * mu_cov)[:, 0].unsqueeze(-1).unsqueeze(-1).unsqueeze(-1).expand((-1, B, G, 1))
     sd4 = torch.sqrt(sd.unsqueeze(0).unsqueeze(0).expand((R, B, -1, -1)))  # model.py:92-98
     alleles_p_bin = get_std_normal_prob(uq, lq, mu4, sd4)
     expected_guide_p = alleles_p_bin.sum(axis=-1)

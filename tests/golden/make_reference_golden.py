@@ -41,7 +41,13 @@ def sorting_cases(ns):
     wide = make_sorting_screen(10, 5, n_reps=8, seed=5, depth=300.0)  # c5 row shape (8 replicates) + bulk pseudo-bin
     ragged = make_sorting_screen(9, "lognormal", n_reps=2, seed=8, depth=25.0, n_negctrl_guides=3)  # low depth: masked rows
     rep_kw = dict(control_can_be_selected=True)
+    cov = make_sorting_screen(10, 4, n_reps=4, seed=14, depth=150.0)  # two 0/1 sample covariates over 4 replicates
+    cov.samples["cell_line"] = [str(int(r[3:]) % 2) for r in cov.samples["replicate"]]
+    cov.samples["batch"] = [str(int(int(r[3:]) >= 2)) for r in cov.samples["replicate"]]
+    cov.uns["sample_covariates"] = ["cell_line", "batch"]
     return [
+        ("normal_covariates", cov, dc.VariantSortingScreenData, rep_kw, partial(m.NormalModel, use_bcmatch=False), m.NormalGuide,
+         "Normal", dict(use_bcmatch=False)),
         # name, screen, data class, data kwargs, model, guide, oracle model name, oracle kwargs
         ("normal_c1", c1, dc.VariantSortingScreenData, c1_kw, partial(m.NormalModel, use_bcmatch=False), m.NormalGuide,
          "Normal", dict(use_bcmatch=False)),
@@ -226,7 +232,7 @@ def main():
     ns = load_reference()
     result_table_golden(ns)
     traj = ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise", "survival_normal", "survival_mixture",
-            "tiling_small", "survival_tiling_acc")
+            "tiling_small", "survival_tiling_acc", "normal_covariates")
     for case in sorting_cases(ns) + survival_cases(ns) + tiling_cases(ns):
         write_case(ns, *case, n_traj=6 if case[0] in traj else 0)
 

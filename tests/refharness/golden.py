@@ -28,6 +28,8 @@ def screen_to_arrays(scr, prefix="screen/"):
             col = df[c].to_numpy()
             out[f"{prefix}{tag}/col/{c}"] = col.astype(str) if col.dtype.kind in "OUS" else col
     for key, tbl in scr.uns.items():  # per-allele count tables of tiling screens (values may be Allele objects -> str)
+        if isinstance(tbl, (list, tuple)) and all(isinstance(v, str) for v in tbl):
+            out[f"{prefix}uns_list/{key}"] = np.asarray(list(tbl)).astype(str)
         if isinstance(tbl, pd.DataFrame):
             out[f"{prefix}uns/{key}/columns"] = np.asarray(list(tbl.columns)).astype(str)
             for c in tbl.columns:
@@ -51,6 +53,9 @@ def screen_from_arrays(z, prefix="screen/"):
             key = k[len(prefix) + 4:-len("/columns")]
             uns[key] = pd.DataFrame({c: (z[f"{prefix}uns/{key}/col/{c}"].astype(str) if z[f"{prefix}uns/{key}/col/{c}"].dtype.kind in "US"
                                          else z[f"{prefix}uns/{key}/col/{c}"]) for c in z[k].astype(str)})
+    for k in z.files:
+        if k.startswith(prefix + "uns_list/"):
+            uns[k[len(prefix) + 9:]] = [str(v) for v in z[k]]
     return MiniScreen(z[prefix + "X"], frame("guides"), frame("samples"), layers, uns)
 
 
@@ -84,6 +89,8 @@ def noise_from_guide_trace(pyro, gt):
         noise["eps_mu"] = (val("mu_targets") - st["mu_loc"].detach()) / st["mu_scale"].detach()
     if "sd_targets" in gt:
         noise["eps_sd"] = (val("sd_targets").log() - st["sd_loc"].detach()) / st["sd_scale"].detach()
+    if "mu_cov" in sampled:
+        noise["eps_cov"] = (val("mu_cov") - st["mu_cov_loc"].detach()) / st["mu_cov_scale"].detach()
     if "pi" in gt:
         noise["pi"] = val("pi")
     if "logit_pi_noise" in gt:

@@ -31,6 +31,10 @@ def make_engine(z, data, cuda_device, dtype, num_steps):
 
         extra = acc if model in ("MixtureNormal", "MultiMixtureNormal") else {}
         return SurvivalSviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True), **extra)
+    if getattr(data, "sample_covariates", None) is not None:
+        from crispr_bean_b200.generic import CovariateNormalEngine
+
+        return CovariateNormalEngine(data, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True))
     if getattr(data, "is_tiling", False):
         from crispr_bean_b200.generic import TilingSviEngine
 
@@ -66,7 +70,7 @@ def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol
 
 
 @pytest.mark.parametrize("name", [c for c in FUSED if c in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise",
-                                                              "survival_normal", "survival_mixture", "tiling_small", "survival_tiling_acc")])
+                                                              "survival_normal", "survival_mixture", "tiling_small", "survival_tiling_acc", "normal_covariates")])
 def test_fused_run_follows_reference_run_inference(cuda_device, name):
     z, data = load_case(name)
     n = int(z["traj/n_steps"])
