@@ -35,13 +35,18 @@ BASELINE_MD_PUBLISHED = None  # BASELINE.md holds no published number for this m
 
 
 def algorithmic_bytes_per_guide(R, B, L, guides_per_variant, itemsize=4):
-    """HBM bytes the guide kernel must move per guide (every input read once, every output written once).
+    """HBM bytes `svi_guide_kernel` (split step) must move per guide: every input read once, every output written once.
 
-    counts L*R*B + a0 L + row mask R (u8) + CSR id 4 B + reporter allele counts 2R + pi_a0 1
-    + alpha_pi (param, m, v) read+write 2*3*2 + per-guide (d_mu, d_sd) out 2 + variant params 4/guide-per-variant.
-    pi never touches HBM (sampled and consumed in registers), unlike SURVEY 8d's 15.3 B/cell estimate."""
+    counts L*R*B + a0 L + row mask R (u8) + CSR id 4 B + reporter allele counts 2R + pi_a0 1 + alpha_pi 2 (read)
+    + per-guide (d_mu, d_sd) out 2 + variant params 4/guide-per-variant + the hand-over to `svi_alpha_kernel`:
+    (pi0, pi1, w0, w1) per replicate 4R + concentration gradients 4."""
     w = itemsize
-    return (L * R * B * w + L * w + R + 4 + 2 * R * w + w + 12 * w + 2 * w + 4.0 * w / guides_per_variant)
+    return (L * R * B * w + L * w + R + 4 + 2 * R * w + w + 2 * w + 2 * w + 4.0 * w / guides_per_variant + 4 * R * w + 4 * w)
+
+
+def alpha_kernel_bytes_per_guide(R, itemsize=4):
+    """`svi_alpha_kernel`: the hand-over records 4R + 4, pi_a0 1, alpha_pi (param, m, v) read + written 12."""
+    return (4 * R + 4 + 1 + 12) * itemsize
 
 
 def build_data(workload, seed):
@@ -224,7 +229,8 @@ def main():
     final_loss = float(eng.loss[eng.step - 1].item())
     # --- per-kernel timing for the roofline (guide kernel alone, same launches, CUDA events) -----
     ms_var = time_steps(eng, args.steps, phases=2) / args.steps
-    ms_guide = ms / args.steps - ms_var  # the guide kernel's share of the timed steps themselves
+    ms_alpha = time_steps(eng, args.steps, phases=4) / args.steps if eng.split else 0.0
+    ms_guide = ms / args.steps - ms_var - ms_alpha  # the guide kernel's share of the timed steps themselves
     itemsize = 4 if dtype == torch.float32 else 8
     bytes_launch = algorithmic_bytes_per_guide(R, B, L, gpv, itemsize) * nv * gpv
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -259,7 +265,8 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r1_final_guide_metrics.txt (ncu --set full, one launch)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": ms_guide,
-                "ms_per_launch_variant_kernel": ms_var,
+                "ms_per_launch_variant_kernel": ms_var, "ms_per_launch_alpha_kernel": ms_alpha,
+                "alpha_kernel_gbs": alpha_kernel_bytes_per_guide(R, itemsize) * nv * gpv / (ms_alpha * 1e-3) / 1e9 if ms_alpha else None,
                 "row_math_ceiling_ms": ms_ceiling, "frac_of_row_math_ceiling": ms_ceiling / ms_guide,
                 "row_math_ceiling_what": "register-only kernel evaluating the same Dirichlet-Multinomial row maths "
                                          f"({R * L} rows x {B} bins per guide: {2 * B + 2} lgamma/digamma pairs + {2 * B} log1p per row) "
@@ -318,7 +325,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
                 "what": f"SviEngine built from HOST tensors (screen upload + re-tiling inside the timed region), {e2e_steps} steps, "
                         "each step's loss copied to pinned host memory, final parameters copied to host"},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": (3 if eng.split else 2) * args.steps,
         "roofline": roofline,
         "final_loss": final_loss,
     }

@@ -64,6 +64,7 @@ class BeanSviState(C.Structure):
         ("acc_k", C.c_void_p), ("noise_u", C.c_void_p), ("noise_m", C.c_void_p), ("noise_v", C.c_void_p),
         ("noise_grad", C.c_void_p),
         ("mu_prior_loc_v", C.c_void_p), ("mu_prior_scale_v", C.c_void_p), ("sd_prior_loc_v", C.c_void_p), ("sd_prior_scale_v", C.c_void_p),
+        ("pw", C.c_void_p), ("dconc", C.c_void_p),
     ]
 
 
@@ -78,7 +79,7 @@ class BeanAlleleMap(C.Structure):
 
 
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 2  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 3  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 

@@ -21,7 +21,8 @@
 namespace bean {
 
 constexpr int SVI_THREADS = 128;
-constexpr int SVI_MIN_CTAS = 4;  // <= 128 registers: 16 warps/SM resident
+constexpr int SVI_MIN_CTAS = 4;        // fused guide step: <= 128 registers, 16 warps/SM (more CTAs measured +-2 %)
+constexpr int SVI_MIN_CTAS_SPLIT = 8;  // split guide step: 64 registers, 32 warps/SM (4: 1.17, 6: 1.11, 8: 1.08 ms/step)
 // ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
 // so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
 constexpr int SVI_WARP = 32;
@@ -60,6 +61,8 @@ struct SviParams {
   real* d_guide;
   real* var_grad;
   real* alpha_grad;
+  real* pw;      // split path: [G][R][4] = (pi0, pi1, w0, w1) of every draw, written by the guide kernel
+  real* dconc;   // split path: [G][4]    = (dcm0, dcm1, dcg0, dcg1) without the pathwise part
   double* partial;
   uint32_t* counter;
   double* loss;
@@ -115,9 +118,12 @@ __device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, re
   sd_t = Num<real>::exp(log_sd);
 }
 
-template <typename real, int NB, bool MIXTURE, bool ACC>
-__global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
-  __shared__ TailQueue<real> tail_queues[SVI_THREADS / SVI_WARP];
+// SPLIT: the pathwise Dirichlet derivative and the alpha_pi update run in `svi_alpha_kernel` instead; this kernel hands
+// over every draw with its upstream weights (16 B per replicate) and the rest of the concentration gradient.  Two small
+// instruction footprints instead of one large one (the I-cache is 32 KB per SM), at +0.26 GB of HBM traffic per step.
+template <typename real, int NB, bool MIXTURE, bool ACC, bool SPLIT>
+__global__ void __launch_bounds__(SVI_THREADS, (SPLIT && sizeof(real) == 4) ? SVI_MIN_CTAS_SPLIT : SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
+  __shared__ TailQueue<real> tail_queues[SPLIT ? 1 : SVI_THREADS / SVI_WARP];
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = p.B;
   const real eps = real(1e-5);
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
   const int lane = threadIdx.x & 31;
   const unsigned wmask = __ballot_sync(0xffffffffu, g < p.G);  // lanes that own a guide: the warp-collective set below
   if (g < p.G) {
-    TailQueue<real>& tq = tail_queues[threadIdx.x / SVI_WARP];
+    TailQueue<real>& tq = tail_queues[SPLIT ? 0 : threadIdx.x / SVI_WARP];
     int n_tail = 0;
     const int v = p.guide_variant[g];
     real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd;
@@ -305,6 +311,12 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         // the saddle-point branch cancels badly in float
         const double gbar = (double)pi0 * (double)go0 + (double)pi1 * (double)go1;
         const double w0 = (double)go0 - gbar, w1 = (double)go1 - gbar;
+        if (SPLIT) {
+          typename Vec4<real>::type rec;
+          rec.x = pi0; rec.y = pi1; rec.z = real(w0); rec.w = real(w1);
+          reinterpret_cast<typename Vec4<real>::type*>(p.pw)[(size_t)g * R + r] = rec;
+          continue;
+        }
         const bool saddle = dirichlet_pair_is_saddle((double)pi0, (double)pi1, (double)cg[0], (double)cg[1]);
         if (saddle) {
           double dg0, dg1;
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
         for (int b = 0; b < NB; ++b) dP[b] += de[b];
       }
     }
-    if (MIXTURE && n_tail > 0) tail_queue_flush(tq, n_tail, wmask, lane, dcg[0], dcg[1]);
+    if (MIXTURE && !SPLIT && n_tail > 0) tail_queue_flush(tq, n_tail, wmask, lane, dcg[0], dcg[1]);
     // per-guide gradient w.r.t. the edited allele's (mu, sd_targets); reduced per variant by the next kernel
     real dmu = real(0), dsg = real(0);
 #pragma unroll
@@ -334,7 +346,12 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
     if (p.sd_is_sqrt) dsg *= real(0.5) / sigma;
     p.d_guide[g] = dmu;
     p.d_guide[(size_t)p.G + g] = dsg;
-    if (MIXTURE) {
+    if (MIXTURE && SPLIT) {
+      typename Vec4<real>::type rec;
+      rec.x = dcm[0]; rec.y = dcm[1]; rec.z = dcg[0]; rec.w = dcg[1];
+      reinterpret_cast<typename Vec4<real>::type*>(p.dconc)[g] = rec;
+    }
+    if (MIXTURE && !SPLIT) {
       // concentration -> log alpha_pi; clamp(min) passes the gradient where its input >= 1e-5
       const real dC0 = dcm[0] + (cm[0] >= eps ? dcg[0] : real(0));
       const real dC1 = dcm[1] + (cm[1] >= eps ? dcg[1] : real(0));
@@ -383,6 +400,73 @@ __global__ void __launch_bounds__(SVI_THREADS, SVI_MIN_CTAS) svi_guide_kernel(co
   }
   const double tot = warp_sum(elbo);
   if ((threadIdx.x & 31) == 0) p.partial[(blockIdx.x * SVI_THREADS + threadIdx.x) / SVI_WARP] = tot;
+}
+
+// concentration gradients -> log alpha_pi gradient -> ClippedAdam (alpha_pi is per guide)
+template <typename real>
+__device__ __forceinline__ void alpha_update(const SviParams<real>& p, int g, real al0, real al1, real pa0, real cm0, real cm1,
+                                             real dcm0, real dcm1, real dcg0, real dcg1) {
+  const real eps = real(1e-5);
+  const real asum = al0 + al1;
+  // clamp(min) passes the gradient where its input >= 1e-5
+  const real dC0 = dcm0 + (cm0 >= eps ? dcg0 : real(0));
+  const real dC1 = dcm1 + (cm1 >= eps ? dcg1 : real(0));
+  const real k = pa0 / (asum * asum);
+  const real dal0 = k * (dC0 * (asum - al0) - dC1 * al1);
+  const real dal1 = k * (dC1 * (asum - al1) - dC0 * al0);
+  const real gl0 = -dal0 * al0, gl1 = -dal1 * al1;  // loss = -ELBO, unconstrained (log) space
+  if (p.alpha_grad) {
+    p.alpha_grad[2 * (size_t)g] = gl0;
+    p.alpha_grad[2 * (size_t)g + 1] = gl1;
+  }
+  if (p.apply_update) {
+    real th0 = p.alpha_u[2 * (size_t)g], th1 = p.alpha_u[2 * (size_t)g + 1];
+    real m0 = p.alpha_m[2 * (size_t)g], m1 = p.alpha_m[2 * (size_t)g + 1];
+    real v0 = p.alpha_v[2 * (size_t)g], v1 = p.alpha_v[2 * (size_t)g + 1];
+    clipped_adam(p, gl0, th0, m0, v0);
+    clipped_adam(p, gl1, th1, m1, v1);
+    p.alpha_u[2 * (size_t)g] = th0; p.alpha_u[2 * (size_t)g + 1] = th1;
+    p.alpha_m[2 * (size_t)g] = m0;  p.alpha_m[2 * (size_t)g + 1] = m1;
+    p.alpha_v[2 * (size_t)g] = v0;  p.alpha_v[2 * (size_t)g + 1] = v1;
+  }
+}
+
+// Second half of the split guide step: pathwise Dirichlet derivative of every draw (saddle-point pairs in place, the other
+// regimes through the per-warp queue), alpha_pi gradient and its ClippedAdam update.  One thread per guide.
+constexpr int ALPHA_THREADS = 128;
+template <typename real>
+__global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviParams<real> p) {
+  __shared__ TailQueue<real> tail_queues[ALPHA_THREADS / SVI_WARP];
+  const int g = blockIdx.x * ALPHA_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const real eps = real(1e-5);
+  const unsigned wmask = __ballot_sync(0xffffffffu, g < p.G);
+  if (g >= p.G) return;
+  TailQueue<real>& tq = tail_queues[threadIdx.x / SVI_WARP];
+  const real al0 = Num<real>::exp(p.alpha_u[2 * (size_t)g]), al1 = Num<real>::exp(p.alpha_u[2 * (size_t)g + 1]);
+  const real asum = al0 + al1, pa0 = p.pi_a0[g];
+  const real cm0 = al0 / asum * pa0, cm1 = al1 / asum * pa0;
+  const real cg0 = Num<real>::fmax(cm0, eps), cg1 = Num<real>::fmax(cm1, eps);
+  const typename Vec4<real>::type dc = reinterpret_cast<const typename Vec4<real>::type*>(p.dconc)[g];
+  real dcg0 = dc.z, dcg1 = dc.w;
+  int n_tail = 0;
+  for (int r = 0; r < p.R; ++r) {
+    const typename Vec4<real>::type rec = reinterpret_cast<const typename Vec4<real>::type*>(p.pw)[(size_t)g * p.R + r];
+    const bool saddle = dirichlet_pair_is_saddle((double)rec.x, (double)rec.y, (double)cg0, (double)cg1);
+    if (saddle) {
+      double dg0, dg1;
+      dirichlet_pair_saddle_f64((double)rec.x, (double)rec.y, (double)cg0, (double)cg1, dg0, dg1);
+      dcg0 += real(dg0 * (double)rec.z);
+      dcg1 += real(dg1 * (double)rec.w);
+    }
+    n_tail = tail_queue_push(tq, n_tail, wmask, lane, !saddle, rec.x, rec.y, cg0, cg1, rec.z, rec.w);
+    if (n_tail >= 32) {
+      tail_queue_flush(tq, n_tail, wmask, lane, dcg0, dcg1);
+      n_tail = 0;
+    }
+  }
+  if (n_tail > 0) tail_queue_flush(tq, n_tail, wmask, lane, dcg0, dcg1);
+  alpha_update(p, g, al0, al1, pa0, cm0, cm1, dc.x, dc.y, dcg0, dcg1);
 }
 
 template <typename real>
@@ -479,15 +563,18 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
   }
 }
 
-template <typename real, bool MIXTURE, bool ACC>
-static void launch_guide(const SviParams<real>& p, cudaStream_t st) {
+template <typename real, bool MIXTURE, bool ACC, bool SPLIT>
+static void launch_guide(const SviParams<real>& p, cudaStream_t st, bool guide, bool alpha) {
   const int grid = (p.G + SVI_THREADS - 1) / SVI_THREADS;
-  if (p.B <= 4)
-    svi_guide_kernel<real, 4, MIXTURE, ACC><<<grid, SVI_THREADS, 0, st>>>(p);
+  if (!guide) {
+  } else if (p.B <= 4)
+    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT><<<grid, SVI_THREADS, 0, st>>>(p);
   else if (p.B == 5)
-    svi_guide_kernel<real, 5, MIXTURE, ACC><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT><<<grid, SVI_THREADS, 0, st>>>(p);
   else
-    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC, SPLIT><<<grid, SVI_THREADS, 0, st>>>(p);
+  // (one thread per (guide, replicate) with a shuffle reduction was tried for this kernel: 0.42 vs 0.27 ms)
+  if (MIXTURE && SPLIT && alpha) svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
 }
 
 template <typename real>
@@ -544,6 +631,9 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.d_guide = static_cast<real*>(state->d_guide);
   p.var_grad = static_cast<real*>(state->var_grad);
   p.alpha_grad = static_cast<real*>(state->alpha_grad);
+  p.pw = static_cast<real*>(state->pw);
+  p.dconc = static_cast<real*>(state->dconc);
+  if (p.pw) BEAN_REQUIRE(aligned16(p.pw) && aligned16(p.dconc), BEAN_EALIGN, "pw / dconc are not 16-byte aligned");
   p.partial = state->partial;
   p.counter = state->counter;
   p.loss = state->loss;
@@ -580,12 +670,17 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
     p.step = (uint32_t)t;
     const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
     p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
-    if (cfg->phases != 2) {
-      if (mix && p.acc_k) launch_guide<real, true, true>(p, st);
-      else if (mix) launch_guide<real, true, false>(p, st);
-      else launch_guide<real, false, false>(p, st);
+    // phases: 0 = the whole step; otherwise a bit mask (1 guide kernel, 2 variant kernel, 4 alpha kernel) so that a
+    // benchmark can time each kernel alone with CUDA events
+    const int ph = cfg->phases == 0 ? 7 : cfg->phases;
+    const bool do_guide = ph & 1, do_alpha = ph & 4;
+    if (do_guide || do_alpha) {
+      const bool split = mix && p.pw != nullptr && p.dconc != nullptr;
+      if (mix && p.acc_k) { if (split) launch_guide<real, true, true, true>(p, st, do_guide, do_alpha); else launch_guide<real, true, true, false>(p, st, do_guide, false); }
+      else if (mix) { if (split) launch_guide<real, true, false, true>(p, st, do_guide, do_alpha); else launch_guide<real, true, false, false>(p, st, do_guide, false); }
+      else launch_guide<real, false, false, false>(p, st, do_guide, false);
     }
-    if (cfg->phases != 1) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
+    if (ph & 2) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
   }
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;

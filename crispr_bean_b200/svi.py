@@ -32,7 +32,7 @@ class SviEngine:
                  seed: int = 101, alpha_prior: float = 1.0, sd_scale: float = 0.01, mask_thres: int = 10,
                  prior_params: Optional[dict] = None, screen: Optional[DeviceScreen] = None,
                  guide_offset: int = 0, variant_offset: int = 0, scale_by_accessibility: bool = False,
-                 fit_noise: bool = False):
+                 fit_noise: bool = False, split: bool = True):
         if model not in ("Normal", "ControlNormal", "MixtureNormal"):
             raise ValueError(f"SviEngine does not implement model {model!r}")
         self.lib = _lib.lib()
@@ -134,6 +134,11 @@ class SviEngine:
         s.var_params, s.var_m, s.var_v = self.var_params.data_ptr(), self.var_m.data_ptr(), self.var_v.data_ptr()
         s.d_guide, s.var_grad = self.d_guide.data_ptr(), self.var_grad.data_ptr()
         s.partial, s.counter, s.loss = self.partial.data_ptr(), self.counter.data_ptr(), self.loss.data_ptr()
+        self.split = bool(split) and self.mixture
+        if self.split:  # scratch of the two-kernel guide step (include/bean_b200.h: pw, dconc)
+            self.pw = torch.empty((G, R, 4), **kw)
+            self.dconc = torch.empty((G, 4), **kw)
+            s.pw, s.dconc = self.pw.data_ptr(), self.dconc.data_ptr()
         for key, field in (("mu_loc", "mu_prior_loc_v"), ("mu_scale", "mu_prior_scale_v"), ("sd_loc", "sd_prior_loc_v"),
                            ("sd_scale", "sd_prior_scale_v")):
             if key in self._prior_v:
