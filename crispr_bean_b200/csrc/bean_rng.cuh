@@ -357,6 +357,48 @@ static __device__ __noinline__ void dirichlet_pair_saddle_f64(double x0, double 
   if (near1) g1 = beta_grad_mid_near_mean(x1, b, a, iT);
 }
 
+// The same, split into the part that depends on the guide's concentrations only (hoisted out of the replicate loop by
+// `svi_alpha_kernel`: one division, one rsqrt and ~25 multiplies per guide instead of per draw) and the per-draw part.
+struct SaddlePair {
+  double a, b, iT, m0, m1, lim_w, rs, s, stirling, k, a2, b2;
+  __device__ __forceinline__ void init(double a_, double b_) {
+    a = a_; b = b_;
+    const double T = a + b;
+    iT = 1.0 / T;
+    m0 = a * iT; m1 = b * iT;
+    lim_w = 0.01 * a * b / ((T + 1.0) * T * T);  // near the mean <=> d^2 <= lim_w
+    const double q = 2.0 * a * b * iT;
+    rs = rsqrt(q);
+    s = q * rs;
+    a2 = a * a; b2 = b * b;
+    const double t2 = T * T;
+    stirling = (288.0 * a2 + 24.0 * a + 1.0) * (288.0 * b2 + 24.0 * b + 1.0) * t2 /
+               (288.0 * a2 * b2 * (288.0 * t2 + 24.0 * T + 1.0));
+    k = rs * iT * iT;
+  }
+  __device__ __forceinline__ void eval(double x0, double x1, double& g0, double& g1) const {
+    const double d0 = x0 - m0, d1 = x1 - m1;
+    const double La = ool_log(m0 / x0), Lb = ool_log(m1 / (1.0 - x0));
+    const double base = b * Lb + a * La;
+    const double rb = rsqrt(base);
+    const double term4 = rb * rb * rb;
+    {
+      const double xm1 = x0 - 1.0;
+      const double iax = 1.0 / (a * xm1 + b * x0);
+      const double term1 = (2.0 * a2 * xm1 + a * b * xm1 - x0 * b2) * b * k * iax * iax;
+      g0 = stirling * (-x0 * rs) * (term1 + 0.5 * La * (2.0 * s * iax + (x0 < m0 ? term4 : -term4)));
+    }
+    {
+      const double y1 = 1.0 - x0, xm1 = -x0;  // component 1 at 1 - x0 throughout (see dirichlet_pair_saddle_f64)
+      const double iax = 1.0 / (b * xm1 + a * y1);
+      const double term1 = (2.0 * b2 * xm1 + a * b * xm1 - y1 * a2) * a * k * iax * iax;
+      g1 = stirling * (-y1 * rs) * (term1 + 0.5 * Lb * (2.0 * s * iax + (y1 < m1 ? term4 : -term4)));
+    }
+    if (d0 * d0 <= lim_w) g0 = beta_grad_mid_near_mean(x0, a, b, iT);
+    if (d1 * d1 <= lim_w) g1 = beta_grad_mid_near_mean(x1, b, a, iT);
+  }
+};
+
 // One component, any regime.  FLOAT_TAILS (the float kernels): the three regimes without cancellation are evaluated in
 // float (1e-6 relative, against the fp32 path's 2e-4 budget for this gradient); the saddle-point regime stays double.
 template <bool FLOAT_TAILS>

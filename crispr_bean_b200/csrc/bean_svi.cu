@@ -450,12 +450,14 @@ __global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviPa
   const typename Vec4<real>::type dc = reinterpret_cast<const typename Vec4<real>::type*>(p.dconc)[g];
   real dcg0 = dc.z, dcg1 = dc.w;
   int n_tail = 0;
+  SaddlePair sp;
+  sp.init((double)cg0, (double)cg1);
   for (int r = 0; r < p.R; ++r) {
     const typename Vec4<real>::type rec = reinterpret_cast<const typename Vec4<real>::type*>(p.pw)[(size_t)g * p.R + r];
     const bool saddle = dirichlet_pair_is_saddle((double)rec.x, (double)rec.y, (double)cg0, (double)cg1);
     if (saddle) {
       double dg0, dg1;
-      dirichlet_pair_saddle_f64((double)rec.x, (double)rec.y, (double)cg0, (double)cg1, dg0, dg1);
+      sp.eval((double)rec.x, (double)rec.y, dg0, dg1);
       dcg0 += real(dg0 * (double)rec.z);
       dcg1 += real(dg1 * (double)rec.w);
     }
