@@ -273,9 +273,10 @@ def main():
                                          "with no memory traffic: the measured FP32/SFU floor of the step's row work",
                 "warp_instructions_per_launch": warp_inst,
                 "issue_floor_ms": (warp_inst / (4 * n_sm * clk) * 1e3) if warp_inst else None,
-                "note": "HBM is 4 % utilised: the kernel is bound by instruction issue (ncu: issue slots 56 % busy, FMA 26 %, ALU 31 %, "
-                        "XU 15 %, FP64 10 %); issue_floor_ms = executed warp instructions / (4 schedulers x SMs x clock), "
-                        "row_math_ceiling_ms = the Dirichlet-Multinomial row maths alone from registers; see DESIGN.md section 3"}
+                "note": "HBM is ~11 % utilised: the kernel is bound by instruction issue (ncu: issue slots 84 % busy; ALU 52 %, FMA 44 %, "
+                        "XU 23 % of their peaks); issue_floor_ms = executed warp instructions / (4 schedulers x SMs x clock), "
+                        "row_math_ceiling_ms = the Dirichlet-Multinomial row maths alone from registers; traffic exceeds the "
+                        "algorithmic bytes by the kernel's register spills (64 registers, 8 CTAs/SM); see DESIGN.md section 3"}
 
     # --- e2e: host-resident screen -> public API -> host-resident results ------------------------
     from crispr_bean_b200.device_pack import DeviceScreen

@@ -61,7 +61,7 @@ struct SviParams {
   real* d_guide;
   real* var_grad;
   real* alpha_grad;
-  real* pw;      // split path: [G][R][4] = (pi0, pi1, w0, w1) of every draw, written by the guide kernel
+  real* pw;      // split path: [R][G][4] = (pi0, pi1, w0, w1) of every draw, written by the guide kernel
   real* dconc;   // split path: [G][4]    = (dcm0, dcm1, dcg0, dcg1) without the pathwise part
   double* partial;
   uint32_t* counter;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(SVI_THREADS, (SPLIT && sizeof(real) == 4) ? SV
         if (SPLIT) {
           typename Vec4<real>::type rec;
           rec.x = pi0; rec.y = pi1; rec.z = real(w0); rec.w = real(w1);
-          reinterpret_cast<typename Vec4<real>::type*>(p.pw)[(size_t)g * R + r] = rec;
+          reinterpret_cast<typename Vec4<real>::type*>(p.pw)[(size_t)r * p.G + g] = rec;  // replicate-major: a warp's stores coalesce
           continue;
         }
         const bool saddle = dirichlet_pair_is_saddle((double)pi0, (double)pi1, (double)cg[0], (double)cg[1]);
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviPa
   SaddlePair sp;
   sp.init((double)cg0, (double)cg1);
   for (int r = 0; r < p.R; ++r) {
-    const typename Vec4<real>::type rec = reinterpret_cast<const typename Vec4<real>::type*>(p.pw)[(size_t)g * p.R + r];
+    const typename Vec4<real>::type rec = reinterpret_cast<const typename Vec4<real>::type*>(p.pw)[(size_t)r * p.G + g];
     const bool saddle = dirichlet_pair_is_saddle((double)rec.x, (double)rec.y, (double)cg0, (double)cg1);
     if (saddle) {
       double dg0, dg1;

@@ -136,7 +136,7 @@ class SviEngine:
         s.partial, s.counter, s.loss = self.partial.data_ptr(), self.counter.data_ptr(), self.loss.data_ptr()
         self.split = bool(split) and self.mixture
         if self.split:  # scratch of the two-kernel guide step (include/bean_b200.h: pw, dconc)
-            self.pw = torch.empty((G, R, 4), **kw)
+            self.pw = torch.empty((R, G, 4), **kw)
             self.dconc = torch.empty((G, 4), **kw)
             s.pw, s.dconc = self.pw.data_ptr(), self.dconc.data_ptr()
         for key, field in (("mu_loc", "mu_prior_loc_v"), ("mu_scale", "mu_prior_scale_v"), ("sd_loc", "sd_prior_loc_v"),

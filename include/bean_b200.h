@@ -219,7 +219,7 @@ typedef struct BeanSviState {
   const void* sd_prior_scale_v;  /* real [T] */
   /* optional scratch of the split guide step (MIXTURE): when both are non-NULL the pathwise Dirichlet derivative and
      the alpha_pi update run in a second kernel that reads what the first one leaves here                          */
-  void* pw;                      /* real [G][R][4]: (pi0, pi1, w0, w1) of every draw                                 */
+  void* pw;                      /* real [R][G][4]: (pi0, pi1, w0, w1) of every draw (replicate-major: coalesced)    */
   void* dconc;                   /* real [G][4]:    concentration gradients without the pathwise part               */
 } BeanSviState;
 
