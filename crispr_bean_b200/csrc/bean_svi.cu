@@ -22,7 +22,8 @@ namespace bean {
 
 constexpr int SVI_THREADS = 128;
 constexpr int SVI_MIN_CTAS = 4;        // fused guide step: <= 128 registers, 16 warps/SM (more CTAs measured +-2 %)
-constexpr int SVI_MIN_CTAS_SPLIT = 8;  // split guide step: 64 registers, 32 warps/SM (4: 1.17, 6: 1.11, 8: 1.08 ms/step)
+constexpr int SVI_MIN_CTAS_SPLIT = 8;  // split guide step and the Normal models: 64 registers, 32 warps/SM
+                                       // (MixtureNormal 4: 1.17, 6: 1.11, 8: 1.08 ms/step; Normal 4: 0.64, 8: 0.58)
 // ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
 // so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
 constexpr int SVI_WARP = 32;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, re
 // over every draw with its upstream weights (16 B per replicate) and the rest of the concentration gradient.  Two small
 // instruction footprints instead of one large one (the I-cache is 32 KB per SM), at +0.26 GB of HBM traffic per step.
 template <typename real, int NB, bool MIXTURE, bool ACC, bool SPLIT>
-__global__ void __launch_bounds__(SVI_THREADS, (SPLIT && sizeof(real) == 4) ? SVI_MIN_CTAS_SPLIT : SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
+__global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(real) == 4) ? SVI_MIN_CTAS_SPLIT : SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
   __shared__ TailQueue<real> tail_queues[SPLIT ? 1 : SVI_THREADS / SVI_WARP];
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = p.B;
