@@ -36,7 +36,7 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 
 // two standard normals from two 32-bit words (Box-Muller)
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  const float r = sqrtf(-2.0f * __logf(u01(a)));
+  const float r = sqrtf(-2.0f * log_ftz(u01(a)));
   float s, c;
   __sincosf(6.283185307179586f * (u01(b) - 0.5f), &s, &c);  // angle in (-pi, pi): MUFU.SIN/COS range
   n0 = r * c;
