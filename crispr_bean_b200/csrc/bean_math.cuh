@@ -44,6 +44,7 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float log1p(float x) { return ool_log1pf(x); }
   static __device__ __forceinline__ float log1p_inl(float x) { return log1pf(x); }
   static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float fabs(float a) { return fabsf(a); }
   static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float rcp(float x) { return rcp_ftz(x); }  // MUFU.RCP, ~1 ulp
   // 2-ulp division (MUFU.RCP + FMUL) for quantities whose own rounding already dominates
@@ -61,6 +62,7 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double log1p(double x) { return ::log1p(x); }
   static __device__ __forceinline__ double log1p_inl(double x) { return ::log1p(x); }
   static __device__ __forceinline__ double fmax(double a, double b) { return ::fmax(a, b); }
+  static __device__ __forceinline__ double fabs(double a) { return ::fabs(a); }
   static __device__ __forceinline__ double fmin(double a, double b) { return ::fmin(a, b); }
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
   static __device__ __forceinline__ double div(double a, double b) { return a / b; }

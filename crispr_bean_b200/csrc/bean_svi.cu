@@ -301,7 +301,12 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
           // (float64 out of the fit even on the float32 path): the host passes the eps that applies (BeanSviConfig)
           const real lo = p.prob_eps, hi = real(1) - p.prob_eps;
           const real c0 = Num<real>::fmin(Num<real>::fmax(pn0, lo), hi), c1 = Num<real>::fmin(Num<real>::fmax(pn1, lo), hi);
-          elbo_g += x0 * Num<real>::log(c0) + x1 * Num<real>::log(c1);
+          // log(pi_a / Sp) = log pi_a - log1p(Sp - 1): Sp = 1 up to rounding of the draw, so two of the replicate's four
+          // accurate logs are saved; a clamped probability (never, for float draws, with the float64 eps) takes the log itself
+          const real ds = Sp - real(1), lSp = ds - real(0.5) * ds * ds;
+          const real l0 = (c0 == pn0 && Num<real>::fabs(ds) < real(1e-3)) ? lp0 - lSp : Num<real>::log(c0);
+          const real l1 = (c1 == pn1 && Num<real>::fabs(ds) < real(1e-3)) ? lp1 - lSp : Num<real>::log(c1);
+          elbo_g += x0 * l0 + x1 * l1;
           const real h0 = (pn0 >= lo && pn0 <= hi) ? Num<real>::div(x0, c0) : real(0), h1 = (pn1 >= lo && pn1 <= hi) ? Num<real>::div(x1, c1) : real(0);
           const real hbar = h0 * pn0 + h1 * pn1;
           go0 += (h0 - hbar) * iSp;
