@@ -458,8 +458,11 @@ __global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviPa
   int n_tail = 0;
   SaddlePair sp;
   sp.init((double)cg0, (double)cg1);
+  const typename Vec4<real>::type* pw = reinterpret_cast<const typename Vec4<real>::type*>(p.pw) + g;
+  typename Vec4<real>::type nxt = pw[0];
   for (int r = 0; r < p.R; ++r) {
-    const typename Vec4<real>::type rec = reinterpret_cast<const typename Vec4<real>::type*>(p.pw)[(size_t)r * p.G + g];
+    const typename Vec4<real>::type rec = nxt;
+    if (r + 1 < p.R) nxt = pw[(size_t)(r + 1) * p.G];  // the next draw's record is in flight while this one is evaluated
     const bool saddle = dirichlet_pair_is_saddle((double)rec.x, (double)rec.y, (double)cg0, (double)cg1);
     if (saddle) {
       double dg0, dg1;
