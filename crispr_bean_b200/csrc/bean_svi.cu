@@ -1,14 +1,17 @@
 // bean_svi.cu -- the fused SVI step of the variant sorting models (Normal / ControlNormal / MixtureNormal).
 //
-// Per step, two kernels and no host round trip (reference: one `svi.step`, bean/model/run.py:376-380,
-// ~2,500 eager torch op dispatches):
+// Per step, three kernels (two for the Normal models) and no host round trip (reference: one `svi.step`,
+// bean/model/run.py:376-380, ~2,500 eager torch op dispatches):
 //
 //   svi_guide_kernel   one thread per guide, looping over its replicates with everything in registers:
 //       draw (mu, sd) of its variant and pi[r] ~ Dirichlet (counter-based Philox), Normal-CDF bin masses,
 //       allele mixture, get_alpha + Dirichlet-Multinomial of both count layers with their digamma
-//       differences, the Dirichlet / Multinomial editing-rate sites, the pathwise Dirichlet derivative,
-//       the alpha_pi gradient AND its ClippedAdam update (alpha_pi is per-guide, so it never leaves the
-//       thread), per-guide d ELBO / d(mu, sd), ELBO partial per CTA.
+//       differences, the Dirichlet / Multinomial editing-rate sites, per-guide d ELBO / d(mu, sd), ELBO partial
+//       per warp; hands every draw (pi0, pi1) with its upstream weights to the alpha kernel.
+//   svi_alpha_kernel   (MixtureNormal) one thread per guide: the pathwise Dirichlet derivative of each draw
+//       (saddle-point pairs in double, the other regimes through a per-warp queue), the alpha_pi gradient AND
+//       its ClippedAdam update (alpha_pi is per-guide, so it never leaves the thread).  With no hand-over scratch
+//       (BeanSviState.pw == NULL) the guide kernel does this part itself.
 //   svi_variant_kernel 8 lanes per variant: segmented reduction of the per-guide gradients over the CSR
 //       variant range (no atomics; guides of a variant are contiguous, data_class.py:511-532), prior and
 //       entropy terms, ClippedAdam on (mu_loc, mu_scale, sd_loc, sd_scale), and -- in the last CTA to
