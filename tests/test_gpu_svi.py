@@ -8,6 +8,8 @@ its fp32 tolerance is 2e-4 relative to the gradient's scale (stated here, tight 
 """
 import math
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -290,3 +292,42 @@ def test_split_and_fused_guide_step_agree(cuda_device, dtype, rtol):
     torch.testing.assert_close(runs[0][0], runs[1][0], rtol=1e-9 if dtype == torch.float64 else 1e-6, atol=0)
     for k, v in runs[0][1].items():
         torch.testing.assert_close(v, runs[1][1][k], rtol=rtol, atol=rtol * 1e-2)
+
+
+def test_sampler_distribution_probability_integral_transform(cuda_device):
+    """Every recorded pi draw pushed through ITS OWN Beta CDF must be uniform (Kolmogorov-Smirnov), across concentrations
+    from 1e-2 (Marsaglia-Tsang boost path, draws piling up at the clamps) to 1e3; and the Normal draws must be normal."""
+    from scipy import stats
+
+    data = H.make_small_mixture_data(n_variants=2500, n_reps=8, with_bulk_bin=False, seed=19)
+    eng = SviEngine(data, "MixtureNormal", cuda_device, dtype=torch.float32, num_steps=2, seed=11)
+    g = torch.Generator().manual_seed(1)
+    eng.alpha_u.copy_(torch.rand(eng.alpha_u.shape, generator=g) * 10 - 5)  # alpha_pi in e^-5 .. e^5
+    eng.gradients({"record": True})
+    al = eng.alpha_u.double().exp().cpu()
+    conc = (al / al.sum(-1, keepdim=True) * eng.pi_a0.double().cpu()[:, None]).clamp(min=1e-5).numpy()  # (G, 2)
+    pi1 = eng.pi_used.double().cpu()[:, :, 1].numpy()  # (G, R)
+    # float32 draws are clamped to [FLT_MIN, 1 - 2^-24] (like torch._sample_dirichlet): for a concentration c the clamp holds
+    # a point mass of ~ (1e-38)^c, so the KS test is run where that is negligible (c > 0.5) ...
+    keep = conc.min(-1) > 0.5
+    u = stats.beta.cdf(pi1[keep], conc[keep, 1:2], conc[keep, 0:1]).reshape(-1)
+    assert u.size > 30_000
+    ks = stats.kstest(u, "uniform")
+    assert ks.statistic < 1.63 / np.sqrt(u.size) * 1.5, ks  # 1 % critical value, with 50 % slack for float32 rounding of the draws
+    for lo, hi in ((0.5, 1.0), (1.0, 30.0), (30.0, 1e4)):  # within concentration bands (boost path / plain / large)
+        band = (conc.min(-1) >= lo) & (conc.min(-1) < hi)
+        if band.sum() * pi1.shape[1] > 3000:
+            ub = stats.beta.cdf(pi1[band], conc[band, 1:2], conc[band, 0:1]).reshape(-1)
+            assert stats.kstest(ub, "uniform").statistic < 1.63 / np.sqrt(ub.size) * 1.5, (lo, hi)
+    # ... and for small concentrations (most draws near 0 or 1, Marsaglia-Tsang boost U^(1/c)) the mass below fixed
+    # thresholds is compared with the Beta CDF (binomial 4-sigma bands)
+    small = (conc[:, 1] > 1e-2) & (conc[:, 1] < 0.5) & (conc[:, 0] > 1.0)
+    assert small.sum() > 100
+    for thr in (1e-30, 1e-12, 1e-4, 1e-1):
+        p_theory = stats.beta.cdf(thr, conc[small, 1:2], conc[small, 0:1])  # (n, 1) per guide
+        expect = (p_theory * pi1.shape[1]).sum()
+        var = (p_theory * (1 - p_theory) * pi1.shape[1]).sum()
+        got = (pi1[small] <= thr).sum()
+        assert abs(got - expect) <= 4 * np.sqrt(var) + 2, (thr, got, expect)
+    eps = eng.eps_used.double().cpu().numpy().reshape(-1)
+    assert stats.kstest(eps, "norm").statistic < 0.02
