@@ -440,6 +440,10 @@ __device__ __forceinline__ void alpha_update(const SviParams<real>& p, int g, re
   }
 }
 
+template <typename real> struct SaddleOf;
+template <> struct SaddleOf<float> { typedef SaddlePairF type; };
+template <> struct SaddleOf<double> { typedef SaddlePair type; };
+
 // Second half of the split guide step: pathwise Dirichlet derivative of every draw (saddle-point pairs in place, the other
 // regimes through the per-warp queue), alpha_pi gradient and its ClippedAdam update.  One thread per guide.
 constexpr int ALPHA_THREADS = 128;
@@ -459,8 +463,9 @@ __global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviPa
   const typename Vec4<real>::type dc = reinterpret_cast<const typename Vec4<real>::type*>(p.dconc)[g];
   real dcg0 = dc.z, dcg1 = dc.w;
   int n_tail = 0;
-  SaddlePair sp;
-  sp.init((double)cg0, (double)cg1);
+  // saddle-point regime: float kernels use the cancellation-free single-precision form, double kernels torch's expression
+  typename SaddleOf<real>::type sp;
+  sp.init(cg0, cg1);
   const typename Vec4<real>::type* pw = reinterpret_cast<const typename Vec4<real>::type*>(p.pw) + g;
   typename Vec4<real>::type nxt = pw[0];
   for (int r = 0; r < p.R; ++r) {
@@ -468,10 +473,10 @@ __global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviPa
     if (r + 1 < p.R) nxt = pw[(size_t)(r + 1) * p.G];  // the next draw's record is in flight while this one is evaluated
     const bool saddle = dirichlet_pair_is_saddle((double)rec.x, (double)rec.y, (double)cg0, (double)cg1);
     if (saddle) {
-      double dg0, dg1;
-      sp.eval((double)rec.x, (double)rec.y, dg0, dg1);
-      dcg0 += real(dg0 * (double)rec.z);
-      dcg1 += real(dg1 * (double)rec.w);
+      real dg0, dg1;
+      sp.eval(rec.x, rec.y, dg0, dg1);
+      dcg0 += dg0 * rec.z;
+      dcg1 += dg1 * rec.w;
     }
     n_tail = tail_queue_push(tq, n_tail, wmask, lane, !saddle, rec.x, rec.y, cg0, cg1, rec.z, rec.w);
     if (n_tail >= 32) {
