@@ -410,26 +410,24 @@ struct SaddlePair {
 //   term1 + term2 (+-term4) = C2 D / delta^2 + beta (2 alpha - beta) / (s T^3 delta),   D = l(u) G^-1.5 - 1,
 //   C2 = 2 alpha beta^2 / (s T^4), s = sqrt(2 alpha beta / T); the 1 / delta term equals -C2 c1 / delta with
 //   c1 = T (2 alpha - beta) / (2 alpha beta) and D = -c1 delta + O(delta^2), so
-//   term1234 = C2 (D + c1 delta) / delta^2 - s l(u) / alpha,      D = expm1(log1p(l1(u)) - 1.5 log1p(G1)).
+//   term1234 = C2 (D + c1 delta) / delta^2 - s l(u) / alpha,      D = (1 + l1(u)) (1 + expm1(-1.5 log1p(G1))) - 1.
 // l1 and g1 are series for small |y| (no cancellation), the defining expressions otherwise.  The second component is the
 // same with alpha <-> beta, u <-> v, delta -> -delta, and shares g1(u), g1(v), G.
-__device__ __forceinline__ float saddle_l1(float y) {  // log1p(y) / y - 1
+// (l1, g1)(y) = (log1p(y) / y - 1,  2 (y - log1p(y)) / y^2 - 1): series for small |y|, one shared log1p otherwise
+__device__ __forceinline__ void saddle_l1_g1(float y, float& l1, float& g1) {
   if (fabsf(y) < 0.3f) {
-    float acc = 1.0f / 13.0f;
+    float p = 1.0f / 13.0f, q = 2.0f / 14.0f;
 #pragma unroll
-    for (int k = 12; k >= 2; --k) acc = fmaf(acc, y, (k & 1) ? 1.0f / k : -1.0f / k);
-    return acc * y;
-  }
-  return log1pf(y) * rcp_ftz(y) - 1.0f;
-}
-__device__ __forceinline__ float saddle_g1(float y) {  // 2 (y - log1p(y)) / y^2 - 1
-  if (fabsf(y) < 0.3f) {
-    float acc = 2.0f / 14.0f;
+    for (int k = 12; k >= 2; --k) p = fmaf(p, y, (k & 1) ? 1.0f / k : -1.0f / k);
 #pragma unroll
-    for (int k = 13; k >= 3; --k) acc = fmaf(acc, y, (k & 1) ? -2.0f / k : 2.0f / k);
-    return acc * y;
+    for (int k = 13; k >= 3; --k) q = fmaf(q, y, (k & 1) ? -2.0f / k : 2.0f / k);
+    l1 = p * y;
+    g1 = q * y;
+  } else {
+    const float lp = log1pf(y), iy = rcp_ftz(y);
+    l1 = lp * iy - 1.0f;
+    g1 = 2.0f * (y - lp) * iy * iy - 1.0f;
   }
-  return 2.0f * (y - log1pf(y)) * rcp_ftz(y * y) - 1.0f;
 }
 
 struct SaddlePairF {
@@ -463,10 +461,11 @@ struct SaddlePairF {
       return;
     }
     const float u = d * im, v = -d * iom;
-    const float l1u = saddle_l1(u), l1v = saddle_l1(v);
-    const float G1 = om * saddle_g1(u) + m * saddle_g1(v);
-    const float lG = 1.5f * log1pf(G1);
-    const float D0 = expm1f(log1pf(l1u) - lG), D1 = expm1f(log1pf(l1v) - lG);
+    float l1u, l1v, g1u, g1v;
+    saddle_l1_g1(u, l1u, g1u);
+    saddle_l1_g1(v, l1v, g1v);
+    const float wm1 = expm1f(-1.5f * log1pf(om * g1u + m * g1v));           // G^-1.5 - 1
+    const float D0 = l1u + wm1 + l1u * wm1, D1 = l1v + wm1 + l1v * wm1;    // (1 + l1)(1 + wm1) - 1
     const float id2 = rcp_ftz(d * d);
     const float t0 = C2a * (D0 + c1a * d) * id2 - s * (1.0f + l1u) * ia;
     const float t1 = C2b * (D1 - c1b * d) * id2 - s * (1.0f + l1v) * ib;

@@ -42,8 +42,8 @@ def saddle_pair_f32(x0, a, b):
     c1a, c1b = h * (2 * a - b), h * (2 * b - a)
     l1u, l1v = l1(u), l1(v)
     G1 = om * g1(u) + m * g1(v)
-    lG = f(1.5) * np.log1p(G1)
-    D0, D1 = np.expm1(np.log1p(l1u) - lG), np.expm1(np.log1p(l1v) - lG)
+    wm1 = np.expm1(f(-1.5) * np.log1p(G1))  # G^-1.5 - 1
+    D0, D1 = l1u + wm1 + l1u * wm1, l1v + wm1 + l1v * wm1  # (1 + l1)(1 + wm1) - 1
     t0 = C2a * (D0 + c1a * d) / (d * d) - s * (1 + l1u) / a
     t1 = C2b * (D1 - c1b * d) / (d * d) - s * (1 + l1v) / b
     return float(stir * (-x0 / s) * t0), float(stir * (-(1 - x0) / s) * t1)
