@@ -89,3 +89,54 @@ def read_csvs(guides_csv: str, samples_csv: str, counts_csv: str,
     for name, path in (layer_csvs or {}).items():
         layers[name] = pd.read_csv(path, index_col=0).loc[guides.index, samples.index].to_numpy()
     return MiniScreen(counts.to_numpy(), guides, samples, layers)
+
+
+# ---- .h5ad input without h5py / anndata ----------------------------------------------
+def _h5ad_value(node):
+    """Decode one element of anndata's on-disk format (encoding-type attributes, anndata >= 0.8)."""
+    from . import h5lite
+
+    enc = node.attrs.get("encoding-type", None)
+    if isinstance(node, h5lite.Dataset):
+        val = node.read()
+        if enc in ("string", "numeric-scalar") and isinstance(val, np.ndarray) and val.shape == ():
+            val = val[()]
+        return val
+    if enc == "dataframe":
+        return _h5ad_dataframe(node)
+    if enc == "categorical":
+        codes, cats = node["codes"].read(), node["categories"].read()
+        return pd.Categorical.from_codes(codes, categories=pd.Index(cats), ordered=bool(node.attrs.get("ordered", False)))
+    if enc in ("csr_matrix", "csc_matrix"):
+        from scipy import sparse
+
+        shape = tuple(int(v) for v in node.attrs["shape"])
+        cls = sparse.csr_matrix if enc == "csr_matrix" else sparse.csc_matrix
+        return cls((node["data"].read(), node["indices"].read(), node["indptr"].read()), shape=shape).toarray()
+    if enc in ("nullable-integer", "nullable-boolean"):
+        vals, mask = node["values"].read(), node["mask"].read().astype(bool)
+        return pd.array(np.where(mask, 0, vals), dtype="Int64" if enc == "nullable-integer" else "boolean").__setitem__(mask, pd.NA) or vals
+    return {k: _h5ad_value(node[k]) for k in node.keys()}  # "dict" and anything unknown: a plain mapping
+
+
+def _h5ad_dataframe(group) -> pd.DataFrame:
+    index_key = group.attrs.get("_index", "_index")
+    order = [str(c) for c in np.atleast_1d(group.attrs.get("column-order", []))]
+    index = pd.Index(np.asarray(group[index_key].read()), name=None if index_key == "_index" else index_key)
+    cols = {}
+    for c in order:
+        cols[c] = _h5ad_value(group[c])  # a "/" in a column name is a nested HDF5 group; the path lookup follows it
+    return pd.DataFrame(cols, index=index)
+
+
+def read_h5ad(path: str) -> MiniScreen:
+    """Read a ReporterScreen `.h5ad` (bean/framework/ReporterScreen.py:1009) into a MiniScreen with the pure-Python
+    HDF5 reader `h5lite`: X (guides x samples), layers, obs -> .guides, var -> .samples, uns (nested tables, scalars)."""
+    from . import h5lite
+
+    f = h5lite.File(path)
+    X = _h5ad_value(f["X"])
+    guides, samples = _h5ad_dataframe(f["obs"]), _h5ad_dataframe(f["var"])
+    layers = {k: np.asarray(_h5ad_value(f["layers"][k])) for k in f["layers"].keys()} if "layers" in f.root else {}
+    uns = _h5ad_value(f["uns"]) if "uns" in f.root else {}
+    return MiniScreen(np.asarray(X), guides, samples, layers, uns)
