@@ -65,6 +65,14 @@ class ScreenData:
 
         screen = screen.copy()
         smp = screen.samples
+        if not (replicate_column in smp.columns and condition_column in smp.columns):
+            # data_class.py:64-70: sample names "<replicate>_<condition>" supply both columns when either is absent
+            parts = [str(s).rsplit("_", 1) for s in smp.index]
+            if any(len(p) != 2 for p in parts):
+                raise ValueError(f"screen.samples lacks '{replicate_column}' / '{condition_column}' and the sample names "
+                                 "are not of the form <replicate>_<condition>.")
+            smp[replicate_column] = [p[0] for p in parts]
+            smp[condition_column] = [p[1] for p in parts]
         covs = screen.uns.get("sample_covariates")
         if covs is not None:
             # sample covariates (data_class.py:75-92): a "replicate" becomes a (replicate, covariates...) combination

@@ -135,6 +135,53 @@ def tiling_cases(ns):
     return out
 
 
+def real_cases(ns):
+    """The reference's own test screens (tests/data/*.h5ad, the inputs of its tests/test_run.py), read with the
+    repo's HDF5 reader and prepared as cli/run.py does (guides sorted by target, negative controls from
+    `target_group`).  The screens travel inside the fixtures, so the tests never open /root/reference."""
+    from crispr_bean_b200.screen import read_h5ad
+
+    ref_data = "/root/reference/tests/data/"
+    m, sm, dc = ns.model, ns.survival_model, ns.data_class
+
+    def load(name):
+        scr = read_h5ad(ref_data + name + ".h5ad")
+        if "target" in scr.guides.columns:
+            scr = scr[np.argsort(scr.guides["target"].to_numpy(), kind="stable"), :]
+        scr.samples["mask"] = 1
+        for key in ("edit_counts",):  # not read by `bean run`; keeps the fixtures small
+            scr.uns.pop(key, None)
+        return scr
+
+    var, til = load("var_mini_screen"), load("tiling_mini_screen")
+    svar, stil = load("survival_var_mini_screen"), load("survival_tiling_mini_screen")
+    sort_kw = dict(condition_column="condition", control_condition="bulk", control_can_be_selected=True)
+    surv_kw = dict(condition_column="condition", time_column="time", control_condition="D7", control_can_be_selected=True)
+    negctrl = np.where(svar.guides["target_group"].map(lambda s: s.lower()) == "negctrl")[0].tolist()
+    til_kw = dict(allele_df_key="allele_counts", control_guide_tag=None)
+    return [
+        # tests/test_run.py: `bean run sorting variant ... --uniform-edit` / default / `--fit-negctrl`
+        ("real_var_mini_normal", var, dc.VariantSortingScreenData, sort_kw, partial(m.NormalModel, use_bcmatch=False), m.NormalGuide,
+         "Normal", dict(use_bcmatch=False)),
+        ("real_var_mini_mixture", var, dc.VariantSortingReporterScreenData, sort_kw, m.MixtureNormalModel, m.MixtureNormalGuide,
+         "MixtureNormal", {}),
+        ("real_var_mini_control_normal", var, dc.VariantSortingScreenData, sort_kw, partial(m.ControlNormalModel, use_bcmatch=False),
+         partial(m.ControlNormalGuide, use_bcmatch=False), "ControlNormal", dict(use_bcmatch=False)),
+        # `bean run sorting tiling ... --allele-df-key allele_counts --control-guide-tag None`
+        ("tiling_real_mini", til, dc.TilingSortingReporterScreenData, dict(sort_kw, **til_kw),
+         partial(m.MultiMixtureNormalModel, scale_by_accessibility=False, use_bcmatch=(True,)),
+         partial(m.MultiMixtureNormalGuide, scale_by_accessibility=False, fit_noise=True), "MultiMixtureNormal", {}),
+        # `bean run survival variant ... --control-condition=D7` (+ --uniform-edit)
+        ("survival_real_var_normal", svar, dc.VariantSurvivalScreenData, dict(surv_kw, negctrl_guide_idx=negctrl),
+         partial(sm.NormalModel, use_bcmatch=False), sm.NormalGuide, "Normal", dict(use_bcmatch=False)),
+        ("survival_real_var_mixture", svar, dc.VariantSurvivalReporterScreenData, dict(surv_kw, negctrl_guide_idx=negctrl),
+         sm.MixtureNormalModel, sm.MixtureNormalGuide, "MixtureNormal", {}),
+        ("survival_tiling_real_mini", stil, dc.TilingSurvivalReporterScreenData, dict(surv_kw, control_condition="D0", **til_kw),
+         partial(sm.MultiMixtureNormalModel, use_bcmatch=(True,)), partial(sm.MultiMixtureNormalGuide, fit_noise=True),
+         "MultiMixtureNormal", {}),
+    ]
+
+
 def with_allele_objects(ns, screen):
     """The reference's tiling tensoriser works on `Allele` objects (bean/framework/Edit.py); the stored screen and
     our tensoriser hold their string form."""
@@ -230,10 +277,15 @@ def main():
         os.environ["PYTHONHASHSEED"] = "0"
         os.execv(sys.executable, [sys.executable] + sys.argv)
     ns = load_reference()
-    result_table_golden(ns)
+    if not sys.argv[1:]:
+        result_table_golden(ns)
     traj = ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise", "survival_normal", "survival_mixture",
-            "tiling_small", "survival_tiling_acc", "normal_covariates")
-    for case in sorting_cases(ns) + survival_cases(ns) + tiling_cases(ns):
+            "tiling_small", "survival_tiling_acc", "normal_covariates",
+            "real_var_mini_mixture", "tiling_real_mini", "survival_real_var_mixture")
+    only = sys.argv[1:]  # optional: case-name prefixes to regenerate
+    for case in sorting_cases(ns) + survival_cases(ns) + tiling_cases(ns) + real_cases(ns):
+        if only and not case[0].startswith(tuple(only)):
+            continue
         write_case(ns, *case, n_traj=6 if case[0] in traj else 0)
 
 
