@@ -4,12 +4,14 @@ loss and gradients w.r.t. the unconstrained parameters at the reference's initia
 reparameterisation draws, and a 6-step `run_inference` trajectory (ClippedAdam, lr decay).
 Tolerances: 1e-9 fp64 / 1e-5 fp32 relative (north_star); alpha_pi fp32 2e-4 (see test_gpu_svi.py)."""
 import ast
+import os
 
 import numpy as np
 import pytest
 import torch
 
 from crispr_bean_b200.svi import SviEngine
+from tests.helpers import GOLDEN
 from tests.test_reference_golden import PROGRAMS, SORTING, edit_perm, group, load_case, oracle_kwargs, to_ours
 
 pytestmark = pytest.mark.gpu
@@ -69,8 +71,7 @@ def test_fused_step_equals_reference_programs(cuda_device, name, dtype, tag, tol
         assert e <= (tol_alpha if k == "alpha_pi" else tol), f"{k}: {e:.3e}"
 
 
-@pytest.mark.parametrize("name", [c for c in FUSED if c in ("mixture_small", "normal_c1", "control_normal_c1", "mixture_acc_fitnoise",
-                                                              "survival_normal", "survival_mixture", "tiling_small", "survival_tiling_acc", "normal_covariates")])
+@pytest.mark.parametrize("name", [c for c in FUSED if "traj/n_steps" in np.load(os.path.join(GOLDEN, f"ref_{c}.npz")).files])
 def test_fused_run_follows_reference_run_inference(cuda_device, name):
     z, data = load_case(name)
     n = int(z["traj/n_steps"])
