@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libbean_b200.so")
 
 BEAN_OK = 0
 MODE_SORTING, MODE_SURVIVAL = 0, 1
-MAX_BINS, MAX_RB, MAX_ALLELES, MAX_LAYERS = 8, 64, 32, 2
+MAX_BINS, MAX_RB, MAX_ALLELES, MAX_LAYERS = 8, 64, 4096, 2
 
 
 class BeanError(RuntimeError):
@@ -79,7 +79,7 @@ class BeanAlleleMap(C.Structure):
 
 
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 3  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 4  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -88,7 +88,7 @@ _PROTOTYPES = {
     "bean_abi_version": (C.c_int, []),
     "bean_last_error": (C.c_char_p, []),
     "bean_device_sm_count": (C.c_int, []),
-    "bean_ll_num_partials": (C.c_int, [C.c_int32]),
+    "bean_ll_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
     "bean_ll_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
     "bean_ll_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanLLArgs), C.c_void_p]),
     "bean_allele_gather_f32": (C.c_int, _GATHER), "bean_allele_gather_f64": (C.c_int, _GATHER),

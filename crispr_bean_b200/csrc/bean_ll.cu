@@ -1,6 +1,7 @@
 // bean_ll.cu -- count log-likelihood forward + local gradients (generic in R, B, A, layers, mode).
 //
-// One thread owns one guide: it builds e[r][b] = sum_a pi[r][a] P[b][a] in per-thread scratch, scores
+// One thread (few alleles) or one warp (tiling: many alleles) owns one guide: it builds
+// e[r][b] = sum_a pi[r][a] P[b][a] in per-thread scratch, scores
 // every (replicate, layer) row with the Dirichlet-Multinomial and turns the digamma differences into
 // d ll / d e in the same pass, then contracts d ll / d e back onto (mu, sd, pi) per allele.  Replaces
 // bean/model/utils.py:10-76 + bean/model/model.py:495-547 (survival_model.py:352-424) and their
@@ -44,6 +45,8 @@ int validate_screen(const BeanScreen* s) {
 }
 
 constexpr int LL_THREADS = 128;
+constexpr int LL_WIDE_WARPS = 4;          // guides per CTA of the warp-per-guide kernel
+constexpr int LL_WIDE_MIN_ALLELES = 8;    // from this many alleles per guide on, a warp owns a guide
 
 template <typename real>
 struct LLParams {
@@ -81,93 +84,143 @@ __device__ __forceinline__ void allele_bin_probs(const LLParams<real>& p, real m
   }
 }
 
+// Dirichlet-Multinomial over every (replicate, layer) row of guide g.  In: e[r][b] expected bin fractions.
+// Out: e[r][b] = d ll / d e[r][b]; returns the guide's masked log-likelihood.  `writer` stores ll_row.
+template <typename real>
+__device__ __forceinline__ double ll_rows(const LLParams<real>& p, int g, real* e, bool writer) {
+  const int R = p.R, B = p.B;
+  const real eps = real(1e-5);
+  double ll_acc = 0.0;
+  for (int r = 0; r < R; ++r) {
+    const bool rmask = p.row_mask[(size_t)g * R + r] != 0;
+    real de[BEAN_MAX_BINS];
+    for (int b = 0; b < B; ++b) de[b] = real(0);
+    for (int l = 0; l < p.L; ++l) {
+      const real* xr = p.x + (((size_t)l * p.G + g) * R + r) * B;
+      const real a0 = p.a0[(size_t)l * p.G + g];
+      real xb[BEAN_MAX_BINS] = {}, pb[BEAN_MAX_BINS];
+      real N = real(0), S = real(0);
+      for (int b = 0; b < B; ++b) {
+        xb[b] = xr[b];
+        N += xb[b];
+        pb[b] = e[r * B + b] * p.t.sf[l][r * B + b];
+        S += pb[b];
+      }
+      const bool w = rmask && (N > p.mask_thres);
+      const real inv = real(1) / (S + eps);
+      real ab[BEAN_MAX_BINS] = {}, frac[BEAN_MAX_BINS];
+      bool live[BEAN_MAX_BINS];
+      real Asum = real(0);
+      for (int b = 0; b < B; ++b) {
+        frac[b] = (pb[b] + eps / real(B)) * inv;
+        const real raw = frac[b] * a0 * p.t.smask[r * B + b];
+        live[b] = raw >= eps;  // clamp(min=eps) passes gradient where input >= eps
+        ab[b] = live[b] ? raw : eps;
+        Asum += ab[b];
+      }
+      real psi_diff[BEAN_MAX_BINS];
+      const real V = dm_row_kl<real, BEAN_MAX_BINS>(B, xb, ab, N, Asum, psi_diff);
+      // data-only part of the log-pmf, hoisted to tensorisation time (row_const is NULL -> 0)
+      const double K = p.row_const ? p.row_const[((size_t)l * p.G + g) * R + r] : 0.0;
+      const double ll = (double)V + K;
+      real gb[BEAN_MAX_BINS];
+      real dot = real(0);
+      for (int b = 0; b < B; ++b) {
+        gb[b] = live[b] ? psi_diff[b] * p.t.smask[r * B + b] : real(0);
+        dot += gb[b] * frac[b];
+      }
+      if (writer && p.ll_row) p.ll_row[((size_t)l * p.G + g) * R + r] = w ? real(ll) : real(0);
+      if (w) {
+        ll_acc += ll;
+        const real c = a0 * inv;
+        for (int b = 0; b < B; ++b) de[b] += p.t.sf[l][r * B + b] * c * (gb[b] - dot);
+      }
+    }
+    for (int b = 0; b < B; ++b) e[r * B + b] = de[b];
+  }
+  return ll_acc;
+}
+
+// One guide, alleles a0, a0 + stride, ...: pass 1 accumulates e[r][b] += pi[r][a] P[b][a].
+template <typename real>
+__device__ __forceinline__ void ll_mix_alleles(const LLParams<real>& p, int g, int a0, int stride, real* e) {
+  const int R = p.R, B = p.B, A = p.A;
+  real P[BEAN_MAX_BINS], dPm[BEAN_MAX_BINS], dPs[BEAN_MAX_BINS];
+  for (int a = a0; a < A; a += stride) {
+    const bool exists = p.allele_mask == nullptr || p.allele_mask[(size_t)g * A + a] != 0;
+    allele_bin_probs(p, p.mu[(size_t)g * A + a], p.sd[(size_t)g * A + a], exists, P, dPm, dPs);
+    for (int r = 0; r < R; ++r) {
+      const real w = p.pi ? p.pi[((size_t)g * R + r) * A + a] : real(1);
+      for (int b = 0; b < B; ++b) e[r * B + b] += w * P[b];
+    }
+  }
+}
+
+// Pass 3: contract d ll / d e (in e[]) onto (mu, sd, pi) of alleles a0, a0 + stride, ...
+template <typename real>
+__device__ __forceinline__ void ll_contract_alleles(const LLParams<real>& p, int g, int a0, int stride, const real* e) {
+  const int R = p.R, B = p.B, A = p.A;
+  real P[BEAN_MAX_BINS], dPm[BEAN_MAX_BINS], dPs[BEAN_MAX_BINS];
+  for (int a = a0; a < A; a += stride) {
+    const bool exists = p.allele_mask == nullptr || p.allele_mask[(size_t)g * A + a] != 0;
+    allele_bin_probs(p, p.mu[(size_t)g * A + a], p.sd[(size_t)g * A + a], exists, P, dPm, dPs);
+    real dmu = real(0), dsd = real(0);
+    for (int r = 0; r < R; ++r) {
+      const real w = p.pi ? p.pi[((size_t)g * R + r) * A + a] : real(1);
+      real dpi = real(0);
+      for (int b = 0; b < B; ++b) {
+        const real d = e[r * B + b];
+        dpi += d * P[b];
+        dmu += d * w * dPm[b];
+        dsd += d * w * dPs[b];
+      }
+      if (p.d_pi) p.d_pi[((size_t)g * R + r) * A + a] = dpi;
+    }
+    p.d_mu[(size_t)g * A + a] = dmu;
+    p.d_sd[(size_t)g * A + a] = dsd;
+  }
+}
+
+// Few alleles (variant designs, A <= LL_WIDE_MIN_ALLELES): one thread owns one guide.
 template <typename real>
 __global__ void __launch_bounds__(LL_THREADS) ll_generic_kernel(const LLParams<real> p) {
   __shared__ double red[32];
   const int g = blockIdx.x * LL_THREADS + threadIdx.x;
-  const int R = p.R, B = p.B, A = p.A;
-  const real eps = real(1e-5);
   double ll_acc = 0.0;
   if (g < p.G) {
     real e[BEAN_MAX_RB];
-    real P[BEAN_MAX_BINS], dPm[BEAN_MAX_BINS], dPs[BEAN_MAX_BINS];
-    for (int i = 0; i < R * B; ++i) e[i] = real(0);
-    // ---- pass 1: expected bin fractions e[r][b] -------------------------------------------------
-    for (int a = 0; a < A; ++a) {
-      const bool exists = p.allele_mask == nullptr || p.allele_mask[(size_t)g * A + a] != 0;
-      allele_bin_probs(p, p.mu[(size_t)g * A + a], p.sd[(size_t)g * A + a], exists, P, dPm, dPs);
-      for (int r = 0; r < R; ++r) {
-        const real w = p.pi ? p.pi[((size_t)g * R + r) * A + a] : real(1);
-        for (int b = 0; b < B; ++b) e[r * B + b] += w * P[b];
-      }
+    for (int i = 0; i < p.R * p.B; ++i) e[i] = real(0);
+    ll_mix_alleles(p, g, 0, 1, e);
+    ll_acc = ll_rows(p, g, e, true);
+    ll_contract_alleles(p, g, 0, 1, e);
+  }
+  const double tot = block_sum(ll_acc, red);
+  if (threadIdx.x == 0) p.ll_partial[blockIdx.x] = tot;
+}
+
+// Many alleles per guide (tiling designs: tens to hundreds): one WARP owns one guide, lanes stride over the
+// alleles so that mu/sd/pi/d_pi rows are read and written coalesced; e[r][b] is completed by a butterfly
+// all-reduce (every lane ends with the same bits), the R x L rows are then scored redundantly by all lanes.
+template <typename real>
+__global__ void __launch_bounds__(LL_WIDE_WARPS * 32) ll_wide_kernel(const LLParams<real> p) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * LL_WIDE_WARPS + (threadIdx.x >> 5);
+  double ll_acc = 0.0;
+  if (g < p.G) {  // warp-uniform
+    real e[BEAN_MAX_RB];
+    const int RB = p.R * p.B;
+    for (int i = 0; i < RB; ++i) e[i] = real(0);
+    ll_mix_alleles(p, g, lane, 32, e);
+    for (int i = 0; i < RB; ++i) {
+      real v = e[i];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      e[i] = v;
     }
-    // ---- pass 2: Dirichlet-Multinomial per (replicate, layer) row; e[] becomes d ll / d e ---------
-    for (int r = 0; r < R; ++r) {
-      const bool rmask = p.row_mask[(size_t)g * R + r] != 0;
-      real de[BEAN_MAX_BINS];
-      for (int b = 0; b < B; ++b) de[b] = real(0);
-      for (int l = 0; l < p.L; ++l) {
-        const real* xr = p.x + (((size_t)l * p.G + g) * R + r) * B;
-        const real a0 = p.a0[(size_t)l * p.G + g];
-        real xb[BEAN_MAX_BINS] = {}, pb[BEAN_MAX_BINS];
-        real N = real(0), S = real(0);
-        for (int b = 0; b < B; ++b) {
-          xb[b] = xr[b];
-          N += xb[b];
-          pb[b] = e[r * B + b] * p.t.sf[l][r * B + b];
-          S += pb[b];
-        }
-        const bool w = rmask && (N > p.mask_thres);
-        const real inv = real(1) / (S + eps);
-        real ab[BEAN_MAX_BINS] = {}, frac[BEAN_MAX_BINS];
-        bool live[BEAN_MAX_BINS];
-        real Asum = real(0);
-        for (int b = 0; b < B; ++b) {
-          frac[b] = (pb[b] + eps / real(B)) * inv;
-          const real raw = frac[b] * a0 * p.t.smask[r * B + b];
-          live[b] = raw >= eps;  // clamp(min=eps) passes gradient where input >= eps
-          ab[b] = live[b] ? raw : eps;
-          Asum += ab[b];
-        }
-        real psi_diff[BEAN_MAX_BINS];
-        const real V = dm_row_kl<real, BEAN_MAX_BINS>(B, xb, ab, N, Asum, psi_diff);
-        // data-only part of the log-pmf, hoisted to tensorisation time (row_const is NULL -> 0)
-        const double K = p.row_const ? p.row_const[((size_t)l * p.G + g) * R + r] : 0.0;
-        const double ll = (double)V + K;
-        real gb[BEAN_MAX_BINS];
-        real dot = real(0);
-        for (int b = 0; b < B; ++b) {
-          gb[b] = live[b] ? psi_diff[b] * p.t.smask[r * B + b] : real(0);
-          dot += gb[b] * frac[b];
-        }
-        if (p.ll_row) p.ll_row[((size_t)l * p.G + g) * R + r] = w ? real(ll) : real(0);
-        if (w) {
-          ll_acc += ll;
-          const real c = a0 * inv;
-          for (int b = 0; b < B; ++b) de[b] += p.t.sf[l][r * B + b] * c * (gb[b] - dot);
-        }
-      }
-      for (int b = 0; b < B; ++b) e[r * B + b] = de[b];
-    }
-    // ---- pass 3: contract d ll / d e onto (mu, sd, pi) per allele ---------------------------------
-    for (int a = 0; a < A; ++a) {
-      const bool exists = p.allele_mask == nullptr || p.allele_mask[(size_t)g * A + a] != 0;
-      allele_bin_probs(p, p.mu[(size_t)g * A + a], p.sd[(size_t)g * A + a], exists, P, dPm, dPs);
-      real dmu = real(0), dsd = real(0);
-      for (int r = 0; r < R; ++r) {
-        const real w = p.pi ? p.pi[((size_t)g * R + r) * A + a] : real(1);
-        real dpi = real(0);
-        for (int b = 0; b < B; ++b) {
-          const real d = e[r * B + b];
-          dpi += d * P[b];
-          dmu += d * w * dPm[b];
-          dsd += d * w * dPs[b];
-        }
-        if (p.d_pi) p.d_pi[((size_t)g * R + r) * A + a] = dpi;
-      }
-      p.d_mu[(size_t)g * A + a] = dmu;
-      p.d_sd[(size_t)g * A + a] = dsd;
-    }
+    const double ll = ll_rows(p, g, e, lane == 0);
+    if (lane == 0) ll_acc = ll;
+    ll_contract_alleles(p, g, lane, 32, e);
   }
   const double tot = block_sum(ll_acc, red);
   if (threadIdx.x == 0) p.ll_partial[blockIdx.x] = tot;
@@ -201,8 +254,11 @@ static int launch_ll(const BeanScreen* s, const BeanLLArgs* a, void* stream) {
   p.d_sd = static_cast<real*>(a->d_sd);
   p.d_pi = static_cast<real*>(a->d_pi);
   fill_tables(s, p.t);
-  const int grid = bean_ll_num_partials(s->n_guides);
-  ll_generic_kernel<real><<<grid, LL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const int grid = bean_ll_num_partials(s->n_guides, a->n_alleles);
+  if (a->n_alleles >= LL_WIDE_MIN_ALLELES)
+    ll_wide_kernel<real><<<grid, LL_WIDE_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    ll_generic_kernel<real><<<grid, LL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;
 }
@@ -222,7 +278,10 @@ int bean_device_sm_count(void) {
   return n;
 }
 
-int bean_ll_num_partials(int32_t n_guides) { return (n_guides + bean::LL_THREADS - 1) / bean::LL_THREADS; }
+int bean_ll_num_partials(int32_t n_guides, int32_t n_alleles) {
+  const int per_cta = n_alleles >= bean::LL_WIDE_MIN_ALLELES ? bean::LL_WIDE_WARPS : bean::LL_THREADS;
+  return (n_guides + per_cta - 1) / per_cta;
+}
 int bean_ll_f32(const BeanScreen* s, const BeanLLArgs* a, void* stream) { return bean::launch_ll<float>(s, a, stream); }
 int bean_ll_f64(const BeanScreen* s, const BeanLLArgs* a, void* stream) { return bean::launch_ll<double>(s, a, stream); }
 

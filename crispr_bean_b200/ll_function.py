@@ -43,7 +43,7 @@ def launch_ll(screen: DeviceScreen, mu_allele, sd_allele, pi=None, allele_mask=N
         allele_mask = allele_mask.to(torch.uint8).contiguous()
         args.allele_mask = allele_mask.data_ptr()
     ll_row = torch.empty((L, G, R), dtype=dtype, device=dev) if want_rows else None
-    partial = torch.empty((lib.bean_ll_num_partials(G),), dtype=torch.float64, device=dev)
+    partial = torch.empty((lib.bean_ll_num_partials(G, A),), dtype=torch.float64, device=dev)
     args.ll_row = ll_row.data_ptr() if want_rows else None
     args.ll_partial = partial.data_ptr()
     args.d_mu, args.d_sd = d_mu.data_ptr(), d_sd.data_ptr()

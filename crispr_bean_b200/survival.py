@@ -91,7 +91,9 @@ class SurvivalSviEngine(AutogradSviEngine):
         if model in ("MixtureNormal", "MultiMixtureNormal"):
             self.pi_a0 = torch.as_tensor(data.pi_a0).to(self.device)  # own dtype (float64), see generic.TilingSviEngine
             self.allele_counts_control = data.allele_counts_control.to(**kw)  # (R, C, G, 2)
-            self.control_timepoint = data.control_timepoint.to(**kw)
+            # own dtype (float64 in the reference's data class): exp(mu * t) and the control-allele Multinomial are then
+            # evaluated in double as in the reference, whose probability clamp [eps, 1 - eps] follows that dtype
+            self.control_timepoint = data.control_timepoint.to(self.device, torch.promote_types(data.control_timepoint.dtype, self.dtype))
             self.rg_mask = data.repguide_mask.to(self.device).unsqueeze(1)  # (R, 1, G)
             x0 = data.X[:, 0, :].to(**kw) + 1  # survival_model.py:306-311: observed initial abundance
             self.obs_abundance = x0 / global_sum(x0.sum(-1, keepdim=True), group)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 3
+#define BEAN_ABI_VERSION 4
 
 enum {
   BEAN_OK = 0,
@@ -44,7 +44,7 @@ enum { BEAN_MODE_SORTING = 0, BEAN_MODE_SURVIVAL = 1 };
 
 #define BEAN_MAX_BINS 8        /* n_condits incl. the control pseudo-bin */
 #define BEAN_MAX_RB 64         /* n_reps * n_bins per guide */
-#define BEAN_MAX_ALLELES 32
+#define BEAN_MAX_ALLELES 4096  /* alleles per guide incl. wild type (raw tiling allele tables reach hundreds) */
 #define BEAN_MAX_LAYERS 2
 
 int bean_abi_version(void);
@@ -91,7 +91,7 @@ typedef struct BeanScreen {
  *      pi                    real [G][R][A] allele weights, or NULL for "all ones" (A must be 1)
  *      allele_mask           u8   [G][A]   or NULL (tiling: 0 = allele does not exist, P := 0)
  * out: ll_row                real [L][G][R] masked per-row log-prob (0 where masked), may be NULL
- *      ll_partial            double [bean_ll_num_partials(G)] per-CTA partial sums of the masked ll
+ *      ll_partial            double [bean_ll_num_partials(G, A)] per-CTA partial sums of the masked ll
  *      d_mu, d_sd            real [G][A]   d(sum ll)/d(mu_allele, sd_allele)
  *      d_pi                  real [G][R][A] d(sum ll)/d(pi), may be NULL when pi is NULL
  * ---------------------------------------------------------------------------------------------- */
@@ -108,7 +108,7 @@ typedef struct BeanLLArgs {
   void* d_pi;
 } BeanLLArgs;
 
-int bean_ll_num_partials(int32_t n_guides);
+int bean_ll_num_partials(int32_t n_guides, int32_t n_alleles);
 int bean_ll_f32(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
 int bean_ll_f64(const BeanScreen* screen, const BeanLLArgs* args, void* stream);
 

@@ -18,6 +18,16 @@ from crispr_bean_b200.synth import make_sorting_screen, make_survival_screen, ma
 pytestmark = pytest.mark.gpu
 
 
+def golden_screen(case):
+    """One of the reference's own test screens (tests/data/*.h5ad), as stored in the reference-computed fixtures."""
+    import os
+
+    from tests.helpers import GOLDEN
+    from tests.refharness.golden import screen_from_arrays
+
+    return screen_from_arrays(np.load(os.path.join(GOLDEN, f"ref_{case}.npz")))
+
+
 def cli_args(**kw):
     base = dict(selection="sorting", library_design="variant", uniform_edit=False, scale_by_acc=False, ignore_bcmatch=False,
                 dont_fit_noise=False, guide_activity_col=None)
@@ -40,6 +50,18 @@ CASES = [
     ("survival-tiling", cli_args(selection="survival", library_design="tiling"),
      lambda: make_tiling_screen(n_guides=40, n_reps=3, seed=7, as_survival=True),
      dict(control_condition="D0", allele_df_key="allele_counts", condition_column="condition", time_column="time")),
+    # the commands of the reference's tests/test_run.py on its own screens
+    ("real-sorting-variant", cli_args(), lambda: golden_screen("real_var_mini_mixture"),
+     dict(condition_column="condition", control_can_be_selected=True)),
+    ("real-sorting-uniform-edit", cli_args(uniform_edit=True), lambda: golden_screen("real_var_mini_normal"),
+     dict(condition_column="condition", control_can_be_selected=True, use_bcmatch=True)),
+    ("real-sorting-tiling", cli_args(library_design="tiling"), lambda: golden_screen("tiling_real_mini"),
+     dict(condition_column="condition", control_can_be_selected=True, allele_df_key="allele_counts", control_guide_tag=None)),
+    ("real-survival-variant", cli_args(selection="survival"), lambda: golden_screen("survival_real_var_mixture"),
+     dict(condition_column="condition", time_column="time", control_condition="D7", control_can_be_selected=True)),
+    ("real-survival-tiling", cli_args(selection="survival", library_design="tiling"), lambda: golden_screen("survival_tiling_real_mini"),
+     dict(condition_column="condition", time_column="time", control_condition="D0", control_can_be_selected=True,
+          allele_df_key="allele_counts", control_guide_tag=None)),
 ]
 
 
@@ -52,7 +74,8 @@ def test_bean_run_flow(cuda_device, tmp_path, name, args, make_screen, data_kw):
     params, hist = run_inference(model, guide, ndata, num_steps=steps, device=cuda_device)
     loss = np.asarray(hist["loss"])
     assert loss.shape == (steps,) and np.isfinite(loss).all()
-    assert loss[-10:].mean() < loss[:10].mean()
+    if not name.startswith("real-"):  # (10-sample screens: 60 steps of a one-particle ELBO are too noisy to order)
+        assert loss[-10:].mean() < loss[:10].mean()
     tiling = args.library_design == "tiling"
     n_elem = ndata.n_edits if tiling else ndata.n_targets
     shape = (n_elem,) if tiling else (n_elem, 1)
@@ -79,7 +102,8 @@ def test_bean_run_flow(cuda_device, tmp_path, name, args, make_screen, data_kw):
                                adjust_confidence_negatives=np.arange(min(12, n_elem)), sd_is_fitted=args.selection == "sorting",
                                guide_acc=(ndata.guide_accessibility.cpu().numpy() if getattr(ndata, "guide_accessibility", None) is not None else None),
                                return_result=True, is_survival_screen=args.selection == "survival")
-    assert len(table) == n_elem and {"mu", "mu_sd", "mu_z", "mu_z_adj", "CI[0.025", "0.975]"} <= set(table.columns)
-    assert np.isfinite(table["mu_z_adj"]).all()
-    assert (np.diff(table["mu_z_adj"].abs().to_numpy()) <= 1e-12).all()  # sorted by |z|, strongest first
+    z = "mu_z_adj" if n_elem >= 10 else "mu_z"  # fewer than 10 negatives: no confidence adjustment (readwrite.py:141-150)
+    assert len(table) == n_elem and {"mu", "mu_sd", "mu_z", z, "CI[0.025", "0.975]"} <= set(table.columns)
+    assert np.isfinite(table[z]).all()
+    assert (np.diff(table[z].abs().to_numpy()) <= 1e-12).all()  # sorted by |z|, strongest first
     assert (tmp_path / f"bean_sgRNA_result.{label}.csv").exists()

@@ -102,6 +102,37 @@ def test_many_alleles_with_mask(cuda_device, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("A,n_variants", [(8, 25), (45, 17), (231, 6)])
+def test_warp_per_guide_kernel_many_alleles(cuda_device, dtype, A, n_variants):
+    """A >= 8: a warp owns a guide (raw tiling allele tables: the reference's tiling_mini_screen has up to 231
+    alleles per guide).  Ragged existence masks, A not a multiple of 32, G not a multiple of the 4 guides per CTA."""
+    data = H.make_small_mixture_data(n_variants=n_variants, n_reps=3, seed=A)
+    g = torch.Generator().manual_seed(A)
+    n_exist = torch.randint(1, A + 1, (data.n_guides,), generator=g)
+    amask = torch.arange(A)[None, :] < n_exist[:, None]
+    print(run_case(data, cuda_device, dtype, A=A, allele_mask=amask, seed=7))
+
+
+def test_thread_and_warp_per_guide_kernels_agree(cuda_device):
+    """The same guides scored with 6 alleles (thread per guide) and padded to 9 with non-existent alleles of zero
+    weight (warp per guide): identical log-likelihood rows and gradients up to summation order."""
+    data = H.make_small_mixture_data(n_variants=30, n_reps=4, seed=2)
+    G = data.n_guides
+    amask = torch.ones((G, 6), dtype=torch.bool)
+    mu, sd, pi = random_inputs(data, 6, seed=9, allele_mask=amask)
+    scr = DeviceScreen(data, cuda_device, dtype=torch.float64)
+    narrow = launch_ll(scr, mu.to(cuda_device), sd.to(cuda_device), pi_to_guide_major(pi).to(cuda_device), amask.to(cuda_device), want_rows=True)
+    pad = lambda t, v: torch.cat([t, torch.full(t.shape[:-1] + (3,), v, dtype=t.dtype)], dim=-1)
+    wide = launch_ll(scr, pad(mu, 0.3).to(cuda_device), pad(sd, 1.1).to(cuda_device), pi_to_guide_major(pad(pi, 0.0)).to(cuda_device),
+                     pad(amask, False).to(cuda_device), want_rows=True)
+    assert torch.allclose(wide["ll_row"], narrow["ll_row"], rtol=1e-13, atol=1e-10)
+    assert torch.allclose(wide["d_mu"][:, :6], narrow["d_mu"], rtol=1e-11, atol=1e-10)
+    assert torch.allclose(wide["d_sd"][:, :6], narrow["d_sd"], rtol=1e-11, atol=1e-10)
+    assert torch.allclose(wide["d_pi"][:, :, :6], narrow["d_pi"], rtol=1e-11, atol=1e-10)
+    assert (wide["d_mu"][:, 6:] == 0).all() and (wide["d_pi"][:, :, 6:] == 0).all()  # non-existent alleles: P := 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_edge_cases_masks_zero_rows_tiny_counts(cuda_device, dtype):
     data = H.make_small_mixture_data(n_variants=20, n_reps=3)
     data.sample_mask = data.sample_mask.clone().bool()

@@ -30,4 +30,5 @@ def test_argument_validation_without_gpu():
     lib = _lib.lib()
     assert lib.bean_ll_f32(None, None, None) == -1
     assert b"screen is NULL" in lib.bean_last_error()
-    assert lib.bean_ll_num_partials(129) == 2
+    assert lib.bean_ll_num_partials(129, 2) == 2      # thread per guide, 128 guides per CTA
+    assert lib.bean_ll_num_partials(129, 231) == 33   # tiling: warp per guide, 4 guides per CTA
