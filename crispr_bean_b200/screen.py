@@ -13,6 +13,15 @@ import numpy as np
 import pandas as pd
 
 
+def _take_columns(a: np.ndarray, cols: np.ndarray) -> np.ndarray:
+    """a[:, cols]; large numeric matrices go through torch's multi-threaded index_select."""
+    if a.size < (1 << 20) or a.dtype.kind not in "fiu" or not a.flags.c_contiguous or not a.flags.writeable:
+        return np.ascontiguousarray(a[:, cols])  # (row-major like an AnnData slice: float32 column means depend on it)
+    import torch
+
+    return torch.from_numpy(a).index_select(1, torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int64))).numpy()
+
+
 class MiniScreen:
     """guides x samples count matrix + per-guide / per-sample tables (+ named layers)."""
 
@@ -59,21 +68,26 @@ class MiniScreen:
 
     def __getitem__(self, key):
         gi, si = key if isinstance(key, tuple) else (key, slice(None))
-        gi = self._resolve(gi, self.guides.index)
+        all_guides = isinstance(gi, slice) and gi == slice(None)
+        all_samples = isinstance(si, slice) and si == slice(None)
         si = self._resolve(si, self.samples.index)
-        uns = dict(self.uns)
-        for k, v in self.uns.items():  # per-guide tables follow the guide subset (repguide_mask)
-            if isinstance(v, pd.DataFrame) and len(v) == len(self.guides) and v.index.equals(self.guides.index):
-                uns[k] = v.iloc[gi]
-        return MiniScreen(
-            self.X[np.ix_(gi, si)],
-            self.guides.iloc[gi].copy(),
-            self.samples.iloc[si].copy(),
-            {k: v[np.ix_(gi, si)] for k, v in self.layers.items()},
-            uns,
-        )
+        if all_guides:  # sample subsets / reorders of a whole library (1M guides): one column gather per matrix
+            if all_samples or np.array_equal(si, np.arange(len(self.samples))):
+                take = lambda a: a
+            else:
+                take = lambda a: _take_columns(a, si)
+            guides, uns = self.guides.copy(), dict(self.uns)
+        else:
+            gi = self._resolve(gi, self.guides.index)
+            take = lambda a: a[np.ix_(gi, si)]
+            guides, uns = self.guides.iloc[gi].copy(), dict(self.uns)
+            for k, v in self.uns.items():  # per-guide tables follow the guide subset (repguide_mask)
+                if isinstance(v, pd.DataFrame) and len(v) == len(self.guides) and v.index.equals(self.guides.index):
+                    uns[k] = v.iloc[gi]
+        return MiniScreen(take(self.X), guides, self.samples.iloc[si].copy(), {k: take(v) for k, v in self.layers.items()}, uns)
 
     def copy(self):
+        """Own tables, shared count matrices (they are never written in place)."""
         return self[:, :]
 
 
