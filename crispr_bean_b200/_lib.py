@@ -78,8 +78,30 @@ class BeanAlleleMap(C.Structure):
                 ("allele_ptr", C.c_void_p), ("allele_edit", C.c_void_p), ("edit_ptr", C.c_void_p), ("edit_slot", C.c_void_p)]
 
 
+ADAM_MAX_TENSORS = 16
+
+
+class BeanAdamTensor(C.Structure):
+    _fields_ = [("theta", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+
+
+class BeanAdamArgs(C.Structure):
+    _fields_ = [("n_tensors", C.c_int32), ("tensors", BeanAdamTensor * ADAM_MAX_TENSORS),
+                ("step_sizes", C.c_void_p), ("step", C.c_void_p), ("n_steps", C.c_int64),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("clip", C.c_double)]
+
+
+class BeanPiSitesArgs(C.Structure):
+    _fields_ = [("n_guides", C.c_int32), ("n_reps", C.c_int32), ("n_alleles", C.c_int32), ("n_controls", C.c_int32),
+                ("mask_guide_site", C.c_int32),
+                ("conc_guide", C.c_void_p), ("conc_model", C.c_void_p), ("pi", C.c_void_p), ("counts", C.c_void_p),
+                ("rep_guide_mask", C.c_void_p), ("growth", C.c_void_p), ("control_time", C.POINTER(C.c_double)),
+                ("prob_eps", C.c_double), ("partial", C.c_void_p),
+                ("d_conc_guide", C.c_void_p), ("d_conc_model", C.c_void_p), ("d_pi", C.c_void_p), ("d_growth", C.c_void_p)]
+
+
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 4  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 6  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -98,6 +120,10 @@ _PROTOTYPES = {
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
     "bean_svi_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSviConfig),
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_pi_sites_f32": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
+    "bean_pi_sites_f64": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
+    "bean_clipped_adam_f32": (C.c_int, [C.POINTER(BeanAdamArgs), C.c_void_p]),
+    "bean_clipped_adam_f64": (C.c_int, [C.POINTER(BeanAdamArgs), C.c_void_p]),
     "bean_row_ceiling_f32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

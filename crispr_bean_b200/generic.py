@@ -18,9 +18,11 @@ from typing import Dict, Optional
 import torch
 import torch.distributions as tdist
 
+from . import _lib
 from ._lib import BeanError
 from .device_pack import DeviceScreen
 from .ll_function import count_log_likelihood
+from .pi_sites import PiSiteData, pi_sites
 from .tiling import AlleleMap, allele_gather
 
 EPS = 1e-5
@@ -146,16 +148,30 @@ class AutogradSviEngine:
         return out, model_lp, guide_lp
 
     def _adam(self):
-        """pyro.optim.ClippedAdam on the unconstrained tensors, step size read from the device."""
-        with torch.no_grad():
-            step_size = self._step_sizes.index_select(0, self._t.clamp(max=self._step_sizes.numel() - 1)).reshape(())
+        """pyro.optim.ClippedAdam on the unconstrained tensors: one `bean_clipped_adam` launch for all
+        tensors of a dtype, step index and step size read from the device (capturable)."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._adam_keep = []  # gradient buffers stay referenced until the next step
+        for dtype, name in ((torch.float32, "bean_clipped_adam_f32"), (torch.float64, "bean_clipped_adam_f64")):
+            args, n = _lib.BeanAdamArgs(), 0
             for k, p in self.theta.items():
-                if p.grad is None:
+                if p.grad is None or p.dtype != dtype:
                     continue
-                g = p.grad.clamp(-10.0, 10.0)
-                self.m[k].mul_(0.9).add_(g, alpha=0.1)
-                self.v[k].mul_(0.999).addcmul_(g, g, value=0.001)
-                p.sub_((step_size * self.m[k] / (self.v[k].sqrt() + 1e-8)).to(p.dtype))
+                if n == _lib.ADAM_MAX_TENSORS:
+                    raise BeanError(f"more than {_lib.ADAM_MAX_TENSORS} parameter tensors")
+                g = p.grad.contiguous()
+                if not (p.is_contiguous() and p.is_cuda and g.dtype == dtype and self.m[k].dtype == dtype and self.v[k].dtype == dtype):
+                    raise BeanError(f"parameter {k}: the optimiser kernel needs contiguous CUDA tensors of one dtype")
+                self._adam_keep.append(g)
+                t = args.tensors[n]
+                t.theta, t.grad, t.m, t.v, t.n = p.data_ptr(), g.data_ptr(), self.m[k].data_ptr(), self.v[k].data_ptr(), p.numel()
+                n += 1
+            if n == 0:
+                continue
+            args.n_tensors = n
+            args.step_sizes, args.step, args.n_steps = self._step_sizes.data_ptr(), self._t.data_ptr(), self._step_sizes.numel()
+            args.beta1, args.beta2, args.eps, args.clip = 0.9, 0.999, 1e-8, 10.0
+            _lib.check(getattr(_lib.lib(), name)(args, stream), name)
 
     def _step_once(self, noise):
         """One SVI step, entirely on the device (capturable)."""
@@ -266,6 +282,7 @@ class TilingSviEngine(AutogradSviEngine):
         self.pi_a0 = torch.as_tensor(data.pi_a0).to(self.device)
         self.allele_counts_control = data.allele_counts_control.to(**kw)  # (R, C, G, A)
         self.rg_mask = data.repguide_mask.to(self.device).unsqueeze(1)  # (R, 1, G)
+        self.pi_data = PiSiteData(self.allele_counts_control, self.rg_mask, None, mask_guide_site=True)
         self.epsilon, self.sd_scale, self.prior_params = epsilon, sd_scale, prior_params
         a0 = torch.full((self.G, self.A), float(alpha_prior), **kw)
         a0[~self.allele_mask] = epsilon
@@ -302,15 +319,13 @@ class TilingSviEngine(AutogradSviEngine):
         mu_a, sd_a = allele_gather(mu_e, sd_e, self.amap)
 
         # editing-rate sites (model.py:632-670 model, :938-950 guide: masked, not clamped)
-        conc_g = (alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+        conc_g = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]  # (G, A)
         conc_m = (alpha_pi + eps / A) / (alpha_pi.sum(-1, keepdim=True) + eps) * self.pi_a0[:, None]
-        conc_m = torch.where(conc_m < eps, torch.full_like(conc_m, eps), conc_m).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+        conc_m = torch.where(conc_m < eps, torch.full_like(conc_m, eps), conc_m)
         injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None  # cast to the concentration's dtype
-        pi = _DirichletRsample.apply(conc_g, injected, self.gen)
-        guide_lp = guide_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi))
-        model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
-        lp_mult = _multinomial_log_prob(pi, self.allele_counts_control)
-        model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
+        pi = _DirichletRsample.apply(conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1), injected, self.gen)
+        # model `pi` Dirichlet + reporter Multinomial - guide `pi` Dirichlet, all under repguide_mask: one kernel
+        model_lp = model_lp + pi_sites(conc_g, conc_m, pi, self.pi_data)
 
         if self.acc:
             pi, m_lp, g_lp = self._acc_apply(pi, noise)

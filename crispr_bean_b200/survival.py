@@ -26,6 +26,7 @@ from .collective import ShardedDirichletRsample, global_sum, sharded_dirichlet_l
 from .device_pack import DeviceScreen
 from .generic import EPS, AutogradSviEngine, _DirichletRsample, _masked_sum, _multinomial_log_prob
 from .ll_function import count_log_likelihood
+from .pi_sites import PiSiteData, pi_sites
 from .tiling import AlleleMap, allele_gather
 
 
@@ -95,6 +96,10 @@ class SurvivalSviEngine(AutogradSviEngine):
             # evaluated in double as in the reference, whose probability clamp [eps, 1 - eps] follows that dtype
             self.control_timepoint = data.control_timepoint.to(self.device, torch.promote_types(data.control_timepoint.dtype, self.dtype))
             self.rg_mask = data.repguide_mask.to(self.device).unsqueeze(1)  # (R, 1, G)
+            # MixtureNormalGuide scores its `pi` draws unmasked (survival_model.py:699-712), the tiling guide under repguide_mask
+            self.pi_data = PiSiteData(self.allele_counts_control, self.rg_mask, self.control_timepoint,
+                                      mask_guide_site=(model == "MultiMixtureNormal"))
+            self.pi_dtype = torch.promote_types(torch.promote_types(self.pi_a0.dtype, self.dtype), self.control_timepoint.dtype)
             x0 = data.X[:, 0, :].to(**kw) + 1  # survival_model.py:306-311: observed initial abundance
             self.obs_abundance = x0 / global_sum(x0.sum(-1, keepdim=True), group)
             self.mu_negctrl = (float(mu_negctrl[0]), float(mu_negctrl[1]))
@@ -152,18 +157,11 @@ class SurvivalSviEngine(AutogradSviEngine):
         mu = torch.cat([u.unsqueeze(-1), mu_g + u.unsqueeze(-1)], dim=-1)  # (G, 2)
         model_lp = model_lp + sharded_dirichlet_log_prob(conc_q, self.obs_abundance.expand_as(conc_q), self.group)
         pi_a_scaled = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]
-        conc_g = pi_a_scaled.clamp(min=1e-5).unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
-        conc_m = pi_a_scaled.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
+        conc_g, conc_m = pi_a_scaled.clamp(min=1e-5), pi_a_scaled  # (G, 2)
         injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None
-        pi = _DirichletRsample.apply(conc_g, injected, self.gen)
-        guide_lp = guide_lp + tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi).sum()
-        model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
-        tc = self.control_timepoint
-        C = tc.shape[0]
-        expanded = pi.expand(-1, C, -1, -1) * torch.exp(mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1)
-                                                        * tc.reshape(1, C, 1, 1).expand(R, -1, G, 2))
-        lp_mult = _multinomial_log_prob(expanded, self.allele_counts_control)
-        model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
+        pi = _DirichletRsample.apply(conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1), injected, self.gen)
+        # model `pi` + Multinomial(control counts; pi exp(mu t_c)) under repguide_mask, minus the guide's `pi` density
+        model_lp = model_lp + pi_sites(conc_g, conc_m, pi, self.pi_data, growth=mu, work_dtype=self.pi_dtype)
         if self.acc:  # survival_model.py:347-351
             pi, m_lp, g_lp = self._acc_apply(pi, noise)
             model_lp, guide_lp = model_lp + m_lp, guide_lp + g_lp
@@ -185,17 +183,9 @@ class SurvivalSviEngine(AutogradSviEngine):
         conc_g = (alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]).clamp(min=1e-5)
         conc_m = (alpha_pi + eps / A) / (alpha_pi.sum(-1, keepdim=True) + eps) * self.pi_a0[:, None]
         conc_m = torch.where(conc_m < eps, torch.full_like(conc_m, eps), conc_m)
-        conc_g = conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
-        conc_m = conc_m.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1)
         injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None
-        pi = _DirichletRsample.apply(conc_g, injected, self.gen)
-        guide_lp = guide_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_g, validate_args=False).log_prob(pi))
-        model_lp = model_lp + _masked_sum(self.rg_mask, tdist.Dirichlet(conc_m, validate_args=False).log_prob(pi))
-        tc = self.control_timepoint
-        C = tc.shape[0]
-        expanded = pi * torch.exp(mu.unsqueeze(0).unsqueeze(0).expand(R, C, -1, -1) * tc.reshape(1, C, 1, 1).expand(R, -1, G, A))
-        lp_mult = _multinomial_log_prob(expanded, self.allele_counts_control)
-        model_lp = model_lp + _masked_sum(self.rg_mask.expand(lp_mult.shape), lp_mult)
+        pi = _DirichletRsample.apply(conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1), injected, self.gen)
+        model_lp = model_lp + pi_sites(conc_g, conc_m, pi, self.pi_data, growth=mu, work_dtype=self.pi_dtype)
         if self.acc:
             pi, m_lp, g_lp = self._acc_apply(pi, noise)
             model_lp, guide_lp = model_lp + m_lp, guide_lp + g_lp

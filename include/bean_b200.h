@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 4
+#define BEAN_ABI_VERSION 6
 
 enum {
   BEAN_OK = 0,
@@ -237,6 +237,71 @@ int bean_svi_run_f32(const BeanScreen* screen, const BeanSviState* state, const 
                      const BeanSviNoise* noise, int32_t first_step, int32_t n_steps, void* stream);
 int bean_svi_run_f64(const BeanScreen* screen, const BeanSviState* state, const BeanSviConfig* cfg,
                      const BeanSviNoise* noise, int32_t first_step, int32_t n_steps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Editing-rate sites of the MultiMixtureNormal (tiling) and survival MixtureNormal programs: forward value and local
+ * gradients in one launch.  Replaces the op chains
+ *   pyro.sample("pi", Dirichlet(pi_a_scaled))            model.py:652-661, survival_model.py:313-322 / :515-524
+ *   pyro.sample("control_allele_count", Multinomial(probs=pi * exp(mu t_c)), obs=allele_counts_control)
+ *                                                         model.py:662-670, survival_model.py:323-346 / :525-548
+ *   guide: pyro.sample("pi", Dirichlet(...))              model.py:938-950, survival_model.py:699-712 / :822-833
+ * and their autograd backward (torch.distributions.Dirichlet / Multinomial.log_prob).
+ *   V = sum m[r,g] log Dir(pi[r,g,:]; conc_model[g,:]) + sum m[r,g] [sum_a x[r,c,g,a] log clamp(q_a / sum q, eps, 1 - eps)]
+ *       - sum m'[r,g] log Dir(pi[r,g,:]; conc_guide[g,:]),   q_a = pi[r,g,a] exp(growth[g,a] control_time[c])
+ *   m = rep_guide_mask; m' = m if mask_guide_site else 1.  The data-only Multinomial constant is left to the caller.
+ * in : conc_guide, conc_model real [G][A]; pi real [R][G][A]; counts real [R][C][G][A]; rep_guide_mask u8 [R][G];
+ *      growth real [G][A] or NULL (q = pi); control_time HOST double [C] (needed with growth)
+ * out: partial double [G] (V = sum of it); d_conc_guide, d_conc_model real [G][A]; d_pi real [R][G][A];
+ *      d_growth real [G][A] (NULL iff growth is NULL) -- all d(V)/d(input)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BeanPiSitesArgs {
+  int32_t n_guides, n_reps, n_alleles, n_controls;
+  int32_t mask_guide_site;
+  const void* conc_guide;
+  const void* conc_model;
+  const void* pi;
+  const void* counts;
+  const uint8_t* rep_guide_mask;
+  const void* growth;
+  const double* control_time;
+  double prob_eps;             /* eps of the dtype the reference evaluates the Multinomial probabilities in */
+  double* partial;
+  void* d_conc_guide;
+  void* d_conc_model;
+  void* d_pi;
+  void* d_growth;
+} BeanPiSitesArgs;
+int bean_pi_sites_f32(const BeanPiSitesArgs* args, void* stream);
+int bean_pi_sites_f64(const BeanPiSitesArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * pyro.optim.ClippedAdam on every parameter tensor of a model in one launch.
+ * Replaces the optimiser half of `svi.step` (bean/model/run.py:368-380: ClippedAdam({"lr", "lrd", "clip_norm": 10}))
+ * for the models whose ELBO is assembled by torch autograd around `bean_ll_*` (tiling, survival, covariates).
+ * Per element of the unconstrained tensors:
+ *   g = clamp(grad, -clip, clip); m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
+ *   theta -= step_sizes[min(*step, n_steps - 1)] * m / (sqrt(v) + eps)
+ * with step_sizes[t] = lr lrd^(t+1) sqrt(1 - b2^(t+1)) / (1 - b1^(t+1)) precomputed by the caller.  `step_sizes` and
+ * `step` are DEVICE pointers: nothing about the launch depends on the host, so it can be captured in a CUDA graph.
+ * ---------------------------------------------------------------------------------------------- */
+#define BEAN_ADAM_MAX_TENSORS 16
+typedef struct BeanAdamTensor {
+  void* theta;        /* real [n] unconstrained parameter, updated in place */
+  const void* grad;   /* real [n] d(-ELBO)/d theta                          */
+  void* m;            /* real [n] first-moment state                        */
+  void* v;            /* real [n] second-moment state                       */
+  int64_t n;
+} BeanAdamTensor;
+typedef struct BeanAdamArgs {
+  int32_t n_tensors;
+  BeanAdamTensor tensors[BEAN_ADAM_MAX_TENSORS];
+  const double* step_sizes;  /* device f64 [n_steps] */
+  const int64_t* step;       /* device i64 [1]: 0-based index of this step */
+  int64_t n_steps;
+  double beta1, beta2, eps, clip;
+} BeanAdamArgs;
+int bean_clipped_adam_f32(const BeanAdamArgs* args, void* stream);
+int bean_clipped_adam_f64(const BeanAdamArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Measurement aid (no reference counterpart): register-only evaluation of the Dirichlet-Multinomial row
