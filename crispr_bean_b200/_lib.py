@@ -100,8 +100,24 @@ class BeanPiSitesArgs(C.Structure):
                 ("d_conc_guide", C.c_void_p), ("d_conc_model", C.c_void_p), ("d_pi", C.c_void_p), ("d_growth", C.c_void_p)]
 
 
+class BeanLatentSitesArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("has_sd", C.c_int32), ("mu_prior_normal", C.c_int32),
+                ("mu_loc", C.c_void_p), ("mu_log_scale", C.c_void_p), ("sd_loc", C.c_void_p), ("sd_log_scale", C.c_void_p),
+                ("eps_mu", C.c_void_p), ("eps_sd", C.c_void_p),
+                ("mu_prior_loc", C.c_double), ("mu_prior_scale", C.c_double), ("sd_prior_loc", C.c_double), ("sd_prior_scale", C.c_double),
+                ("mu_prior_loc_v", C.c_void_p), ("mu_prior_scale_v", C.c_void_p), ("sd_prior_loc_v", C.c_void_p), ("sd_prior_scale_v", C.c_void_p),
+                ("mu", C.c_void_p), ("sd", C.c_void_p), ("partial", C.c_void_p), ("dv", C.c_void_p)]
+
+
+class BeanLatentSitesGradArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("has_sd", C.c_int32),
+                ("mu_log_scale", C.c_void_p), ("sd_log_scale", C.c_void_p), ("eps_mu", C.c_void_p), ("eps_sd", C.c_void_p),
+                ("sd", C.c_void_p), ("dv", C.c_void_p), ("g_mu", C.c_void_p), ("g_sd", C.c_void_p), ("g_v", C.c_void_p),
+                ("grad", C.c_void_p)]
+
+
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 6  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 7  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -122,6 +138,11 @@ _PROTOTYPES = {
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
     "bean_pi_sites_f32": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
     "bean_pi_sites_f64": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
+    "bean_latent_sites_num_partials": (C.c_int, [C.c_int64]),
+    "bean_latent_sites_f32": (C.c_int, [C.POINTER(BeanLatentSitesArgs), C.c_void_p]),
+    "bean_latent_sites_f64": (C.c_int, [C.POINTER(BeanLatentSitesArgs), C.c_void_p]),
+    "bean_latent_sites_grad_f32": (C.c_int, [C.POINTER(BeanLatentSitesGradArgs), C.c_void_p]),
+    "bean_latent_sites_grad_f64": (C.c_int, [C.POINTER(BeanLatentSitesGradArgs), C.c_void_p]),
     "bean_clipped_adam_f32": (C.c_int, [C.POINTER(BeanAdamArgs), C.c_void_p]),
     "bean_clipped_adam_f64": (C.c_int, [C.POINTER(BeanAdamArgs), C.c_void_p]),
     "bean_row_ceiling_f32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -22,6 +22,7 @@ from . import _lib
 from ._lib import BeanError
 from .device_pack import DeviceScreen
 from .ll_function import count_log_likelihood
+from .latent_sites import LatentPrior, latent_sites
 from .pi_sites import PiSiteData, pi_sites
 from .tiling import AlleleMap, allele_gather
 
@@ -293,6 +294,7 @@ class TilingSviEngine(AutogradSviEngine):
         self.acc = bool(scale_by_accessibility)
         if self.acc:
             self._acc_init(data, theta, positive, fit_noise)
+        self.latent_prior = LatentPrior(self.E, prior_params, sd_scale, self.device, dtype)
         self._init_optim(theta, positive, num_steps, initial_lr, gamma, seed)
 
     # ---------------------------------------------------------------------------------------------
@@ -302,18 +304,12 @@ class TilingSviEngine(AutogradSviEngine):
         E, G, A, R = self.E, self.G, self.A, self.R
         eps = self.epsilon
         P = self.theta
-        mu_loc, sd_loc = P["mu_loc"], P["sd_loc"]
-        mu_scale, sd_scale_q, alpha_pi = P["mu_scale"].exp(), P["sd_scale"].exp(), P["alpha_pi"].exp()
+        alpha_pi = P["alpha_pi"].exp()
         alpha_pi = torch.where(self.allele_mask, alpha_pi, torch.full_like(alpha_pi, eps))  # model.py:645 / :937
-
-        mu_e = mu_loc + mu_scale * self._draw(noise, "eps_mu", (E,))
-        sd_e = torch.exp(sd_loc + sd_scale_q * self._draw(noise, "eps_sd", (E,)))
-        guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_e).sum() + tdist.LogNormal(sd_loc, sd_scale_q).log_prob(sd_e).sum()
-        pp = self.prior_params or {}
-        mu_prior = (tdist.Normal(self._prior_t(pp.get("mu_loc", 0.0)), self._prior_t(pp.get("mu_scale", 1.0)))
-                    if ("mu_loc" in pp or "mu_scale" in pp) else tdist.Laplace(self._c(0.0), self._c(1.0)))
-        sd_prior = tdist.LogNormal(self._prior_t(pp.get("sd_loc", 0.0)), self._prior_t(pp.get("sd_scale", self.sd_scale)))
-        model_lp = mu_prior.log_prob(mu_e).sum() + sd_prior.log_prob(sd_e).sum()
+        # `mu_alleles` / `sd_alleles` per edit: draws, Laplace | Normal and LogNormal priors, guide densities (one kernel)
+        mu_e, sd_e, model_lp = latent_sites(P["mu_loc"], P["mu_scale"], self._draw(noise, "eps_mu", (E,)), self.latent_prior,
+                                            P["sd_loc"], P["sd_scale"], self._draw(noise, "eps_sd", (E,)))
+        guide_lp = self._c(0.0)
 
         # allele <- edit contraction (CUDA CSR gather / CSC scatter), WT column (0, 1)
         mu_a, sd_a = allele_gather(mu_e, sd_e, self.amap)

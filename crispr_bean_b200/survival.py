@@ -25,6 +25,7 @@ from ._lib import BeanError
 from .collective import ShardedDirichletRsample, global_sum, sharded_dirichlet_log_prob
 from .device_pack import DeviceScreen
 from .generic import EPS, AutogradSviEngine, _DirichletRsample, _masked_sum, _multinomial_log_prob
+from .latent_sites import LatentPrior, latent_sites
 from .ll_function import count_log_likelihood
 from .pi_sites import PiSiteData, pi_sites
 from .tiling import AlleleMap, allele_gather
@@ -105,6 +106,8 @@ class SurvivalSviEngine(AutogradSviEngine):
             self.mu_negctrl = (float(mu_negctrl[0]), float(mu_negctrl[1]))
         if self.acc:
             self._acc_init(data, theta, positive, fit_noise)
+        prior = {"mu_loc": 0.0, "mu_scale": 1.0} if model == "ControlNormal" else prior_params
+        self.latent_prior = LatentPrior(theta["mu_loc"].numel(), prior, 1.0, self.device, dtype)
         self._init_optim(theta, positive, num_steps, initial_lr, gamma, seed)
 
     # ---------------------------------------------------------------------------------------------
@@ -120,19 +123,17 @@ class SurvivalSviEngine(AutogradSviEngine):
         kw = dict(device=self.device, dtype=self.dtype)
         G, R, T = self.G, self.R, self.T
         P = self.theta
-        mu_loc, mu_scale = P["mu_loc"], P["mu_scale"].exp()
         shape = () if self.model == "ControlNormal" else ((T,) if self.model == "MultiMixtureNormal" else (T, 1))
-        mu_t = mu_loc + mu_scale * self._draw(noise, "eps_mu", shape)
-        guide_lp = tdist.Normal(mu_loc, mu_scale).log_prob(mu_t).sum()
+        # `mu_targets` site: draw, prior (Laplace | Normal; ControlNormal: Normal(0, 1)) and guide density in one kernel
+        mu_t, model_lp = latent_sites(P["mu_loc"], P["mu_scale"], self._draw(noise, "eps_mu", shape), self.latent_prior)
+        guide_lp = self._c(0.0)
         injected_q = noise["q0"].to(**kw) if (noise is not None and "q0" in noise) else None
 
         if self.model == "ControlNormal":
-            model_lp = tdist.Normal(self._c(0.0), self._c(1.0)).log_prob(mu_t).sum()
             mu_a = mu_t.reshape(1, 1).expand(G, 1)
             ll = count_log_likelihood(self.screen, mu_a, torch.ones_like(mu_a), None, None)
             return -(model_lp + ll - guide_lp)
 
-        model_lp = self._mu_prior().log_prob(mu_t).sum()
         if self.model == "MultiMixtureNormal":
             return self._elbo_tiling(mu_t, model_lp, guide_lp, noise)
         mu_g = torch.repeat_interleave(mu_t, self.target_lengths, dim=0, output_size=self.G)  # (G, 1); output_size: no host sync

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 6
+#define BEAN_ABI_VERSION 7
 
 enum {
   BEAN_OK = 0,
@@ -273,6 +273,59 @@ typedef struct BeanPiSitesArgs {
 } BeanPiSitesArgs;
 int bean_pi_sites_f32(const BeanPiSitesArgs* args, void* stream);
 int bean_pi_sites_f64(const BeanPiSitesArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-variant / per-edit latent sites `mu_targets` (and `sd_targets`) of the programs that run on torch autograd around
+ * bean_ll_*: reparameterised draws, prior and guide log-densities, closed-form gradients.
+ * Replaces  guide: pyro.sample("mu_targets", Normal(mu_loc, mu_scale)), pyro.sample("sd_targets", LogNormal(sd_loc, sd_scale))
+ *                  (model.py:893-921, survival_model.py:640-652 / :770-789)
+ *           model: pyro.sample("mu_targets", Laplace(0, 1) | Normal(prior)), pyro.sample("sd_targets", LogNormal(prior))
+ *                  (model.py:579-610, survival_model.py:37-56 / :246-274 / :440-468)
+ * and their autograd backward.  Forward: mu = mu_loc + exp(mu_log_scale) eps_mu, sd = exp(sd_loc + exp(sd_log_scale) eps_sd),
+ *   V = sum_i [log p(mu_i) - log q(mu_i)] + [log p(sd_i) - log q(sd_i)]  (what the sites add to the ELBO),
+ *   dv[4][n] = dV/d(mu_loc, mu_log_scale, sd_loc, sd_log_scale) including the path through the draws.
+ * Backward (bean_latent_sites_grad_*): grad[4][n] = d L/d(the four parameters) from the upstream d L/d(mu, sd, V).
+ * Prior hyper-parameters: scalar, or per element where the *_v pointer is non-NULL (`bean build-prior` tensors).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BeanLatentSitesArgs {
+  int64_t n;
+  int32_t has_sd;              /* 0: survival programs (no sd_targets site) */
+  int32_t mu_prior_normal;     /* 0: Laplace(0, 1); 1: Normal(mu_prior_loc, mu_prior_scale) */
+  const void* mu_loc;          /* real [n] */
+  const void* mu_log_scale;    /* real [n] */
+  const void* sd_loc;          /* real [n] or NULL */
+  const void* sd_log_scale;    /* real [n] or NULL */
+  const void* eps_mu;          /* real [n] standard-normal noise */
+  const void* eps_sd;          /* real [n] or NULL */
+  double mu_prior_loc, mu_prior_scale, sd_prior_loc, sd_prior_scale;
+  const void* mu_prior_loc_v;  /* real [n] or NULL */
+  const void* mu_prior_scale_v;
+  const void* sd_prior_loc_v;
+  const void* sd_prior_scale_v;
+  void* mu;                    /* out real [n] */
+  void* sd;                    /* out real [n] or NULL */
+  double* partial;             /* out f64 [bean_latent_sites_num_partials(n)], V = sum */
+  void* dv;                    /* out real [4][n] (rows 2, 3 untouched without sd) */
+} BeanLatentSitesArgs;
+typedef struct BeanLatentSitesGradArgs {
+  int64_t n;
+  int32_t has_sd;
+  const void* mu_log_scale;
+  const void* sd_log_scale;
+  const void* eps_mu;
+  const void* eps_sd;
+  const void* sd;              /* the forward's sd draws */
+  const void* dv;              /* the forward's dv */
+  const void* g_mu;            /* real [n] upstream d L/d mu, or NULL (= 0) */
+  const void* g_sd;            /* real [n] upstream d L/d sd, or NULL */
+  const void* g_v;             /* real [1] DEVICE scalar d L/d V, or NULL */
+  void* grad;                  /* out real [4][n] */
+} BeanLatentSitesGradArgs;
+int bean_latent_sites_num_partials(int64_t n);
+int bean_latent_sites_f32(const BeanLatentSitesArgs* args, void* stream);
+int bean_latent_sites_f64(const BeanLatentSitesArgs* args, void* stream);
+int bean_latent_sites_grad_f32(const BeanLatentSitesGradArgs* args, void* stream);
+int bean_latent_sites_grad_f64(const BeanLatentSitesGradArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * pyro.optim.ClippedAdam on every parameter tensor of a model in one launch.
