@@ -16,6 +16,7 @@ mode); the Dirichlet-over-guides abundance sites, the editing-rate sites, priors
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional
 
 import torch
@@ -151,12 +152,15 @@ class SurvivalSviEngine(AutogradSviEngine):
         alpha_pi = P["alpha_pi"].exp()
         conc_q = P["q0"].exp().unsqueeze(0).expand(R, -1)
         ia = ShardedDirichletRsample.apply(conc_q, injected_q, self.gen, self.group)  # guide-only draw (App. B8)
-        guide_lp = guide_lp + sharded_dirichlet_log_prob(conc_q, ia, self.group)
+        # model: Dirichlet(conc_q).log_prob(observed abundance); guide: Dirichlet(conc_q).log_prob(ia).  Same concentration on
+        # both sides, so the normalisers lgamma(sum c) - sum lgamma(c) (and their digamma gradients, and the all-reduce of
+        # sum c when guides are sharded) cancel in model - guide: only sum (c - 1) (log obs - log ia) remains.
+        model_lp = model_lp + (torch.xlogy(conc_q - 1.0, self.obs_abundance.expand_as(conc_q)) - torch.xlogy(conc_q - 1.0, ia)).sum()
         m0, s0 = self.mu_negctrl
-        u = m0 + s0 * self._draw(noise, "eps_negctrl", (G,))  # model-only latent: fresh prior noise every step
-        model_lp = model_lp + tdist.Normal(self._c(m0), self._c(s0)).log_prob(u).sum()
+        e_u = self._draw(noise, "eps_negctrl", (G,))
+        u = m0 + s0 * e_u  # model-only latent: fresh prior noise every step; its Normal(m0, s0) density has no parameters
+        model_lp = model_lp - 0.5 * e_u.square().sum() - G * (math.log(s0) + 0.5 * math.log(2 * math.pi))
         mu = torch.cat([u.unsqueeze(-1), mu_g + u.unsqueeze(-1)], dim=-1)  # (G, 2)
-        model_lp = model_lp + sharded_dirichlet_log_prob(conc_q, self.obs_abundance.expand_as(conc_q), self.group)
         pi_a_scaled = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]
         conc_g, conc_m = pi_a_scaled.clamp(min=1e-5), pi_a_scaled  # (G, 2)
         injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None
@@ -177,8 +181,9 @@ class SurvivalSviEngine(AutogradSviEngine):
         alpha_pi = self.theta["alpha_pi"].exp()
         alpha_pi = torch.where(self.allele_mask, alpha_pi, torch.full_like(alpha_pi, eps))  # in-place overwrite in the reference
         m0, s0 = self.mu_negctrl
-        u = m0 + s0 * self._draw(noise, "eps_negctrl", (G,))
-        model_lp = model_lp + tdist.Normal(self._c(m0), self._c(s0)).log_prob(u).sum()
+        e_u = self._draw(noise, "eps_negctrl", (G,))
+        u = m0 + s0 * e_u
+        model_lp = model_lp - 0.5 * e_u.square().sum() - G * (math.log(s0) + 0.5 * math.log(2 * math.pi))
         mu_targets, _ = allele_gather(mu_e, torch.ones_like(mu_e), self.amap)  # (G, A): column 0 = 0, column j = sum of edit rates
         mu = u.unsqueeze(-1) + mu_targets
         conc_g = (alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]).clamp(min=1e-5)
