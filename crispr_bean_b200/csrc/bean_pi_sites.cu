@@ -10,7 +10,7 @@
 // In the torch-op version these sites and their autograd backward were ~150 of the ~290 kernel launches of a step.
 // The data-only part of the Multinomial (lgamma(N + 1) - sum lgamma(x + 1)) is a constant the caller adds once.
 //
-// One warp owns one guide; lanes stride over the alleles (coalesced pi / counts / gradient rows).  Three sweeps over the
+// One warp (tiling) or one thread (A < 8) owns one guide; a warp's lanes stride over the alleles (coalesced rows).  Three sweeps over the
 // alleles: (1) concentration sums and the Multinomial normalisers S[r,c]; (2) the Multinomial value and
 // hbar[r,c] = sum_a h_a n_a; (3) the Dirichlet values and every gradient.
 #include "bean_common.cuh"
@@ -19,6 +19,7 @@
 namespace bean {
 
 constexpr int PI_WARPS = 4;
+constexpr int PI_WIDE_MIN_ALLELES = 8;  // from this many alleles per guide on, a warp owns a guide
 
 template <typename real>
 struct PiSitesParams {
@@ -38,25 +39,28 @@ struct PiSitesParams {
   real* d_growth;
 };
 
-template <typename real>
+template <int LPG, typename real>
 __device__ __forceinline__ real warp_all_sum(real v) {
+  if (LPG == 1) return v;
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
 }
 
-template <typename real>
+// LPG lanes per guide: 32 (tiling: tens to hundreds of alleles) or 1 (variant designs, A = 2: a warp per guide left 30 of
+// 32 lanes idle -- 5.2 ms of a 7.5 ms survival step at 1M guides)
+template <typename real, int LPG>
 __global__ void __launch_bounds__(PI_WARPS * 32) pi_sites_kernel(const PiSitesParams<real> p) {
-  const int lane = threadIdx.x & 31;
-  const int g = blockIdx.x * PI_WARPS + (threadIdx.x >> 5);
-  if (g >= p.G) return;  // warp-uniform
+  const int lane = LPG == 1 ? 0 : (threadIdx.x & 31);
+  const int g = LPG == 1 ? blockIdx.x * (PI_WARPS * 32) + threadIdx.x : blockIdx.x * PI_WARPS + (threadIdx.x >> 5);
+  if (g >= p.G) return;  // LPG == 32: warp-uniform; LPG == 1: no warp collectives below
   const int R = p.R, A = p.A, C = p.C, G = p.G;
   const size_t ga = (size_t)g * A;
   // ---- sweep 1: sum of concentrations; S[r][c] = sum_a pi[r,g,a] w[c,a] ---------------------------------------
   real S[BEAN_MAX_RB], H[BEAN_MAX_RB];
   for (int i = 0; i < R * C; ++i) S[i] = H[i] = real(0);
   real sum_g = real(0), sum_m = real(0);
-  for (int a = lane; a < A; a += 32) {
+  for (int a = lane; a < A; a += LPG) {
     sum_g += p.conc_g[ga + a];
     sum_m += p.conc_m[ga + a];
     const real mu = p.growth ? p.growth[ga + a] : real(0);
@@ -65,15 +69,15 @@ __global__ void __launch_bounds__(PI_WARPS * 32) pi_sites_kernel(const PiSitesPa
       for (int r = 0; r < R; ++r) S[r * C + c] += p.pi[((size_t)r * G + g) * A + a] * w;
     }
   }
-  sum_g = warp_all_sum(sum_g);
-  sum_m = warp_all_sum(sum_m);
-  for (int i = 0; i < R * C; ++i) S[i] = warp_all_sum(S[i]);
+  sum_g = warp_all_sum<LPG>(sum_g);
+  sum_m = warp_all_sum<LPG>(sum_m);
+  for (int i = 0; i < R * C; ++i) S[i] = warp_all_sum<LPG>(S[i]);
   int n_in = 0;  // replicates of this guide inside the repguide mask
   for (int r = 0; r < R; ++r) n_in += p.mask[(size_t)r * G + g] != 0;
   const int n_guide = p.mask_guide_site ? n_in : R;
   // ---- sweep 2: Multinomial value, hbar[r][c] ---------------------------------------------------------------
   double val = 0.0;
-  for (int a = lane; a < A; a += 32) {
+  for (int a = lane; a < A; a += LPG) {
     const real mu = p.growth ? p.growth[ga + a] : real(0);
     for (int c = 0; c < C; ++c) {
       const real w = p.growth ? Num<real>::exp(mu * p.tc[c]) : real(1);
@@ -88,13 +92,13 @@ __global__ void __launch_bounds__(PI_WARPS * 32) pi_sites_kernel(const PiSitesPa
       }
     }
   }
-  for (int i = 0; i < R * C; ++i) H[i] = warp_all_sum(H[i]);
+  for (int i = 0; i < R * C; ++i) H[i] = warp_all_sum<LPG>(H[i]);
   // ---- sweep 3: Dirichlet values, all gradients -----------------------------------------------------------------
   real lg_sg, dg_sg, lg_sm, dg_sm;
   lgamma_digamma(sum_g, lg_sg, dg_sg);
   lgamma_digamma(sum_m, lg_sm, dg_sm);
   if (lane == 0) val += (double)n_in * (double)lg_sm - (double)n_guide * (double)lg_sg;
-  for (int a = lane; a < A; a += 32) {
+  for (int a = lane; a < A; a += LPG) {
     const real cg = p.conc_g[ga + a], cm = p.conc_m[ga + a];
     real lg_g, dg_g, lg_m, dg_m;
     lgamma_digamma(cg, lg_g, dg_g);
@@ -136,8 +140,7 @@ __global__ void __launch_bounds__(PI_WARPS * 32) pi_sites_kernel(const PiSitesPa
     p.d_conc_m[ga + a] = dcm;
     if (p.d_growth) p.d_growth[ga + a] = dmu;
   }
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) val += __shfl_xor_sync(0xffffffffu, val, m);
+  val = warp_all_sum<LPG>(val);
   if (lane == 0) p.partial[g] = val;
 }
 
@@ -171,8 +174,13 @@ static int launch_pi_sites(const BeanPiSitesArgs* a, void* stream) {
   p.d_conc_m = static_cast<real*>(a->d_conc_model);
   p.d_pi = static_cast<real*>(a->d_pi);
   p.d_growth = static_cast<real*>(a->d_growth);
-  const int grid = (a->n_guides + PI_WARPS - 1) / PI_WARPS;
-  pi_sites_kernel<real><<<grid, PI_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (a->n_alleles < PI_WIDE_MIN_ALLELES) {
+    const int grid = (a->n_guides + PI_WARPS * 32 - 1) / (PI_WARPS * 32);
+    pi_sites_kernel<real, 1><<<grid, PI_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    const int grid = (a->n_guides + PI_WARPS - 1) / PI_WARPS;
+    pi_sites_kernel<real, 32><<<grid, PI_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  }
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;
 }

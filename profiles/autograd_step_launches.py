@@ -19,8 +19,9 @@ def main():
     if which == "survival":
         from crispr_bean_b200.survival import SurvivalSviEngine
 
-        d = dc.VariantSurvivalReporterScreenData(make_survival_screen(690, "lognormal", n_reps=3, seed=21, n_negctrl_guides=101),
-                                                 control_condition="D7")
+        n_var = int(sys.argv[2]) if len(sys.argv) > 2 else 690  # 200000 -> the 1M-guide survival screen
+        d = dc.VariantSurvivalReporterScreenData(make_survival_screen(n_var, "lognormal" if n_var == 690 else 5, n_reps=3, seed=21,
+                                                                      n_negctrl_guides=101), control_condition="D7")
         eng = SurvivalSviEngine(d, "MixtureNormal", "cuda", num_steps=100)
     else:
         from crispr_bean_b200.generic import TilingSviEngine
