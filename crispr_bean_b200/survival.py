@@ -25,7 +25,7 @@ import torch.distributions as tdist
 from ._lib import BeanError
 from .collective import ShardedDirichletRsample, global_sum, sharded_dirichlet_log_prob
 from .device_pack import DeviceScreen
-from .generic import EPS, AutogradSviEngine, _DirichletRsample, _masked_sum, _multinomial_log_prob
+from .generic import EPS, AutogradSviEngine, _DirichletRsample
 from .latent_sites import LatentPrior, latent_sites
 from .ll_function import count_log_likelihood
 from .pi_sites import PiSiteData, pi_sites
@@ -112,13 +112,6 @@ class SurvivalSviEngine(AutogradSviEngine):
         self._init_optim(theta, positive, num_steps, initial_lr, gamma, seed)
 
     # ---------------------------------------------------------------------------------------------
-    def _mu_prior(self):
-        kw = dict(device=self.device, dtype=self.dtype)
-        pp = self.prior_params or {}
-        if "mu_loc" in pp or "mu_scale" in pp:
-            return tdist.Normal(self._prior_t(pp.get("mu_loc", 0.0)), self._prior_t(pp.get("mu_scale", 1.0)))
-        return tdist.Laplace(self._c(0.0), self._c(1.0))
-
     def elbo_loss(self, noise: Optional[Dict[str, torch.Tensor]] = None):
         """-ELBO of one particle (site lists: SURVEY App. A.8)."""
         kw = dict(device=self.device, dtype=self.dtype)
