@@ -20,7 +20,6 @@ import math
 from typing import Dict, Optional
 
 import torch
-import torch.distributions as tdist
 
 from ._lib import BeanError
 from .collective import ShardedDirichletRsample, global_sum, sharded_dirichlet_log_prob
