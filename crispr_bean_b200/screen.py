@@ -60,6 +60,8 @@ class MiniScreen:
         if isinstance(idx, (pd.Series, pd.Index)):
             idx = idx.to_numpy()
         idx = np.asarray(idx)
+        if idx.ndim == 0 and idx.dtype.kind in "biu":
+            return np.asarray([int(idx)])  # AnnData: a scalar (bool included, an int subclass) selects that one position
         if idx.dtype == bool:
             return np.nonzero(idx)[0]
         if idx.dtype.kind in "OUS":

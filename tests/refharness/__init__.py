@@ -4,9 +4,9 @@ for golden-vector generation and cross-checks.  TEST INFRASTRUCTURE ONLY; availa
 
 What is real and what is shimmed:
   real  (unmodified reference code): bean/model/{model,survival_model,utils,run,readwrite}.py,
-        bean/preprocessing/{data_class,get_alpha0,get_pi_alpha0,utils}.py, bean/framework/Edit.py
+        bean/preprocessing/{data_class,get_alpha0,get_pi_alpha0,utils}.py, bean/framework/Edit.py, bean/qc/guide_qc.py
   shim  pyro (tests/refharness/pyro: restated effect handlers, Trace_ELBO, ClippedAdam), `bean` top-level
-        package (its __init__ imports anndata / perturb_tools, absent here), pyBigWig, bean.qc.guide_qc
+        package (its __init__ imports anndata / perturb_tools, absent here), pyBigWig, perturb_tools (empty)
 """
 from __future__ import annotations
 
@@ -48,19 +48,24 @@ def load_reference():
     bean.ReporterScreen = object  # only used in annotations (data_class.py:38)
     for sub in ("model", "preprocessing", "framework", "utils"):
         setattr(bean, sub, pkg(f"bean.{sub}", os.path.join(REFERENCE_ROOT, "bean", sub)))
-    qc = pkg("bean.qc", os.path.join(_HERE, "_absent"))
-    gq = types.ModuleType("bean.qc.guide_qc")
-    gq.filter_no_info_target = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("bean.qc is out of scope"))
-    sys.modules["bean.qc.guide_qc"] = gq
-    qc.guide_qc = gq
-    bean.qc = qc
+    # bean/qc/guide_qc.py is real code too (prepare_bdata calls its filter_no_info_target); only its perturb_tools import
+    # (the outlier-guide QC, out of scope) is given an empty stand-in
+    for name in ("perturb_tools", "perturb_tools._qc", "perturb_tools._qc.qc"):
+        if name not in sys.modules:
+            stub = types.ModuleType(name)
+            stub.__path__ = []
+            sys.modules[name] = stub
+    if not hasattr(sys.modules["perturb_tools._qc.qc"], "get_outlier_guides"):
+        sys.modules["perturb_tools._qc.qc"].get_outlier_guides = None
+    bean.qc = pkg("bean.qc", os.path.join(REFERENCE_ROOT, "bean", "qc"))
     sys.modules.setdefault("pyBigWig", types.ModuleType("pyBigWig"))
 
     ns = types.SimpleNamespace(pyro=pyro)
     for attr, mod in [("utils", "bean.model.utils"), ("data_class", "bean.preprocessing.data_class"),
                       ("get_alpha0", "bean.preprocessing.get_alpha0"), ("get_pi_alpha0", "bean.preprocessing.get_pi_alpha0"),
                       ("model", "bean.model.model"), ("survival_model", "bean.model.survival_model"),
-                      ("run", "bean.model.run"), ("readwrite", "bean.model.readwrite"), ("edit", "bean.framework.Edit")]:
+                      ("run", "bean.model.run"), ("readwrite", "bean.model.readwrite"), ("edit", "bean.framework.Edit"),
+                      ("prep_utils", "bean.preprocessing.utils"), ("guide_qc", "bean.qc.guide_qc")]:
         setattr(ns, attr, importlib.import_module(mod))
     bean.__refharness_ns__ = ns
     return ns
