@@ -89,6 +89,60 @@ class MiniScreen:
         """Own tables, shared count matrices (they are never written in place)."""
         return self[:, :]
 
+    # ---- the ReporterScreen members `bean run` touches besides the tables (bean/framework/ReporterScreen.py) -----------
+    @property
+    def tiling(self):
+        return self.uns["tiling"]  # ReporterScreen.py:172-174
+
+    @property
+    def target_base_changes(self):
+        """{"A": "G", ...} from uns["target_base_changes"] ("A>G,C>T"; ReporterScreen.py:164-170)."""
+        spec = self.uns["target_base_changes"] if "target_base_changes" in self.uns else self.uns["target_base_change"]
+        return {change[0]: change[-1] for change in spec.split(",")}
+
+    def get_guide_edit_rate(self, normalize_by_editable_base=None, edited_bases=None, editable_base_start=3, editable_base_end=8,
+                            bcmatch_thres=1, prior_weight=None, return_result=False, count_layer="X_bcmatch", edit_layer="edits",
+                            condition_col="condition", unsorted_condition_label=None):
+        """Per-guide reporter editing rate in the unsorted samples, written to `guides["edit_rate"]` (and
+        `guides["edit_rate_norm"]`, per editable base of the guide's activity window, for tiling screens).
+
+        Restatement of ReporterScreen.get_guide_edit_rate (ReporterScreen.py:448-529; that module needs anndata, so it is
+        not executed by tests/refharness): rate = (edits + w/2) / (barcode-matched reads + w/2) over the samples whose
+        condition contains `unsorted_condition_label`, w = prior_weight (default 1); NaN below `bcmatch_thres` reads."""
+        if normalize_by_editable_base is None:
+            normalize_by_editable_base = self.tiling
+        if count_layer not in self.layers or edit_layer not in self.layers:
+            raise ValueError("edits or barcode matched guide counts not available.")
+        n_sites = 1.0
+        if normalize_by_editable_base:
+            bases = list(self.target_base_changes.keys()) if edited_bases is None else ([edited_bases] if isinstance(edited_bases, str) else edited_bases)
+            if any(b not in ("A", "C", "T", "G") for b in bases):
+                raise ValueError("Specify the correct edited_base")
+            window = self.guides["sequence"].map(lambda seq: seq[editable_base_start:editable_base_end])
+            n_sites = sum(window.map(lambda w, b=b: w.count(b)) for b in bases)
+        if unsorted_condition_label is not None:
+            cols = np.where(self.samples[condition_col].astype(str).map(lambda c: unsorted_condition_label in c))[0]
+            if len(cols) == 0:
+                raise ValueError(f"'{unsorted_condition_label}' is not found in ReporterScreen.samples['{condition_col}'] that has values "
+                                 f"{self.samples[condition_col].unique()}. Check your input.")
+        else:
+            cols = np.arange(len(self.samples))
+        w = 1 if prior_weight is None else prior_weight
+        n_edits = self.layers[edit_layer][:, cols].sum(axis=1)
+        n_counts = self.layers[count_layer][:, cols].sum(axis=1)
+        rate = (n_edits + w / 2) / (n_counts + w / 2)
+        rate[n_counts < bcmatch_thres] = np.nan
+        if normalize_by_editable_base:
+            sites = np.asarray(n_sites, dtype=np.float64)
+            rate_norm = (n_edits + w / 2) / (n_counts * sites + w / 2)
+            rate_norm[sites == 0] = np.nan
+        if return_result:
+            return rate
+        self.guides["edit_rate"] = rate
+        if normalize_by_editable_base:
+            self.guides["edit_rate_norm"] = rate_norm
+        return None
+
 
 def read_csvs(guides_csv: str, samples_csv: str, counts_csv: str,
               layer_csvs: Optional[Dict[str, str]] = None) -> MiniScreen:

@@ -71,3 +71,43 @@ def test_latent_prior_defaults_scalars_and_per_variant_tensors():
     assert p.mu_normal and set(p.vectors) == {"mu_loc", "mu_scale"} and p.vectors["mu_loc"].shape == (5,)
     assert p.vectors["mu_loc"].dtype == torch.float32 and p.vectors["mu_loc"].is_contiguous()
     assert p.scalars["sd_scale"] == pytest.approx(0.05)
+
+
+def test_get_guide_edit_rate_follows_the_reporter_screen_definition():
+    """ReporterScreen.get_guide_edit_rate (bean/framework/ReporterScreen.py:448-529), hand-computed."""
+    X = np.full((3, 4), 100.0, dtype=np.float32)
+    bc = np.asarray([[10, 20, 30, 40], [0, 0, 5, 5], [8, 8, 0, 0]], dtype=np.float32)
+    ed = np.asarray([[1, 2, 3, 4], [0, 0, 1, 1], [4, 4, 0, 0]], dtype=np.float32)
+    guides = pd.DataFrame({"sequence": ["GGGAACAAGG", "GGGCCCCCGG", "AAAAAAAAAA"]}, index=["g0", "g1", "g2"])
+    samples = pd.DataFrame({"condition": ["top", "bulk", "bot", "bulk_2"]}, index=["s0", "s1", "s2", "s3"])
+    scr = MiniScreen(X, guides, samples, {"X_bcmatch": bc, "edits": ed}, {"tiling": False, "target_base_changes": "A>G,C>T"})
+    assert scr.tiling is False and scr.target_base_changes == {"A": "G", "C": "T"}
+    scr.get_guide_edit_rate(unsorted_condition_label="bulk")  # samples s1 and s3 (label contained in the condition)
+    assert np.allclose(scr.guides["edit_rate"], [(2 + 4 + 0.5) / (20 + 40 + 0.5), (0 + 1 + 0.5) / (0 + 5 + 0.5), (4 + 0 + 0.5) / (8 + 0 + 0.5)])
+    assert "edit_rate_norm" not in scr.guides.columns
+    all_samples = scr.get_guide_edit_rate(return_result=True, bcmatch_thres=17)
+    assert np.isnan(all_samples[1]) and np.isnan(all_samples[2]) and np.isclose(all_samples[0], 10.5 / 100.5)
+    til = MiniScreen(X, guides.copy(), samples, {"X_bcmatch": bc, "edits": ed}, {"tiling": True, "target_base_change": "A>G"})
+    til.get_guide_edit_rate(unsorted_condition_label="bulk")
+    # editable A's in positions 3..7 of the protospacer: "AACAA" -> 4, "CCCCC" -> 0 (NaN), "AAAAA" -> 5
+    assert np.allclose(til.guides["edit_rate_norm"].to_numpy()[[0, 2]], [6.5 / (60 * 4 + 0.5), 4.5 / (8 * 5 + 0.5)]) and np.isnan(til.guides["edit_rate_norm"].iloc[1])
+    with pytest.raises(ValueError, match="is not found"):
+        scr.get_guide_edit_rate(unsorted_condition_label="plasmid")
+    with pytest.raises(ValueError, match="not available"):
+        MiniScreen(X, guides, samples, {}, {"tiling": False}).get_guide_edit_rate()
+
+
+def test_edit_rate_equals_the_column_stored_in_the_reference_fixture():
+    """The reference's survival_var_mini_screen.h5ad (travelling inside the golden fixture) carries the `edit_rate` column its
+    own pipeline wrote (ReporterScreen.get_guide_edit_rate with the control condition D7, tests/test_run.py:166): the
+    restatement reproduces it exactly."""
+    import os
+
+    from tests.helpers import GOLDEN
+    from tests.refharness.golden import screen_from_arrays
+
+    scr = screen_from_arrays(np.load(os.path.join(GOLDEN, "ref_survival_real_var_mixture.npz")))
+    stored = scr.guides["edit_rate"].to_numpy().copy()
+    scr.uns["tiling"] = False
+    got = scr.get_guide_edit_rate(return_result=True, unsorted_condition_label="D7")
+    assert np.allclose(got, stored, rtol=1e-12, atol=0, equal_nan=True) and np.isfinite(stored).sum() >= 20
