@@ -44,10 +44,6 @@ class ScreenData:
                  lower_quantile_column: str = "lower_quantile", upper_quantile_column: str = "upper_quantile",
                  time_column: str = "time", use_bcmatch: bool = False, impute_pi_popt: bool = False,
                  **kwargs):
-        if accessibility_bw_path is not None and accessibility_col is None:
-            raise NotImplementedError(
-                "bigWig accessibility lookup (preprocessing/utils.py:111-146) needs pyBigWig, which is out of "
-                "scope; precompute the signal into a guide column and pass accessibility_col.")
         self.device = device
         self.condition_column = condition_column
         self.replicate_column = replicate_column
@@ -60,6 +56,7 @@ class ScreenData:
         self.pi_popt = pi_popt
         self.negctrl_guide_idx = negctrl_guide_idx
         self.accessibility_col = accessibility_col
+        self.accessibility_bw_path = accessibility_bw_path
         self.target_col = target_col
         self._lq_col, self._uq_col, self.time_column = lower_quantile_column, upper_quantile_column, time_column
 
@@ -128,6 +125,10 @@ class ScreenData:
         sel, ctl = self.screen_selected, self.screen_control
         if self.accessibility_col is not None:
             self.guide_accessibility = torch.as_tensor(self.screen.guides[self.accessibility_col].to_numpy().copy())
+        elif self.accessibility_bw_path is not None:  # data_class.py:130-133
+            from .accessibility import get_accessibility_guides
+
+            self.guide_accessibility = get_accessibility_guides(self.accessibility_bw_path, self.screen.guides)
         else:
             self.guide_accessibility = None
         if self.sample_mask_column is not None and self.sample_mask_column in sel.samples.columns:
