@@ -154,6 +154,13 @@ def real_cases(ns):
         return scr
 
     var, til = load("var_mini_screen"), load("tiling_mini_screen")
+    # `--scale-by-acc --acc-bw-path tests/data/accessibility_signal.bw` (tests/test_run.py:85): the signal is looked up with
+    # this repo's bigWig reader and handed to BOTH tensorisers as a guide column (the reference's own pyBigWig wrapper cannot
+    # run here); tests/test_bigwig_accessibility.py ties that lookup to the reference's per-guide function
+    from crispr_bean_b200.accessibility import get_accessibility_guides
+
+    til_acc = til.copy()
+    til_acc.guides["accessibility"] = get_accessibility_guides(ref_data + "accessibility_signal.bw", til_acc.guides).numpy()
     svar, stil = load("survival_var_mini_screen"), load("survival_tiling_mini_screen")
     sort_kw = dict(condition_column="condition", control_condition="bulk", control_can_be_selected=True)
     surv_kw = dict(condition_column="condition", time_column="time", control_condition="D7", control_can_be_selected=True)
@@ -171,6 +178,10 @@ def real_cases(ns):
         ("tiling_real_mini", til, dc.TilingSortingReporterScreenData, dict(sort_kw, **til_kw),
          partial(m.MultiMixtureNormalModel, scale_by_accessibility=False, use_bcmatch=(True,)),
          partial(m.MultiMixtureNormalGuide, scale_by_accessibility=False, fit_noise=True), "MultiMixtureNormal", {}),
+        ("tiling_real_mini_acc", til_acc, dc.TilingSortingReporterScreenData, dict(sort_kw, accessibility_col="accessibility", **til_kw),
+         partial(m.MultiMixtureNormalModel, scale_by_accessibility=True, use_bcmatch=(True,)),
+         partial(m.MultiMixtureNormalGuide, scale_by_accessibility=True, fit_noise=True), "MultiMixtureNormal",
+         dict(scale_by_accessibility=True, fit_noise=True)),
         # `bean run survival variant ... --control-condition=D7` (+ --uniform-edit)
         ("survival_real_var_normal", svar, dc.VariantSurvivalScreenData, dict(surv_kw, negctrl_guide_idx=negctrl),
          partial(sm.NormalModel, use_bcmatch=False), sm.NormalGuide, "Normal", dict(use_bcmatch=False)),
