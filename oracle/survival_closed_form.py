@@ -144,3 +144,56 @@ def survival_mixture_step(data, theta, noise, mu_negctrl=(0.0, 0.1), use_bcmatch
     grads["mu_loc"] = -d_mu_t
     grads["mu_scale"] = -(d_mu_t * s * eps_mu + d_ls_direct)
     return -elbo, grads
+
+
+def survival_normal_step(data, theta, noise, use_bcmatch=True, mask_thres=10):
+    """survival Normal program (`--uniform-edit`; survival_model.py:15-130, guide :629-650) in closed form.
+
+    Here the Dirichlet draw over all guides DOES reach the likelihood (e[r, b, g] = q_0[r, g] exp(mu_g t_b)), so the pathwise
+    derivative needs a third library-wide sum per replicate, sum_g x_rg gout_rg -- the one exchange step of the sharded path
+    (crispr_bean_b200/collective.py).  Unconstrained parameters: initial_abundance_u = log c (G,), mu_loc, mu_scale_u (T, 1)."""
+    G, R, T = data.n_guides, data.n_reps, data.n_targets
+    c_u, mu_loc, ls = (_np(theta[k]) for k in ("initial_abundance", "mu_loc", "mu_scale"))
+    eps_mu, x = _np(noise["eps_mu"]), _np(noise["q0"])                 # x (R, G) on the simplex
+    seg = np.repeat(np.arange(T), _np(data.target_lengths).astype(np.int64))
+    rg = _np(data.repguide_mask) > 0
+    tb = _np(data.timepoints)
+    s = np.exp(ls)
+    mu_t = mu_loc + s * eps_mu
+    elbo = float((-np.log(2.0) - np.abs(mu_t) + ls + 0.5 * eps_mu ** 2 + HALF_LOG_2PI).sum())
+    d_mu_t = -np.sign(mu_t)
+    keep = np.ones(G)
+    if hasattr(data, "negctrl_guide_idx"):  # survival_model.py:59-60: None zeroes EVERY guide's growth rate
+        keep = np.zeros(G) if data.negctrl_guide_idx is None else keep
+        if data.negctrl_guide_idx is not None:
+            keep[np.asarray(data.negctrl_guide_idx, dtype=np.int64)] = 0.0
+    mu = mu_t[seg, 0] * keep                                           # (G,)
+    # Dirichlet over all guides: model prior Dir(1/G), guide Dir(c)
+    c = np.exp(c_u)
+    prior = np.full(G, 1.0 / G)
+    lx = np.log(x)
+    C = c.sum()
+    norm = lambda a: gammaln(a.sum()) - gammaln(a).sum()
+    elbo += R * (norm(prior) - norm(c)) + float((((prior - c)[None]) * lx).sum())
+    d_c = -(R * (digamma(C) - digamma(c)) + lx.sum(0))
+    gout = (prior - c)[None] / x                                       # d ELBO / d x so far
+    # likelihood
+    P = np.exp(mu[None] * tb[:, None])                                 # (B, G)
+    e = x[:, None, :] * P[None]
+    layers = [(_np(data.size_factor), _np(data.a0), _np(data.X_masked))]
+    if use_bcmatch:
+        layers.append((_np(data.size_factor_bcmatch), _np(data.a0_bcmatch), _np(data.X_bcmatch_masked)))
+    smask = _np(data.sample_mask)
+    de = np.zeros_like(e)
+    for sf, a0, xx in layers:
+        w = (xx.transpose(0, 2, 1).sum(-1) > mask_thres) & rg
+        ll, de_l = dm_rows(e, sf, smask, a0, xx, w)
+        elbo += ll
+        de += de_l
+    gout += (de * P[None]).sum(1)
+    d_mu = (de * e * tb[None, :, None]).sum((0, 1)) * keep
+    # pathwise derivative: D (gout - sum_h x_h gout_h): the third sum over all guides
+    D = dirichlet_grad(x, np.broadcast_to(c, (R, G)).copy(), np.full((R, G), C))
+    d_c += (D * (gout - (x * gout).sum(-1, keepdims=True))).sum(0)
+    d_mu_t[:, 0] += np.bincount(seg, weights=d_mu, minlength=T)
+    return -elbo, {"initial_abundance": -(d_c * c), "mu_loc": -d_mu_t, "mu_scale": -(d_mu_t * s * eps_mu + 1.0)}

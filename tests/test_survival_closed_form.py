@@ -61,3 +61,28 @@ def test_reference_golden_cases(name):
     _, _, theta = oracle_eval(data64, noise)
     loss, _ = survival_mixture_step(data64, theta, noise)
     assert abs(loss - float(z["f64/loss"])) <= 1e-10 * abs(float(z["f64/loss"]))
+
+
+@pytest.mark.parametrize("name", ["survival_normal", "survival_normal_no_negctrl_idx", "survival_normal_bcmatch", "survival_real_var_normal"])
+def test_survival_normal_closed_form_on_golden_cases(name):
+    """`--uniform-edit` survival program: the Dirichlet draw over all guides feeds the likelihood (third library-wide sum)."""
+    import ast
+
+    from oracle.survival_closed_form import survival_normal_step
+
+    z, data = load_case(name)
+    kw = ast.literal_eval(str(z["meta/oracle_kwargs"]))
+    noise = {k: torch.as_tensor(v) for k, v in group(z, "f64/noise/").items() if "/" not in k}
+    data = cast_data(data, torch.float64)
+    with default_dtype(torch.float64):
+        ps = O.ParamStore()
+        loss, _ = O.elbo_survival_normal(data, ps, noise=noise, **kw)
+        loss.backward()
+    theta = {k: v.detach().clone() for k, v in ps.unconstrained.items()}
+    got_loss, got = survival_normal_step(data, theta, noise, **kw)
+    assert abs(got_loss - float(loss.detach())) <= 1e-11 * abs(float(loss.detach()))
+    assert abs(got_loss - float(z["f64/loss"])) <= 1e-10 * abs(float(z["f64/loss"]))
+    for k, v in ps.unconstrained.items():
+        g = v.grad.detach().double().numpy()
+        err = np.abs(got[k].reshape(g.shape) - g).max() / max(np.abs(g).max(), 1e-300)
+        assert err <= 1e-8, (k, err)
