@@ -52,3 +52,25 @@ def test_reference_golden_cases(name):
     perm = edit_perm(z, data)
     noise = {k: torch.as_tensor(to_ours(v, perm, k)) for k, v in group(z, "f64/noise/").items() if "/" not in k}
     check(data, noise, ref_loss=float(z["f64/loss"]))
+
+
+@pytest.mark.parametrize("name", ["survival_tiling", "survival_tiling_real_mini"])
+def test_survival_tiling_closed_form_on_golden_cases(name):
+    from oracle.tiling_closed_form import survival_tiling_step
+
+    z, data = load_case(name)
+    perm = edit_perm(z, data)
+    noise = {k: torch.as_tensor(to_ours(v, perm, k)) for k, v in group(z, "f64/noise/").items() if "/" not in k}
+    data = cast_data(data, torch.float64)
+    with default_dtype(torch.float64):
+        ps = O.ParamStore()
+        loss, _ = O.elbo_survival_multi_mixture_normal(data, ps, noise=noise)
+        loss.backward()
+    theta = {k: v.detach().clone() for k, v in ps.unconstrained.items()}
+    got_loss, got = survival_tiling_step(data, theta, noise)
+    assert abs(got_loss - float(loss.detach())) <= 1e-11 * abs(float(loss.detach()))
+    assert abs(got_loss - float(z["f64/loss"])) <= 1e-10 * abs(float(z["f64/loss"]))
+    for k, v in ps.unconstrained.items():
+        g = (v.grad if v.grad is not None else torch.zeros_like(v)).detach().double().numpy()
+        err = np.abs(got[k].reshape(g.shape) - g).max() / max(np.abs(g).max(), 1e-300)
+        assert err <= 1e-8, (k, err)
