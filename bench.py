@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- SVI throughput of the `bean run` hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5_genome_scale] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--scaling strong|weak] [--workload c5_genome_scale] [--impl reference]
 
-One "step" = one complete SVI step (guide sampling + ELBO forward/backward + ClippedAdam) of the
-MixtureNormal sorting model over one synthetic screen.  N=1 workload: the configuration BASELINE.json's
-target is quoted on, c5 = 1M guides x 8 replicates x 4 bins (+ barcode-matched layer, reporter edits).
-N>1 (torchrun): every rank owns its own 1M-guide shard of variants (weak scaling; the path has no
-data-path collective -- MixtureNormal has no global parameter, SURVEY section 8e -- only the ELBO
-scalar is all-reduced, once, after the timed loop).
+One "step" = one complete SVI step (guide sampling + ELBO forward/backward + ClippedAdam) of the MixtureNormal sorting
+model over one synthetic screen.  Workload: the configuration BASELINE.json's target is quoted on, c5 = 1M guides x 8
+replicates x 4 bins (+ barcode-matched layer, reporter edits).
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path
-(pyro is not installable here, so the reference itself cannot run) on a bounded sample.
+N > 1 (torchrun, one rank per GPU).  Default `--scaling strong`, the north_star's own configuration: the ONE 1M-guide
+screen is split into contiguous variant blocks (`dist.shard_variants`), every rank runs its block, and the per-step
+ELBO scalars -- the only quantity of this model that crosses ranks -- are all-reduced over NCCL in
+batches of <= 100 steps INSIDE the timed region (the reference prints the loss every 100 steps, run.py:378).
+`--scaling weak` gives every rank its own 1M-guide screen instead.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path on the box's host
+cores at the FULL workload size (pyro is not installable here, so the reference itself cannot run).
 """
 import argparse
 import json
@@ -32,16 +35,22 @@ WORKLOADS = {
     "tiny": (2_000, 5, 8),
 }
 BASELINE_MD_PUBLISHED = None  # BASELINE.md holds no published number for this metric -> vs_baseline null
+LOSS_BATCH = 100              # steps per ELBO all-reduce (reference print cadence, bean/model/run.py:378)
+GUIDE_PROFILE = os.path.join(ROOT, "profiles", "r2_guide_metrics.txt")  # ncu --set full capture of the dominant kernel
 
 
 def algorithmic_bytes_per_guide(R, B, L, guides_per_variant, itemsize=4):
-    """HBM bytes `svi_guide_kernel` (split step) must move per guide: every input read once, every output written once.
-
-    counts L*R*B + a0 L + row mask R (u8) + CSR id 4 B + reporter allele counts 2R + pi_a0 1 + alpha_pi 2 (read)
-    + per-guide (d_mu, d_sd) out 2 + variant params 4/guide-per-variant + the hand-over to `svi_alpha_kernel`:
-    (pi0, pi1, w0, w1) per replicate 4R + concentration gradients 4."""
+    """HBM bytes the guide kernel must move per guide with every input read once and every output written once
+    (SURVEY 8d): counts L*R*B + a0 L + row mask R (u8) + CSR id 4 B + reporter allele counts 2R + pi_a0 1 + alpha_pi 2
+    (read) + per-guide (d_mu, d_sd) out 2 + variant params 4/guides-per-variant.  The hand-over to `svi_alpha_kernel`
+    is NOT algorithmic (it exists because the step is split in two kernels); it is reported separately."""
     w = itemsize
-    return (L * R * B * w + L * w + R + 4 + 2 * R * w + w + 2 * w + 2 * w + 4.0 * w / guides_per_variant + 4 * R * w + 4 * w)
+    return L * R * B * w + L * w + R + 4 + 2 * R * w + w + 2 * w + 2 * w + 4.0 * w / guides_per_variant
+
+
+def handover_bytes_per_guide(R, itemsize=4):
+    """(pi0, pi1, w0, w1) per replicate + 4 concentration gradients, written by the guide kernel, read by the alpha kernel."""
+    return (4 * R + 4) * itemsize
 
 
 def alpha_kernel_bytes_per_guide(R, itemsize=4):
@@ -110,24 +119,41 @@ def time_steps(engine, steps, phases=0):
     return start.elapsed_time(stop)
 
 
-def oracle_step_time(data, n_guides_sample, steps, warmup=1):
-    """Seconds per SVI step of the CPU oracle (plain-torch restatement of the reference) on a guide subset."""
+def run_with_loss_exchange(engine, steps, world):
+    """`steps` SVI steps; the per-step ELBO scalars are summed over ranks in batches of LOSS_BATCH (one NCCL all-reduce
+    of <= 100 doubles per batch, asynchronous, ordered after the batch on the launching stream)."""
+    done = 0
+    while done < steps:
+        n = min(LOSS_BATCH, steps - done)
+        losses = engine.run(n)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(losses)  # a view of the engine's loss buffer: reduced in place
+        done += n
+
+
+def oracle_step_time(data, steps, warmup=1, anomaly=True):
+    """Seconds per SVI step of the CPU oracle (plain-torch restatement of the reference's MixtureNormal program)."""
     from oracle import bean_oracle as O
 
-    sub = data[torch.arange(n_guides_sample)] if n_guides_sample < data.n_guides else data
     ps = O.ParamStore()
     opt = O.ClippedAdam(lr=0.01, lrd=0.1 ** (1 / 2000))
     times = []
-    for t in range(warmup + steps):
-        t0 = time.perf_counter()
-        loss, _ = O.elbo_mixture_normal(sub, ps)
-        ps.zero_grad()
-        loss.backward()
-        opt.step(ps.unconstrained)
-        float(loss.detach())  # the reference syncs the loss every step (run.py:377-380)
-        if t >= warmup:
-            times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), sub
+    torch.autograd.set_detect_anomaly(anomaly)  # the reference switches it on for good (model.py:399; SURVEY App. B6)
+    try:
+        for t in range(warmup + steps):
+            t0 = time.perf_counter()
+            loss, _ = O.elbo_mixture_normal(data, ps)
+            ps.zero_grad()
+            loss.backward()
+            opt.step(ps.unconstrained)
+            float(loss.detach())  # the reference syncs the loss every step (run.py:377-380)
+            if t >= warmup:
+                times.append(time.perf_counter() - t0)
+    finally:
+        torch.autograd.set_detect_anomaly(False)
+    return sum(times) / len(times)
 
 
 def main():
@@ -137,11 +163,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5_genome_scale", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--cpu-sample-guides", type=int, default=50_000)
+    ap.add_argument("--cpu-sample-guides", type=int, default=0, help="0 = the full workload (default)")
+    ap.add_argument("--cpu-max-steps", type=int, default=25, help="upper bound on the reference arm's timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-run-steps", type=int, default=4000, help="length of the complete run timed after the K steps (0 = skip)")
     ap.add_argument("--burn-in", type=int, default=300,
-                    help="untimed SVI steps before the timed region: a step gets ~20 %% slower over the first ~300 steps of a run "
+                    help="untimed SVI steps before the timed region: a step gets slower over the first ~300 steps of a run "
                          "(alpha_pi fits the low editing rates, more Dirichlet draws leave the saddle-point regime), so the "
                          "timed steps are taken where a real 2000-step run spends its time")
     args = ap.parse_args()
@@ -152,12 +181,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     nv, gpv, nr = WORKLOADS[args.workload]
     R, B, L = nr, 4, 2
-    cells_per_step_rank = nv * gpv * R * B
-    config = {"workload": f"{args.workload}: MixtureNormal sorting, {nv * gpv} guides x {R} reps x {B} bins per GPU, "
-                          f"{nv} variants, bcmatch layer + reporter edits",
-              "model": None, "l2": "per-step inputs (0.40 GB) exceed the 126 MB L2; no flush needed",
-              "sharding": f"variants sharded, {world} shard(s) of {nv} variants (weak scaling)"}
-    config.pop("model")
+    G_total = nv * gpv * (world if args.scaling == "weak" else 1)
+    cells_per_step = G_total * R * B
+    scaling = args.scaling if world > 1 else "strong"  # at N = 1 both are the same workload
+    if args.scaling == "strong":
+        shard_txt = f"ONE screen of {nv * gpv} guides / {nv} variants split into {world} contiguous variant block(s) (strong scaling)"
+    else:
+        shard_txt = f"{world} independent screen(s) of {nv * gpv} guides, one per GPU (weak scaling)"
+    config = {"workload": f"{args.workload}: MixtureNormal sorting, {G_total} guides x {R} reps x {B} bins in total, "
+                          f"bcmatch layer + reporter edits",
+              "l2": "per-step inputs (0.36 GB per 1M guides) exceed the 126 MB L2 down to 8 shards x 45 MB + scratch; the kernels "
+                    "stream every buffer once per step, so nothing is served from a previous step's L2 lines at N <= 4; no flush",
+              "sharding": shard_txt,
+              "exchange": f"per-step ELBO scalars all-reduced over NCCL every {LOSS_BATCH} steps inside the timed region" if world > 1 else "none (one GPU)"}
 
     # ------------------------------------------------------------------------------------------
     if args.impl == "reference":
@@ -165,20 +201,25 @@ def main():
             return 0
         torch.set_num_threads(os.cpu_count() or 1)
         data = build_data(args.workload, seed=101)
-        n_sample = min(args.cpu_sample_guides, data.n_guides)
-        # warm-up + timed steps on a bounded sample of the workload's guides
-        sec, sub = oracle_step_time(data, n_sample, max(args.steps, 1), warmup=max(args.warmup, 1))
-        cells = sub.n_guides * R * B
+        if args.cpu_sample_guides and args.cpu_sample_guides < data.n_guides:
+            data = data[torch.arange(args.cpu_sample_guides)]
+        steps = max(1, min(args.steps, args.cpu_max_steps))
+        sec = oracle_step_time(data, steps, warmup=max(min(args.warmup, 2), 1), anomaly=True)
+        sec_off = oracle_step_time(data, min(steps, 3), warmup=1, anomaly=False)
+        cells = data.n_guides * R * B
         value = cells / sec
+        sample = (f"{'all' if data.n_guides == nv * gpv else 'first'} {data.n_guides} guides of the workload, {steps} timed SVI steps of the "
+                  f"plain-torch oracle port on {torch.get_num_threads()} threads, torch anomaly mode ON as the reference leaves it "
+                  f"(model.py:399): {sec * 1e3:.0f} ms/step; anomaly mode off: {sec_off * 1e3:.0f} ms/step; pyro itself is not "
+                  "installable (no poutine overhead in this number)")
         line = {
             "impl": "reference", "metric": "guide_rep_bin_cells_per_sec", "value": value, "unit": "cells/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 mixed (as the reference)",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32/f64 mixed (as the reference)",
             "data": "synthetic", "config": config,
-            "svi_steps_per_sec_at_full_size_extrapolated": value / cells_per_step_rank,
-            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"first {sub.n_guides} guides of the workload, {args.steps} SVI steps of the plain-torch "
-                                       "oracle port (pyro is not installable; no poutine overhead, anomaly mode off)"},
+            "svi_steps_per_sec": 1.0 / sec, "timed_steps": steps,
+            "anomaly_mode_off": {"value": cells / sec_off, "ms_per_step": sec_off * 1e3},
+            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -193,46 +234,60 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    from crispr_bean_b200.dist import shard_data
     from crispr_bean_b200.svi import SviEngine
 
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
-    data = build_data(args.workload, seed=101 + rank)
+    if args.scaling == "strong":
+        full = build_data(args.workload, seed=101)  # a0 / pi_a0 / size factors are fitted on the WHOLE screen, then sliced
+        data, off = shard_data(full, rank, world)
+        del full
+    else:
+        data = build_data(args.workload, seed=101 + rank)
+        off = {"guide_offset": rank * nv * gpv, "variant_offset": rank * nv, "n_guides": nv * gpv, "n_variants": nv}
+    G_rank = data.n_guides
     total_steps = args.warmup + args.steps
-    G_rank = nv * gpv
     burn_in = max(args.burn_in, 0)
     eng = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=max(2000, burn_in + 4 * total_steps + 64), seed=101,
-                    guide_offset=rank * G_rank, variant_offset=rank * nv)
-    config["burn_in_steps"] = burn_in
+                    guide_offset=off["guide_offset"], variant_offset=off["variant_offset"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
     # --- device-resident throughput: inputs already in HBM --------------------------------------
-    eng.run(burn_in)  # untimed: reach the steady-state regime of a long run (see --burn-in)
-    eng.run(args.warmup)
+    run_with_loss_exchange(eng, burn_in, world)  # untimed: reach the steady-state regime of a long run (see --burn-in)
+    run_with_loss_exchange(eng, args.warmup, world)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms = time_steps(eng, args.steps)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    run_with_loss_exchange(eng, args.steps, world)
+    stop.record()
     barrier()
     sampler.stop_flag = True
     sampler.join()
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+    ms = max_over_ranks(start.elapsed_time(stop))
     steps_per_sec = args.steps / (ms * 1e-3)
-    value = cells_per_step_rank * world * steps_per_sec
-
+    value = cells_per_step * steps_per_sec
     final_loss = float(eng.loss[eng.step - 1].item())
-    # --- per-kernel timing for the roofline (guide kernel alone, same launches, CUDA events) -----
-    ms_var = time_steps(eng, args.steps, phases=2) / args.steps
-    ms_alpha = time_steps(eng, args.steps, phases=4) / args.steps if eng.split else 0.0
-    ms_guide = ms / args.steps - ms_var - ms_alpha  # the guide kernel's share of the timed steps themselves
+
+    # --- per-kernel timing for the roofline: each kernel alone, same launches, CUDA events --------
+    ms_guide = max_over_ranks(time_steps(eng, args.steps, phases=1) / args.steps)
+    ms_alpha = max_over_ranks(time_steps(eng, args.steps, phases=4) / args.steps) if eng.split else 0.0
+    ms_var = max_over_ranks(time_steps(eng, args.steps, phases=2) / args.steps)
     itemsize = 4 if dtype == torch.float32 else 8
-    bytes_launch = algorithmic_bytes_per_guide(R, B, L, gpv, itemsize) * nv * gpv
+    bytes_launch = algorithmic_bytes_per_guide(R, B, L, gpv, itemsize) * G_rank
+    handover = handover_bytes_per_guide(R, itemsize) * G_rank if eng.split else 0.0
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
@@ -241,76 +296,105 @@ def main():
     # empirical FP32/SFU ceiling: the Dirichlet-Multinomial row maths alone, operands in registers
     from crispr_bean_b200 import _lib as L_
 
-    sink = torch.empty((nv * gpv + 127) // 128, device=dev, dtype=torch.float32)
+    sink = torch.empty((G_rank + 127) // 128, device=dev, dtype=torch.float32)
     st = torch.cuda.current_stream(dev).cuda_stream
     for _ in range(3):
-        L_.check(L_.lib().bean_row_ceiling_f32(nv * gpv, R * L, B, sink.data_ptr(), st), "bean_row_ceiling_f32")
+        L_.check(L_.lib().bean_row_ceiling_f32(G_rank, R * L, B, sink.data_ptr(), st), "bean_row_ceiling_f32")
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
     for _ in range(20):
-        L_.check(L_.lib().bean_row_ceiling_f32(nv * gpv, R * L, B, sink.data_ptr(), st), "bean_row_ceiling_f32")
+        L_.check(L_.lib().bean_row_ceiling_f32(G_rank, R * L, B, sink.data_ptr(), st), "bean_row_ceiling_f32")
     c1.record()
     torch.cuda.synchronize()
     ms_ceiling = c0.elapsed_time(c1) / 20
     achieved = bytes_launch / (ms_guide * 1e-3) / 1e9
-    # DRAM traffic and instruction count of one launch, from the committed ncu --set full capture of this kernel
-    traffic, warp_inst, prof = None, None, os.path.join(ROOT, "profiles", "r1_final_guide_metrics.txt")
-    if os.path.exists(prof) and args.workload == "c5_genome_scale" and dtype == torch.float32:
-        m = {ln.split(" [")[0]: float(ln.rsplit("=", 1)[1]) for ln in open(prof) if " = " in ln and " [" in ln}
-        traffic = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) * 1e6
-        warp_inst = m["smsp__inst_executed.sum"]
+    # DRAM traffic, instruction count and pipe utilisation of one launch, from the committed ncu --set full capture
+    traffic = warp_inst = None
+    note = "no ncu capture of this configuration committed"
+    if os.path.exists(GUIDE_PROFILE) and args.workload == "c5_genome_scale" and dtype == torch.float32 and world == 1:
+        m = {}
+        for ln in open(GUIDE_PROFILE):
+            if " = " in ln:
+                key, val = ln.rsplit(" = ", 1)
+                try:
+                    m[key.split(" [")[0].strip()] = float(val)
+                except ValueError:
+                    pass
+        if "dram__bytes_read.sum" in m:
+            traffic = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) * m.get("_dram_unit_bytes", 1e6)
+            warp_inst = m.get("smsp__inst_executed.sum")
+            note = ("from " + os.path.relpath(GUIDE_PROFILE, ROOT) + ": issue slots "
+                    f"{m.get('smsp__issue_active.avg.pct_of_peak_sustained_active', float('nan')):.1f} % busy, FMA pipe "
+                    f"{m.get('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', float('nan')):.1f} %, ALU "
+                    f"{m.get('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', float('nan')):.1f} %, XU "
+                    f"{m.get('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', float('nan')):.1f} %, DRAM "
+                    f"{m.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', float('nan')):.1f} % of peak")
     clk = (sampler.summary()["sm_mhz"] or 1965) * 1e6
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     roofline = {"bound": "hbm", "kernel": "svi_guide_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r1_final_guide_metrics.txt (ncu --set full, one launch)",
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": os.path.relpath(GUIDE_PROFILE, ROOT) + " (ncu --set full, one launch)" if traffic else None,
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": ms_guide,
+                "algorithmic_bytes_per_launch": bytes_launch, "handover_bytes_per_launch": handover,
+                "ms_per_launch": ms_guide, "ms_per_launch_how": "the guide kernel launched alone (BeanSviConfig.phases = 1), CUDA events",
                 "ms_per_launch_variant_kernel": ms_var, "ms_per_launch_alpha_kernel": ms_alpha,
-                "alpha_kernel_gbs": alpha_kernel_bytes_per_guide(R, itemsize) * nv * gpv / (ms_alpha * 1e-3) / 1e9 if ms_alpha else None,
-                "row_math_ceiling_ms": ms_ceiling, "frac_of_row_math_ceiling": ms_ceiling / ms_guide,
-                "row_math_ceiling_what": "register-only kernel evaluating the same Dirichlet-Multinomial row maths "
-                                         f"({R * L} rows x {B} bins per guide: {2 * B + 2} lgamma/digamma pairs + {2 * B} log1p per row) "
-                                         "with no memory traffic: the measured FP32/SFU floor of the step's row work",
-                "warp_instructions_per_launch": warp_inst,
-                "issue_floor_ms": (warp_inst / (4 * n_sm * clk) * 1e3) if warp_inst else None,
-                "note": "HBM is ~11 % utilised: the kernel is bound by instruction issue (ncu: issue slots 84 % busy; ALU 52 %, FMA 44 %, "
-                        "XU 23 % of their peaks); issue_floor_ms = executed warp instructions / (4 schedulers x SMs x clock), "
-                        "row_math_ceiling_ms = the Dirichlet-Multinomial row maths alone from registers; traffic exceeds the "
-                        "algorithmic bytes by the kernel's register spills (64 registers, 8 CTAs/SM); see DESIGN.md section 3"}
+                "alpha_kernel_gbs": alpha_kernel_bytes_per_guide(R, itemsize) * G_rank / (ms_alpha * 1e-3) / 1e9 if ms_alpha else None,
+                "whole_step_frac": (bytes_launch + (12 * itemsize + 24.0 * itemsize / gpv) * G_rank) / (ms / args.steps * 1e-3) / 1e9 / peak,
+                "compute_roofline": {
+                    "what": "register-only kernel evaluating the same Dirichlet-Multinomial row maths "
+                            f"({R * L} rows x {B} bins per guide: {2 * B + 2} lgamma/digamma corrections + {2 * B} log1p per row) with "
+                            "no memory traffic at the same launch geometry: the measured FP32/SFU floor of the step's row work",
+                    "row_math_ceiling_ms": ms_ceiling, "frac": ms_ceiling / ms_guide,
+                    "warp_instructions_per_launch": warp_inst,
+                    "issue_floor_ms": (warp_inst / (4 * n_sm * clk) * 1e3) if warp_inst else None},
+                "note": note}
 
     # --- e2e: host-resident screen -> public API -> host-resident results ------------------------
-    from crispr_bean_b200.device_pack import DeviceScreen
-
     data.pin_memory()  # the contract's e2e starts from PINNED host memory; pinning itself is not timed
     barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = args.steps
     loss_host = torch.zeros(e2e_steps, dtype=torch.float64).pin_memory()
     t0.record()
-    eng2 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=e2e_steps, seed=7,  # H2D of the whole screen
-                     guide_offset=rank * G_rank, variant_offset=rank * nv)
+    eng2 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=e2e_steps, seed=7,  # H2D of the whole shard
+                     guide_offset=off["guide_offset"], variant_offset=off["variant_offset"])
     for t in range(e2e_steps):
         eng2.run(1)
-        loss_host[t].copy_(eng2.loss[t], non_blocking=True)  # the step's result back on the host, every step
+        if world == 1:
+            loss_host[t].copy_(eng2.loss[t], non_blocking=True)  # the step's result back on the host, every step
+        elif (t + 1) % LOSS_BATCH == 0 or t + 1 == e2e_steps:
+            lo = (t // LOSS_BATCH) * LOSS_BATCH
+            dist.all_reduce(eng2.loss[lo:t + 1])
+            loss_host[lo:t + 1].copy_(eng2.loss[lo:t + 1], non_blocking=True)
     params_host = {k: v.cpu() for k, v in eng2.params().items()}
     t1.record()
     barrier()
-    ms_e2e = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = t.item()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
     scr = eng2.screen
     h2d = (scr.x.numel() + scr.a0.numel()) * itemsize + scr.row_mask.numel() + (eng2.allele_counts.numel() + eng2.pi_a0.numel()) * itemsize \
         + eng2.guide_variant.numel() * 4 + eng2.variant_ptr.numel() * 4
     d2h = 8 * e2e_steps + sum(v.numel() * v.element_size() for v in params_host.values())
-    e2e_value = cells_per_step_rank * world * e2e_steps / (ms_e2e * 1e-3)
+    e2e_value = cells_per_step * e2e_steps / (ms_e2e * 1e-3)
     assert torch.isfinite(loss_host).all()
+    del eng2
 
-    if world > 1:  # the only collective of the path: the ELBO scalar, outside the timed loops
-        l = eng.loss[: eng.step].clone()
-        dist.all_reduce(l)
+    # --- the north_star's run: a complete SVI fit of `--full-run-steps` steps from step 0 --------
+    full_run = None
+    if args.full_run_steps > 0:
+        eng3 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=args.full_run_steps, seed=101,
+                         guide_offset=off["guide_offset"], variant_offset=off["variant_offset"])
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        run_with_loss_exchange(eng3, args.full_run_steps, world)
+        f1.record()
+        barrier()
+        ms_full = max_over_ranks(f0.elapsed_time(f1))
+        full_run = {"steps": args.full_run_steps, "seconds": ms_full * 1e-3, "svi_steps_per_sec": args.full_run_steps / (ms_full * 1e-3),
+                    "value": cells_per_step * args.full_run_steps / (ms_full * 1e-3), "unit": "cells/s",
+                    "loss_first": float(eng3.loss[0].item()), "loss_last": float(eng3.loss[args.full_run_steps - 1].item()),
+                    "what": "fresh engine, steps 0..N-1 with lr decay over the run, ELBO exchange included; device-resident screen"}
+        del eng3
 
     if rank != 0:
         if world > 1:
@@ -319,25 +403,29 @@ def main():
 
     line = {
         "metric": "guide_rep_bin_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": BASELINE_MD_PUBLISHED, "dtype": args.dtype, "data": "synthetic", "config": config,
+        "burn_in_steps": burn_in, "guides_per_gpu": G_rank,
         "svi_steps_per_sec": steps_per_sec,
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
-                "what": f"SviEngine built from HOST tensors (screen upload + re-tiling inside the timed region), {e2e_steps} steps, "
-                        "each step's loss copied to pinned host memory, final parameters copied to host"},
+                "what": f"SviEngine built from PINNED HOST tensors (this rank's shard: upload + re-tiling + data-only constants inside the "
+                        f"timed region), {e2e_steps} steps from step 0, losses copied to pinned host memory (every step at N = 1, per "
+                        f"{LOSS_BATCH}-step all-reduce batch at N > 1), final parameters copied to host; per-rank bytes"},
         "gpu_launches": (3 if eng.split else 2) * args.steps,
         "roofline": roofline,
         "final_loss": final_loss,
     }
+    if full_run:
+        line["full_run"] = full_run
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        n_sample = min(args.cpu_sample_guides, data.n_guides)
-        sec, sub = oracle_step_time(data, n_sample, steps=3, warmup=1)
-        cpu_val = sub.n_guides * R * B / sec
-        line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"first {sub.n_guides} guides of the workload, 3 timed SVI steps of the plain-torch oracle "
-                                          f"port ({sec * 1e3:.0f} ms/step); pyro itself is not installable here"}
+        sub = data if not args.cpu_sample_guides or args.cpu_sample_guides >= data.n_guides else data[torch.arange(args.cpu_sample_guides)]
+        sec = oracle_step_time(sub, steps=3, warmup=1, anomaly=True)
+        line["cpu_baseline"] = {"value": sub.n_guides * R * B / sec, "unit": "cells/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{'all' if sub.n_guides == data.n_guides else 'first'} {sub.n_guides} guides of the workload, 3 timed SVI "
+                                          f"steps of the plain-torch oracle port ({sec * 1e3:.0f} ms/step, torch anomaly mode on as in the "
+                                          "reference); pyro itself is not installable here"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

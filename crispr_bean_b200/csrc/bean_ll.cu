@@ -92,11 +92,11 @@ __device__ __forceinline__ double ll_rows(const LLParams<real>& p, int g, real* 
   const real eps = real(1e-5);
   double ll_acc = 0.0;
   for (int r = 0; r < R; ++r) {
-    const bool rmask = p.row_mask[(size_t)g * R + r] != 0;
+    const bool rmask = p.row_mask[(size_t)r * p.G + g] != 0;
     real de[BEAN_MAX_BINS];
     for (int b = 0; b < B; ++b) de[b] = real(0);
     for (int l = 0; l < p.L; ++l) {
-      const real* xr = p.x + (((size_t)l * p.G + g) * R + r) * B;
+      const real* xr = p.x + (((size_t)l * R + r) * p.G + g) * B;
       const real a0 = p.a0[(size_t)l * p.G + g];
       real xb[BEAN_MAX_BINS] = {}, pb[BEAN_MAX_BINS];
       real N = real(0), S = real(0);
@@ -118,10 +118,14 @@ __device__ __forceinline__ double ll_rows(const LLParams<real>& p, int g, real* 
         ab[b] = live[b] ? raw : eps;
         Asum += ab[b];
       }
+      if (!w) {  // poutine.mask: the row contributes nothing
+        if (writer && p.ll_row) p.ll_row[((size_t)l * R + r) * p.G + g] = real(0);
+        continue;
+      }
       real psi_diff[BEAN_MAX_BINS];
       const real V = dm_row_kl<real, BEAN_MAX_BINS>(B, xb, ab, N, Asum, psi_diff);
       // data-only part of the log-pmf, hoisted to tensorisation time (row_const is NULL -> 0)
-      const double K = p.row_const ? p.row_const[((size_t)l * p.G + g) * R + r] : 0.0;
+      const double K = p.row_const ? p.row_const[((size_t)l * R + r) * p.G + g] : 0.0;
       const double ll = (double)V + K;
       real gb[BEAN_MAX_BINS];
       real dot = real(0);
@@ -129,12 +133,10 @@ __device__ __forceinline__ double ll_rows(const LLParams<real>& p, int g, real* 
         gb[b] = live[b] ? psi_diff[b] * p.t.smask[r * B + b] : real(0);
         dot += gb[b] * frac[b];
       }
-      if (writer && p.ll_row) p.ll_row[((size_t)l * p.G + g) * R + r] = w ? real(ll) : real(0);
-      if (w) {
-        ll_acc += ll;
-        const real c = a0 * inv;
-        for (int b = 0; b < B; ++b) de[b] += p.t.sf[l][r * B + b] * c * (gb[b] - dot);
-      }
+      if (writer && p.ll_row) p.ll_row[((size_t)l * R + r) * p.G + g] = real(ll);
+      ll_acc += ll;
+      const real c = a0 * inv;
+      for (int b = 0; b < B; ++b) de[b] += p.t.sf[l][r * B + b] * c * (gb[b] - dot);
     }
     for (int b = 0; b < B; ++b) e[r * B + b] = de[b];
   }

@@ -71,36 +71,159 @@ template <> struct Num<double> {
 
 // ---- Gamma-function corrections to the Stirling main part, z > 0 ---------------------------------
 // gamma_corr(z) returns
-//   cv = lgamma(z)  - [(z - 1/2) ln z - z + ln(2 pi)/2]
+//   cv = lgamma(z)  - [(z - 1/2) ln z - z + ln(2 pi)/2]      (Binet's function)
 //   dl = digamma(z) - ln z
+//   iz = 1 / z                                                (a by-product every caller needs)
 // The Dirichlet-Multinomial row is assembled from these in "KL form" (bean_row.cuh): every large
 // z ln z product cancels ANALYTICALLY and only logs of near-1 ratios remain, so float keeps ~1e-6
 // absolute accuracy on a row whose individual lgamma terms are O(1e3..1e4) (a float lgamma(300) alone
 // is already off by 1e-4, which is the noise floor of the reference's own fp32 torch.lgamma path).
-// float, z >= 4: pure series in 1/z (no log at all); z < 4: 4-step upward recurrence first.
-__device__ __forceinline__ void gamma_corr(float z, float& cv, float& dl) {
-  float zs = z;
-  if (z < 4.0f) zs = z + 4.0f;
-  const float rz = rcp_ftz(zs);
-  const float r2 = rz * rz;
-  // lgamma tail: 1/(12 z) - 1/(360 z^3) + 1/(1260 z^5) - 1/(1680 z^7)
-  cv = rz * (8.3333333333e-2f + r2 * (-2.7777777778e-3f + r2 * (7.9365079365e-4f + r2 * -5.9523809524e-4f)));
-  // digamma tail: -1/(2z) - 1/(12 z^2) + 1/(120 z^4) - 1/(252 z^6) + 1/(240 z^8)
-  dl = -0.5f * rz - r2 * (8.3333333333e-2f + r2 * (-8.3333333333e-3f + r2 * (3.9682539683e-3f + r2 * -4.1666666667e-3f)));
-  if (z < 4.0f) {
-    // Gamma(z) = Gamma(z+4) / P(z), P = z (z+1) (z+2) (z+3);  psi(z) = psi(z+4) - P'(z)/P(z).
-    //   cv(z) = cv(z+4) + (z + 1/2) ln(1 + 4/z) + ln((z+4)^3 / ((z+1)(z+2)(z+3))) - 4
-    //   dl(z) = dl(z+4) + ln(1 + 4/z) - P'/P
-    // Both logs are multiplied by factors <= 4.5, so the 3-ulp MUFU log is accurate enough here.
-    const float z1 = z + 1.0f, z2 = z + 2.0f, z3 = z + 3.0f;
-    const float p123 = z1 * z2 * z3;
-    const float iz = rcp_ftz(z), ip = rcp_ftz(p123);
-    const float ls = log_ftz(zs * iz);
-    const float lr = log_ftz(zs * zs * zs * ip);
-    cv += (z + 0.5f) * ls + lr - 4.0f;
-    // P'/P = 1/z + ((z+1)(z+2) + (z+1)(z+3) + (z+2)(z+3)) / ((z+1)(z+2)(z+3))
-    dl += ls - (iz + (z1 * z2 + z1 * z3 + z2 * z3) * ip);
+//
+// float: Binet's function is exactly odd in w = 1/z (mu(z) = 2 int_0^inf atan(t w) / (e^{2 pi t} - 1) dt) and
+// dl + w/2 is w^2 times an even function, so on z >= 1
+//   cv = w Q(w^2),   dl = -w/2 - w^2 R(w^2)
+// with degree-6 polynomials fitted on w^2 in [0, 1] (tools/fit_gamma_corr.py: 1.2e-8 / 4.2e-8 absolute in float
+// arithmetic).  ONE uniform path -- 1 MUFU + 17 FP32 instructions -- replaces round 1's 4-term asymptotic series
+// (z >= 4) / 4-step product recurrence (z < 4, 3 MUFU.RCP + 2 MUFU.LG2 + ~40 FP32), whose two branches nearly every
+// warp executed one after the other.  z < 1 (concentrations of low-depth guides) takes one recurrence step first:
+//   cv(z) = cv(z+1) + (z + 1/2) ln(1 + 1/z) - 1,   dl(z) = dl(z+1) + ln(1 + 1/z) - 1/z.
+__device__ __forceinline__ void gamma_corr(float z, float& cv, float& dl, float& iz) {
+  const bool small = z < 1.0f;
+  const float zs = small ? z + 1.0f : z;
+  const float w = rcp_ftz(zs);
+  const float s = w * w;
+  float q = -4.973261975e-05f, r = 3.128883582e-04f;
+  r = fmaf(r, s, -1.310639309e-03f);
+  q = fmaf(q, s, 2.012484825e-04f);   r = fmaf(r, s, 2.468633250e-03f);
+  q = fmaf(q, s, -4.087322828e-04f);  r = fmaf(r, s, -3.093881036e-03f);
+  q = fmaf(q, s, 7.606665913e-04f);   r = fmaf(r, s, 3.831227344e-03f);
+  q = fmaf(q, s, -2.775296125e-03f);  r = fmaf(r, s, -8.325798381e-03f);
+  q = fmaf(q, s, 8.333329976e-02f);   r = fmaf(r, s, 8.333325842e-02f);
+  cv = w * q;
+  dl = fmaf(-s, r, -0.5f * w);
+  iz = w;
+  if (small) {
+    iz = rcp_ftz(z);
+    const float ls = log_ftz(zs * iz);  // ln(1 + 1/z) >= ln 2: the MUFU log's absolute error is relative here
+    cv += fmaf(z + 0.5f, ls, -1.0f);
+    dl += ls - iz;
   }
+}
+__device__ __forceinline__ void gamma_corr(float z, float& cv, float& dl) {
+  float iz;
+  gamma_corr(z, cv, dl, iz);
+}
+
+// log1p(y) for the ratio arguments of the KL-form row, y > -1.  1 + y in [0.4, 2.5] (every bin whose posterior and prior
+// fractions are within a factor 2.5 of each other -- all but outlier bins):
+//   log1p(y) = 2 atanh(s) = 2 s + s^3 P(s^2),  s = y / (2 + y),  |s| <= 3/7,
+// P of degree 4 (tools/fit_log1p_ratio.py: 8.8e-9 truncation, 1.6e-7 in float arithmetic = the rounding of the division):
+// 1 MUFU + 10 FP32 instructions against ~26 for log1pf.  The argument itself carries ~3 ulp (a product of two MUFU
+// reciprocals), so nothing is lost against log1pf.  Outside that range: MUFU lg2 of the rounded 1 + y plus the
+// first-order term of the rounding residue; |log| >= ln 2.5 there, so lg2's 2^-22 ABSOLUTE error is ~2e-7 relative.
+__device__ __forceinline__ bool log1p_ratio_in_range(float y) { return y > -0.6f && y < 1.5f; }
+__device__ __forceinline__ float log1p_ratio_wide(float y) {
+  const float u = 1.0f + y;
+  const float c = y - (u - 1.0f);
+  return fmaf(c, rcp_ftz(u), log_ftz(u));
+}
+__device__ __forceinline__ float log1p_ratio(float y) {
+  const float d = 2.0f + y;
+  const float s = y * rcp_ftz(d);
+  const float t = s * s;
+  float p = 2.757020617e-01f;
+  p = fmaf(p, t, 2.058080059e-01f);
+  p = fmaf(p, t, 2.868322504e-01f);
+  p = fmaf(p, t, 3.999738930e-01f);
+  p = fmaf(p, t, 6.666667629e-01f);
+  float r = fmaf(s * t, p, s + s);
+  if (!log1p_ratio_in_range(y)) r = log1p_ratio_wide(y);
+  return r;
+}
+
+// ---- the same two functions on PAIRS, through Blackwell's packed FP32 instructions ---------------------------------------
+// sm_100 has FFMA2 / FMUL2 / FADD2 (PTX fma.rn.f32x2 ...): one issue slot, two IEEE-rounded FP32 operations on a 64-bit
+// register pair.  The SVI guide kernel is bound by instruction ISSUE (profiles/), and its row maths comes in natural
+// pairs -- gamma_corr of (a_b, x_b + a_b) and of (A, N + A), the two log1p of a bin -- so each pair's Horner chains run
+// as one chain of packed instructions.  Results are bit-identical to the scalar functions above (same operations, same
+// rounding), which is what the CPU-side emulation in tests/ checks them against.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+
+// (cv, dl, 1/z) of z.x and z.y
+__device__ __forceinline__ void gamma_corr2(float2 z, float2& cv, float2& dl, float2& iz) {
+  const bool sx = z.x < 1.0f, sy = z.y < 1.0f;
+  const float2 zs = make_float2(sx ? z.x + 1.0f : z.x, sy ? z.y + 1.0f : z.y);
+  const float2 w = make_float2(rcp_ftz(zs.x), rcp_ftz(zs.y));
+  const float2 s = mul2(w, w);
+  float2 q = splat2(-4.973261975e-05f), r = splat2(3.128883582e-04f);
+  r = fma2(r, s, splat2(-1.310639309e-03f));
+  q = fma2(q, s, splat2(2.012484825e-04f));   r = fma2(r, s, splat2(2.468633250e-03f));
+  q = fma2(q, s, splat2(-4.087322828e-04f));  r = fma2(r, s, splat2(-3.093881036e-03f));
+  q = fma2(q, s, splat2(7.606665913e-04f));   r = fma2(r, s, splat2(3.831227344e-03f));
+  q = fma2(q, s, splat2(-2.775296125e-03f));  r = fma2(r, s, splat2(-8.325798381e-03f));
+  q = fma2(q, s, splat2(8.333329976e-02f));   r = fma2(r, s, splat2(8.333325842e-02f));
+  cv = mul2(w, q);
+  dl = fma2(make_float2(-s.x, -s.y), r, mul2(w, splat2(-0.5f)));
+  iz = w;
+  if (sx | sy) {  // one recurrence step for arguments below 1 (see gamma_corr)
+    if (sx) {
+      iz.x = rcp_ftz(z.x);
+      const float ls = log_ftz(zs.x * iz.x);
+      cv.x += fmaf(z.x + 0.5f, ls, -1.0f);
+      dl.x += ls - iz.x;
+    }
+    if (sy) {
+      iz.y = rcp_ftz(z.y);
+      const float ls = log_ftz(zs.y * iz.y);
+      cv.y += fmaf(z.y + 0.5f, ls, -1.0f);
+      dl.y += ls - iz.y;
+    }
+  }
+}
+
+// (log1p(y.x), log1p(y.y))
+__device__ __forceinline__ float2 log1p_ratio2(float2 y) {
+  const float2 d = add2(y, splat2(2.0f));
+  const float2 s = mul2(y, make_float2(rcp_ftz(d.x), rcp_ftz(d.y)));
+  const float2 t = mul2(s, s);
+  float2 p = splat2(2.757020617e-01f);
+  p = fma2(p, t, splat2(2.058080059e-01f));
+  p = fma2(p, t, splat2(2.868322504e-01f));
+  p = fma2(p, t, splat2(3.999738930e-01f));
+  p = fma2(p, t, splat2(6.666667629e-01f));
+  float2 r = fma2(mul2(s, t), p, add2(s, s));
+  if (!(log1p_ratio_in_range(y.x) && log1p_ratio_in_range(y.y))) {  // outlier bin: rare, one branch for the pair
+    if (!log1p_ratio_in_range(y.x)) r.x = log1p_ratio_wide(y.x);
+    if (!log1p_ratio_in_range(y.y)) r.y = log1p_ratio_wide(y.y);
+  }
+  return r;
 }
 
 __device__ __forceinline__ double digamma_f64(double z) {
@@ -120,6 +243,11 @@ __device__ __forceinline__ void gamma_corr(double z, double& cv, double& dl) {
   cv = ::lgamma(z) - ((z - 0.5) * lz - z + 0.91893853320467274178);
   dl = digamma_f64(z) - lz;
 }
+__device__ __forceinline__ void gamma_corr(double z, double& cv, double& dl, double& iz) {
+  gamma_corr(z, cv, dl);
+  iz = 1.0 / z;
+}
+__device__ __forceinline__ double log1p_ratio(double y) { return ::log1p(y); }
 
 // full lgamma / digamma of one argument (off the hot row loop: Dirichlet normalisers)
 template <typename real>
@@ -179,6 +307,30 @@ static __device__ __noinline__ void bin_prob_sorting(float thr_u, float thr_l, f
   const float zfu = hu ? zu * fu : 0.0f, zfl = hl ? zl * fl : 0.0f;
   dP_dmu = -(fu - fl) * rs;
   dP_dsd = -(zfu - zfl) * rs;
+}
+
+// The same split in two: the mass alone (prologue of the SVI guide kernel) and its (mu, sd) derivatives alone (epilogue).
+__device__ __forceinline__ double bin_mass_sorting(double thr_u, double thr_l, double mu, double sd) {
+  double P, a, b;
+  bin_prob_sorting(thr_u, thr_l, mu, sd, P, a, b);
+  return P;
+}
+static __device__ __noinline__ float bin_mass_sorting(float thr_u, float thr_l, float mu, float sd) {
+  const float rs = 1.0f / sd;
+  const float zu = !isinf(thr_u) ? (thr_u - mu) * rs : INFINITY;
+  const float zl = !isinf(thr_l) ? (thr_l - mu) * rs : -INFINITY;
+  const float k = 0.70710678118654752440f;
+  if (zl > 0.0f) return 0.5f * (ool_erfcf(zl * k) - ool_erfcf(zu * k));
+  return 0.5f * (ool_erfcf(-zu * k) - ool_erfcf(-zl * k));
+}
+template <typename real>
+__device__ __forceinline__ void bin_mass_grad_sorting(real thr_u, real thr_l, real mu, real sd, real& dP_dmu, real& dP_dsd) {
+  const real rs = real(1) / sd;
+  const bool hu = !isinf(thr_u), hl = !isinf(thr_l);
+  const real zu = hu ? (thr_u - mu) * rs : real(0), zl = hl ? (thr_l - mu) * rs : real(0);
+  const real fu = hu ? std_normal_pdf(zu) : real(0), fl = hl ? std_normal_pdf(zl) : real(0);
+  dP_dmu = -(fu - fl) * rs;
+  dP_dsd = -(zu * fu - zl * fl) * rs;
 }
 
 // ---- block reduction of a double (deterministic order) ------------------------------------------

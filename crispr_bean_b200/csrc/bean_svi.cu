@@ -25,7 +25,10 @@ namespace bean {
 
 constexpr int SVI_THREADS = 128;
 constexpr int SVI_MIN_CTAS = 4;        // fused guide step: <= 128 registers, 16 warps/SM (more CTAs measured +-2 %)
-constexpr int SVI_MIN_CTAS_SPLIT = 8;  // split guide step and the Normal models: 64 registers, 32 warps/SM
+#ifndef BEAN_GUIDE_MIN_CTAS
+#define BEAN_GUIDE_MIN_CTAS 8
+#endif
+constexpr int SVI_MIN_CTAS_SPLIT = BEAN_GUIDE_MIN_CTAS;  // split guide step and the Normal models: 64 registers, 32 warps/SM
                                        // (MixtureNormal 4: 1.17, 6: 1.11, 8: 1.08 ms/step; Normal 4: 0.64, 8: 0.58; final kernel 7: 0.650, 8: 0.640 ms)
 // ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
 // so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
@@ -141,38 +144,42 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
     real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd;
     variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd);
     const real sigma = p.sd_is_sqrt ? Num<real>::sqrt(sd_t) : sd_t;  // model.py:92-98
-    real P1[NB], dPm[NB], dPs[NB], dP[NB];
+    // bin masses of the edited allele now; their (mu, sd) derivatives are recomputed in the epilogue (two exp per bin)
+    // instead of being carried through the replicate loop in 2 NB registers
+    real P1[NB], dP[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      P1[b] = dPm[b] = dPs[b] = dP[b] = real(0);
-      if (b < B) bin_prob_sorting(p.t.thr_u[b], p.t.thr_l[b], mu_t, sigma, P1[b], dPm[b], dPs[b]);
+      P1[b] = dP[b] = real(0);
+      if (b < B) P1[b] = bin_mass_sorting(p.t.thr_u[b], p.t.thr_l[b], mu_t, sigma);
     }
     // editing-rate concentrations (model.py:449 / :835): model = alpha/sum*pi_a0, guide = clamp(model, 1e-5)
     real al[2] = {real(1), real(1)}, cm[2] = {real(1), real(1)}, cg[2] = {real(1), real(1)};
-    real lg_cm = real(0), lg_cg = real(0), dg_cm[3] = {}, dg_cg[3] = {}, dcm[2] = {}, dcg[2] = {};
+    real lg_cm = real(0), lg_cg = real(0), dgd_cm[2] = {}, dgd_cg[2] = {}, dcm[2] = {}, dcg[2] = {};  // dgd = psi(sum) - psi(c_a)
     real asum = real(2), pa0 = real(0);
     if (MIXTURE) {
       al[0] = Num<real>::exp(p.alpha_u[2 * (size_t)g]);
       al[1] = Num<real>::exp(p.alpha_u[2 * (size_t)g + 1]);
       asum = al[0] + al[1];
       pa0 = p.pi_a0[g];
-      real lg0, lg1, lgs;
+      real lg0, lg1, lgs, d0, d1, ds;
       cm[0] = al[0] / asum * pa0;
       cm[1] = al[1] / asum * pa0;
-      lgamma_digamma(cm[0], lg0, dg_cm[0]);
-      lgamma_digamma(cm[1], lg1, dg_cm[1]);
-      lgamma_digamma(cm[0] + cm[1], lgs, dg_cm[2]);
+      lgamma_digamma(cm[0], lg0, d0);
+      lgamma_digamma(cm[1], lg1, d1);
+      lgamma_digamma(cm[0] + cm[1], lgs, ds);
       lg_cm = lgs - lg0 - lg1;
+      dgd_cm[0] = ds - d0; dgd_cm[1] = ds - d1;
       cg[0] = Num<real>::fmax(cm[0], eps);
       cg[1] = Num<real>::fmax(cm[1], eps);
       if (cg[0] == cm[0] && cg[1] == cm[1]) {
         lg_cg = lg_cm;
-        dg_cg[0] = dg_cm[0]; dg_cg[1] = dg_cm[1]; dg_cg[2] = dg_cm[2];
+        dgd_cg[0] = dgd_cm[0]; dgd_cg[1] = dgd_cm[1];
       } else {
-        lgamma_digamma(cg[0], lg0, dg_cg[0]);
-        lgamma_digamma(cg[1], lg1, dg_cg[1]);
-        lgamma_digamma(cg[0] + cg[1], lgs, dg_cg[2]);
+        lgamma_digamma(cg[0], lg0, d0);
+        lgamma_digamma(cg[1], lg1, d1);
+        lgamma_digamma(cg[0] + cg[1], lgs, ds);
         lg_cg = lgs - lg0 - lg1;
+        dgd_cg[0] = ds - d0; dgd_cg[1] = ds - d1;
       }
     }
     // --scale-by-acc: per-guide logit-space noise (utils.py:133-178)
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
     }
     real elbo_g = real(0);
     for (int r = 0; r < R; ++r) {
-      const bool rmask = p.row_mask[(size_t)g * R + r] != 0;
+      const bool rmask = p.row_mask[(size_t)r * p.G + g] != 0;  // replicate-major: a warp reads 32 consecutive bytes
       real pi0 = real(0), pi1 = real(1);
       if (MIXTURE) {
         if (p.pi_in) {
@@ -232,13 +239,21 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         de[b] = real(0);
       }
       for (int l = 0; l < p.L; ++l) {
-        const real* xr = p.x + (((size_t)l * p.G + g) * R + r) * B;
+        // x[l][r][g][b]: the rows of 32 consecutive guides are contiguous, so a warp's loads coalesce; with B = 4 a row
+        // is one 128-bit load
+        const real* xr = p.x + (((size_t)l * R + r) * p.G + g) * B;
         real xb[NB], pb[NB], ab[NB], frac[NB], gb[NB];
         bool live[NB];
         real N = real(0), S = real(0);
+        if (NB == 4 && B == 4) {
+          const typename Vec4<real>::type q = *reinterpret_cast<const typename Vec4<real>::type*>(xr);
+          xb[0] = q.x; xb[1] = q.y; xb[2] = q.z; xb[3] = q.w;
+        } else {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) xb[b] = b < B ? xr[b] : real(0);
+        }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          xb[b] = b < B ? xr[b] : real(0);
           N += xb[b];
           pb[b] = b < B ? e[b] * p.t.sf[l][r * B + b] : real(0);
           S += pb[b];
@@ -288,17 +303,18 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
         go0 -= (cg[0] - real(1)) * ip0;
         go1 -= (cg[1] - real(1)) * ip1;
-        dcg[0] -= dg_cg[2] - dg_cg[0] + lp0;
-        dcg[1] -= dg_cg[2] - dg_cg[1] + lp1;
+        dcg[0] -= dgd_cg[0] + lp0;
+        dcg[1] -= dgd_cg[1] + lp1;
         if (rmask) {
           // model sites under poutine.mask(repguide_mask): Dirichlet prior on pi and Multinomial reporter
           // counts (model.py:454-474); torch Multinomial normalises probs and clamps them to [eps, 1-eps]
           elbo_g += lg_cm + (cm[0] - real(1)) * lp0 + (cm[1] - real(1)) * lp1;
           go0 += (cm[0] - real(1)) * ip0;
           go1 += (cm[1] - real(1)) * ip1;
-          dcm[0] += dg_cm[2] - dg_cm[0] + lp0;
-          dcm[1] += dg_cm[2] - dg_cm[1] + lp1;
-          const real x0 = p.allele_counts[((size_t)g * R + r) * 2], x1 = p.allele_counts[((size_t)g * R + r) * 2 + 1];
+          dcm[0] += dgd_cm[0] + lp0;
+          dcm[1] += dgd_cm[1] + lp1;
+          const typename Vec2<real>::type ac = reinterpret_cast<const typename Vec2<real>::type*>(p.allele_counts)[(size_t)r * p.G + g];
+          const real x0 = ac.x, x1 = ac.y;
           const real Sp = pi0 + pi1, iSp = Num<real>::rcp(Sp), pn0 = pi0 * iSp, pn1 = pi1 * iSp;
           // torch clamps Multinomial probs to [eps, 1 - eps] of THEIR dtype; in the reference pi inherits pi_a0's dtype
           // (float64 out of the fit even on the float32 path): the host passes the eps that applies (BeanSviConfig)
@@ -349,8 +365,12 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
     real dmu = real(0), dsg = real(0);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      dmu += dP[b] * dPm[b];
-      dsg += dP[b] * dPs[b];
+      if (b < B) {
+        real dPm, dPs;
+        bin_mass_grad_sorting(p.t.thr_u[b], p.t.thr_l[b], mu_t, sigma, dPm, dPs);
+        dmu += dP[b] * dPm;
+        dsg += dP[b] * dPs;
+      }
     }
     if (p.sd_is_sqrt) dsg *= real(0.5) / sigma;
     p.d_guide[g] = dmu;

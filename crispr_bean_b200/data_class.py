@@ -143,8 +143,16 @@ class ScreenData:
         self.X_control_masked = self.X_control * self.control_sample_mask[:, :, None]
         self.repguide_mask = ~(self.X == 0).any(axis=1)
         if self.repguide_mask_key is not None:
+            # guides x replicates table, applied by LABEL: the reference asserts that its index equals guides.index and its
+            # columns equal the (sorted) replicate order (data_class.py:167-178) and applies it by position
             tbl = self.screen.uns[self.repguide_mask_key]
             assert tbl.shape == (self.n_guides, R), tbl.shape
+            reps = list(pd.unique(sel.samples[self.replicate_column]))
+            if not (tbl.index.equals(self.screen.guides.index) and list(tbl.columns) == reps):
+                missing = [g for g in self.screen.guides.index if g not in tbl.index][:3] + [r for r in reps if r not in tbl.columns][:3]
+                if missing:
+                    raise ValueError(f"screen.uns[{self.repguide_mask_key!r}] lacks guides / replicates {missing}")
+                tbl = tbl.reindex(index=self.screen.guides.index, columns=reps)
             self.repguide_mask = torch.logical_and(torch.as_tensor(tbl.to_numpy().T) > 0, self.repguide_mask)
         self.size_factor = torch.as_tensor(sel.samples["size_factor"].to_numpy().copy()).reshape(R, B)
         self.size_factor_control = torch.as_tensor(ctl.samples["size_factor"].to_numpy().copy()).reshape(R, C)

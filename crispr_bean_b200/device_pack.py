@@ -1,8 +1,9 @@
-"""Guide-major device records of a tensorised screen + the `BeanScreen` C struct that points at them.
+"""Device records of a tensorised screen + the `BeanScreen` C struct that points at them.
 
 The reference keeps counts as `(R, B, G)` with G fastest (data_class.py:220-228) and permutes views per
-step (model.py:362, :534).  The kernels own whole guides, so the screen is re-tiled ONCE here to
-`x[layer][g][r][b]` (a guide's R*B cells are one contiguous record: 128 B at R=8, B=4, fp32).
+step (model.py:362, :534).  A kernel thread owns a whole guide and walks its replicates, so the screen is re-tiled
+ONCE here to replicate-major rows `x[layer][r][g][b]`: the rows the 32 threads of a warp read for replicate r are
+contiguous (one 128-bit load per thread at B = 4, 512 contiguous bytes per warp).
 """
 from __future__ import annotations
 
@@ -28,7 +29,7 @@ def _dptr(a: np.ndarray):
 
 
 class DeviceScreen:
-    """Device-resident, guide-major copy of the per-step data of a *ScreenData object."""
+    """Device-resident, replicate-major copy of the per-step data of a *ScreenData object."""
 
     def __init__(self, data, device="cuda", dtype=torch.float32, use_bcmatch=True, mask_thres=10):
         self.device = torch.device(device)
@@ -40,11 +41,11 @@ class DeviceScreen:
             layers.append((data.X_bcmatch_masked, data.size_factor_bcmatch, data.a0_bcmatch))
         self.n_guides, self.n_reps, self.n_bins, self.n_layers = G, R, B, len(layers)
         self.mask_thres = int(mask_thres)
-        # (R, B, G) -> (G, R, B), layers stacked in front; uploaded as they are (asynchronously when the host
+        # (R, B, G) -> (R, G, B), layers stacked in front; uploaded as they are (asynchronously when the host
         # tensors are pinned, `data.pin_memory()`) and re-tiled on the device
-        self.x = torch.stack([x.to(self.device, non_blocking=True).permute(2, 0, 1) for x, _, _ in layers]).to(dtype).contiguous()
+        self.x = torch.stack([x.to(self.device, non_blocking=True).permute(0, 2, 1) for x, _, _ in layers]).to(dtype).contiguous()
         self.a0 = torch.stack([torch.as_tensor(a) for _, _, a in layers]).to(device=self.device, dtype=dtype).contiguous()
-        self.row_mask = data.repguide_mask.to(self.device, non_blocking=True).T.to(torch.uint8).contiguous()  # (G, R)
+        self.row_mask = data.repguide_mask.to(self.device, non_blocking=True).to(torch.uint8).contiguous()  # (R, G)
         self._sf = np.ascontiguousarray(torch.stack([torch.as_tensor(s).double() for _, s, _ in layers]).numpy())
         self._smask = np.ascontiguousarray(data.sample_mask.double().numpy())
         if self.mode == _lib.MODE_SORTING:
@@ -58,8 +59,8 @@ class DeviceScreen:
         x64 = self.x.double()
         n64 = x64.sum(-1)
         self.row_const = (torch.lgamma(n64 + 1) - torch.lgamma(x64 + 1).sum(-1)
-                          + torch.xlogy(x64, x64 / n64.clamp(min=1.0).unsqueeze(-1)).sum(-1)).contiguous()  # (L, G, R)
-        self.row_weight = (n64 > self.mask_thres) & (self.row_mask != 0).unsqueeze(0)  # (L, G, R)
+                          + torch.xlogy(x64, x64 / n64.clamp(min=1.0).unsqueeze(-1)).sum(-1)).contiguous()  # (L, R, G)
+        self.row_weight = (n64 > self.mask_thres) & (self.row_mask != 0).unsqueeze(0)  # (L, R, G)
         self.ll_const = float((self.row_const * self.row_weight).sum())
         del x64, n64
         s = _lib.BeanScreen()

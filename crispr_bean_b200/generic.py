@@ -79,7 +79,14 @@ class AutogradSviEngine:
         self.lr0, self.lrd, self.num_steps = float(initial_lr), float(gamma) ** (1.0 / max(num_steps, 1)), int(num_steps)
         self.step = 0
         self.loss = torch.zeros(max(num_steps, 1), dtype=torch.float64, device=self.device)
-        self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
+        # draws of different shards must be independent (a Dirichlet over all guides is assembled from the shards' gammas):
+        # the generator stream is keyed by (seed, rank of this shard)
+        rank = 0
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            rank = dist.get_rank(getattr(self, "group", None))
+        self.gen = torch.Generator(device=self.device).manual_seed(int(seed) + 1_000_003 * rank)
         # device-side step counter and the ClippedAdam step size of every step: a captured step reads
         # step_sizes[t] and writes loss[t], then increments t -- nothing about a step depends on the host
         t = torch.arange(1, max(num_steps, 1) + 1, dtype=torch.float64)
@@ -193,6 +200,7 @@ class AutogradSviEngine:
         registered).  Warm-up steps run for real, so the optimiser state is snapshotted and restored around them."""
         keep = [(t, t.detach().clone()) for t in list(self.theta.values()) + list(self.m.values()) + list(self.v.values())
                 + [self._t, self.loss]]
+        gen_state = self.gen.get_state()  # the warm-up draws must not advance the run's noise stream
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -203,6 +211,7 @@ class AutogradSviEngine:
         torch.cuda.current_stream(self.device).wait_stream(side)
         for p in self.theta.values():
             p.grad = None  # the captured backward allocates the gradients inside the graph's pool
+        self.gen.set_state(gen_state)
         graph = torch.cuda.CUDAGraph()
         graph.register_generator_state(self.gen)
         with torch.cuda.graph(graph):

@@ -18,7 +18,7 @@ _REAL = {torch.float32: "bean_ll_f32", torch.float64: "bean_ll_f64"}
 def launch_ll(screen: DeviceScreen, mu_allele, sd_allele, pi=None, allele_mask=None, want_rows=False):
     """Raw launch.  mu/sd `(G, A)`, pi `(G, R, A)` or None (A == 1).
 
-    Returns dict(ll=0-dim tensor, ll_row=(L,G,R)|None, d_mu, d_sd, d_pi)."""
+    Returns dict(ll=0-dim tensor, ll_row=(L,R,G)|None, d_mu, d_sd, d_pi)."""
     lib = _lib.lib()
     if not mu_allele.is_cuda:
         raise _lib.BeanError("bean_ll needs CUDA tensors: there is no CPU fallback")
@@ -42,7 +42,7 @@ def launch_ll(screen: DeviceScreen, mu_allele, sd_allele, pi=None, allele_mask=N
     if allele_mask is not None:
         allele_mask = allele_mask.to(torch.uint8).contiguous()
         args.allele_mask = allele_mask.data_ptr()
-    ll_row = torch.empty((L, G, R), dtype=dtype, device=dev) if want_rows else None
+    ll_row = torch.empty((L, R, G), dtype=dtype, device=dev) if want_rows else None
     partial = torch.empty((lib.bean_ll_num_partials(G, A),), dtype=torch.float64, device=dev)
     args.ll_row = ll_row.data_ptr() if want_rows else None
     args.ll_partial = partial.data_ptr()

@@ -64,11 +64,11 @@ class SviEngine:
             ac = data.allele_counts_control  # (R, C, G, 2); the model observes condition 0 of the control
             if ac.shape[1] != 1:
                 raise NotImplementedError("more than one control condition")
-            self.allele_counts = ac.to(dev, non_blocking=True)[:, 0].permute(1, 0, 2).to(dtype).contiguous()  # (G, R, 2)
+            self.allele_counts = ac.to(dev, non_blocking=True)[:, 0].to(dtype).contiguous()  # (R, G, 2)
             self.pi_a0 = torch.as_tensor(data.pi_a0).to(**kw).contiguous()
             # data-only part of the Multinomial log-pmf, masked like the site (model.py:455, :470-474)
             a64 = self.allele_counts.double()
-            mconst = torch.lgamma(a64.sum(-1) + 1) - torch.lgamma(a64 + 1).sum(-1)  # (G, R)
+            mconst = torch.lgamma(a64.sum(-1) + 1) - torch.lgamma(a64 + 1).sum(-1)  # (R, G)
             ll_const += float((mconst * (self.screen.row_mask != 0)).sum())
         self.acc = bool(scale_by_accessibility) and self.mixture
         self.fit_noise = bool(fit_noise) and self.acc
@@ -83,7 +83,9 @@ class SviEngine:
             self.noise_grad = torch.zeros((2, G), **kw)
         self.partial = torch.zeros((self.lib.bean_svi_num_partials(G, T),), dtype=torch.float64, device=dev)
         self.counter = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.loss = torch.zeros((max(self.num_steps, 1),), dtype=torch.float64, device=dev)
+        # one spare slot: `gradients()` evaluates a step without updating and writes its loss at index `step`, which is
+        # num_steps after a complete run
+        self.loss = torch.zeros((max(self.num_steps, 1) + 1,), dtype=torch.float64, device=dev)
         self.step = 0
 
         c = _lib.BeanSviConfig()
@@ -184,7 +186,7 @@ class SviEngine:
 
     def run(self, n_steps: int, noise: Optional[Dict[str, torch.Tensor]] = None, apply_update: bool = True):
         """Advance `n_steps` SVI steps (asynchronously); injected `noise` applies to every one of them."""
-        if self.step + n_steps > self.loss.numel():
+        if self.step + n_steps > self.loss.numel() - (1 if apply_update else 0):
             raise ValueError("loss buffer exhausted: construct the engine with a larger num_steps")
         n, keep = self._noise_struct(noise)
         self.cfg.apply_update = 1 if apply_update else 0

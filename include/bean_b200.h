@@ -19,8 +19,10 @@
  *    below are `real*`); count tensors hold integer-valued reals exactly as the reference stores them
  *    (`.float()`, bean/preprocessing/data_class.py:220-228).
  *
- * Layout (device): GUIDE-MAJOR records, re-tiled once at tensorisation from the reference's
- * (R, B, G) tensors:  x[layer][g][r][b],  pi[g][r][a],  allele_counts[g][r][a],  row_mask[g][r].
+ * Layout (device): count rows are REPLICATE-MAJOR, re-tiled once at tensorisation from the reference's
+ * (R, B, G) tensors:  x[layer][r][g][b],  allele_counts[r][g][a],  row_mask[r][g]  -- a kernel thread owns a guide,
+ * so the rows the 32 threads of a warp read for replicate r are contiguous (one 128-bit load per thread at B = 4);
+ * per-guide allele vectors stay guide-major:  pi[g][r][a],  mu_allele[g][a].
  */
 #ifndef BEAN_B200_H_
 #define BEAN_B200_H_
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 7
+#define BEAN_ABI_VERSION 8
 
 enum {
   BEAN_OK = 0,
@@ -65,10 +67,10 @@ typedef struct BeanScreen {
   int32_t n_layers;            /* 1 = guide counts, 2 = + barcode-matched counts (use_bcmatch) */
   int32_t mode;                /* BEAN_MODE_SORTING | BEAN_MODE_SURVIVAL */
   int32_t mask_thres;          /* row kept iff sum_b x > mask_thres (model.py:132-137; 10) */
-  const void* x;               /* real [L][G][R][B]   X_masked / X_bcmatch_masked               */
+  const void* x;               /* real [L][R][G][B]   X_masked / X_bcmatch_masked               */
   const void* a0;              /* real [L][G]         a0 / a0_bcmatch                           */
-  const uint8_t* row_mask;     /* u8   [G][R]         repguide_mask                             */
-  const double* row_const;     /* f64  [L][G][R] or NULL: data-only part of each row's log-pmf,
+  const uint8_t* row_mask;     /* u8   [R][G]         repguide_mask (the reference's own layout)        */
+  const double* row_const;     /* f64  [L][R][G] or NULL: data-only part of each row's log-pmf,
                                   lgamma(N+1) - sum_b lgamma(x_b+1) + sum_{x_b>0} x_b ln(x_b/N)   */
   /* small per-sample tables, HOST pointers (copied into kernel arguments):                      */
   const double* size_factor;   /* [L][R][B]           size_factor / size_factor_bcmatch         */
@@ -90,7 +92,7 @@ typedef struct BeanScreen {
  * in : mu_allele, sd_allele  real [G][A]   per-guide allele mean / sd (sd ignored for survival)
  *      pi                    real [G][R][A] allele weights, or NULL for "all ones" (A must be 1)
  *      allele_mask           u8   [G][A]   or NULL (tiling: 0 = allele does not exist, P := 0)
- * out: ll_row                real [L][G][R] masked per-row log-prob (0 where masked), may be NULL
+ * out: ll_row                real [L][R][G] masked per-row log-prob (0 where masked), may be NULL
  *      ll_partial            double [bean_ll_num_partials(G, A)] per-CTA partial sums of the masked ll
  *      d_mu, d_sd            real [G][A]   d(sum ll)/d(mu_allele, sd_allele)
  *      d_pi                  real [G][R][A] d(sum ll)/d(pi), may be NULL when pi is NULL
@@ -191,7 +193,7 @@ typedef struct BeanSviState {
   int32_t loss_capacity;
   const int32_t* guide_variant;  /* i32 [G]   variant of each guide (guides of a variant contiguous)  */
   const int32_t* variant_ptr;    /* i32 [T+1] CSR: guides of variant v are [ptr[v], ptr[v+1])          */
-  const void* allele_counts;     /* real [G][R][2] control-condition reporter allele counts (MIXTURE)  */
+  const void* allele_counts;     /* real [R][G][2] control-condition reporter allele counts (MIXTURE)  */
   const void* pi_a0;             /* real [G]                                                            */
   void* var_params;              /* real [4][T]: mu_loc, log mu_scale, sd_loc, log sd_scale             */
   void* var_m;                   /* real [4][T] Adam first moments                                      */

@@ -1,0 +1,49 @@
+"""The reference's OWN float32 error, measured per golden case -- the yardstick for the fp32 kernels' tolerances.
+
+north_star asks for 1e-5 relative in fp32.  Some gradients cannot be had to 1e-5 in float32 by ANY implementation that
+follows the reference's formulas (the ControlNormal parameters are a 40x-cancelling sum over all guides; `alpha_pi` goes
+through torch's `_dirichlet_grad`, whose float32 kernel evaluates a twice-cancelling saddle-point expression), and round 1
+simply waived those to 2e-4.  Instead of asserting a waiver, this module MEASURES the floor: the gradients the reference
+itself produced in its native float32 run (`native/grad/*` of tests/golden/ref_*.npz) against a float64 evaluation of the
+same programs on the SAME float32 draws (the CPU oracle, pinned to the reference's float64 run at 1e-11 / 1e-9 by
+tests/test_reference_golden.py).  The fp32 kernels are then held to  max(1e-5, 2 x floor)  against that float64 truth.
+
+Error metric: element-wise relative error, |got - ref| / max(|ref|, MAG * max|ref|) -- entries smaller than MAG of the
+largest entry are compared on the absolute scale MAG * max|ref| (a gradient entry that is itself a rounding residue has
+no meaningful relative error).
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import torch
+
+MAG = 1e-3
+NORTH_STAR_FP32 = 1e-5
+
+
+def elem_rel(got, ref, mag=MAG) -> float:
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    scale = np.maximum(np.abs(ref), mag * np.abs(ref).max()) + 1e-300
+    return float((np.abs(got - ref) / scale).max())
+
+
+@functools.lru_cache(maxsize=None)
+def reference_fp32_floor(name: str):
+    """-> (truth, floor): truth = {"loss": float, "grads": {k: f64 array}} evaluated in float64 on the native run's draws;
+    floor = {"loss": rel err, k: elem_rel} of the reference's own float32 results against it."""
+    from tests.test_reference_golden import edit_perm, group, load_case, oracle_eval, to_ours
+
+    z, data = load_case(name)
+    loss64, grads64, _ = oracle_eval(z, data, "native", torch.float64, name)
+    perm = edit_perm(z, data)
+    floor = {"loss": abs(float(z["native/loss"]) - loss64) / abs(loss64)}
+    for k, g in group(z, "native/grad/").items():
+        floor[k] = elem_rel(to_ours(g, perm, k), grads64[k].reshape(g.shape))
+    return {"loss": loss64, "grads": grads64}, floor
+
+
+def fp32_tolerance(floor: float) -> float:
+    return max(NORTH_STAR_FP32, 2.0 * floor)
