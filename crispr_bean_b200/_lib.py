@@ -116,6 +116,12 @@ class BeanLatentSitesGradArgs(C.Structure):
                 ("grad", C.c_void_p)]
 
 
+class BeanDirichletArgs(C.Structure):
+    _fields_ = [("n_guides", C.c_int32), ("n_reps", C.c_int32), ("n_alleles", C.c_int32), ("site", C.c_uint32),
+                ("conc", C.c_void_p), ("x", C.c_void_p), ("grad_x", C.c_void_p), ("d_conc", C.c_void_p),
+                ("seed", C.c_uint64), ("guide_offset", C.c_uint32), ("step", C.c_void_p), ("step_value", C.c_int64)]
+
+
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
 ABI_VERSION = 8  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -145,6 +151,10 @@ _PROTOTYPES = {
     "bean_latent_sites_grad_f64": (C.c_int, [C.POINTER(BeanLatentSitesGradArgs), C.c_void_p]),
     "bean_clipped_adam_f32": (C.c_int, [C.POINTER(BeanAdamArgs), C.c_void_p]),
     "bean_clipped_adam_f64": (C.c_int, [C.POINTER(BeanAdamArgs), C.c_void_p]),
+    "bean_dirichlet_rsample_f32": (C.c_int, [C.POINTER(BeanDirichletArgs), C.c_void_p]),
+    "bean_dirichlet_rsample_f64": (C.c_int, [C.POINTER(BeanDirichletArgs), C.c_void_p]),
+    "bean_dirichlet_rsample_grad_f32": (C.c_int, [C.POINTER(BeanDirichletArgs), C.c_void_p]),
+    "bean_dirichlet_rsample_grad_f64": (C.c_int, [C.POINTER(BeanDirichletArgs), C.c_void_p]),
     "bean_row_ceiling_f32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

@@ -21,6 +21,7 @@ import torch.distributions as tdist
 from . import _lib
 from ._lib import BeanError
 from .device_pack import DeviceScreen
+from .dirichlet import DirichletStream, dirichlet_rsample
 from .ll_function import count_log_likelihood
 from .latent_sites import LatentPrior, latent_sites
 from .pi_sites import PiSiteData, pi_sites
@@ -28,28 +29,6 @@ from .tiling import AlleleMap, allele_gather
 
 EPS = 1e-5
 PI_NOISE_SD = 0.655
-
-
-class _DirichletRsample(torch.autograd.Function):
-    """Dirichlet.rsample(): value drawn with torch's sampler (or supplied from outside for parity runs);
-    backward = torch's pathwise derivative (`_Dirichlet_backward`), with `torch._dirichlet_grad` evaluated in
-    DOUBLE also on the float path -- the CUDA float kernel loses the saddle-point cancellation (1e-2 errors),
-    the reference's CPU kernel computes in double internally."""
-
-    @staticmethod
-    def forward(ctx, concentration, injected, generator):
-        x = injected.to(concentration.dtype) if injected is not None else torch._sample_dirichlet(concentration.contiguous(), generator)
-        x = x.to(concentration.device)
-        ctx.save_for_backward(x, concentration)
-        return x.clone()
-
-    @staticmethod
-    def backward(ctx, grad_output):
-        x, concentration = ctx.saved_tensors
-        c64 = concentration.double().contiguous()
-        total = c64.sum(-1, True).expand_as(c64).contiguous()
-        grad = torch._dirichlet_grad(x.double().contiguous(), c64, total).to(concentration.dtype)
-        return grad * (grad_output - (x * grad_output).sum(-1, True)), None, None
 
 
 def _multinomial_log_prob(probs, value):
@@ -92,6 +71,8 @@ class AutogradSviEngine:
         t = torch.arange(1, max(num_steps, 1) + 1, dtype=torch.float64)
         self._step_sizes = (self.lr0 * self.lrd ** t * torch.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)).to(self.device)
         self._t = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # the `pi` draws: counter-based, keyed by (seed, global guide id, replicate, allele, device step counter)
+        self.pi_stream = DirichletStream(seed, self._t, guide_offset=getattr(self, "guide_offset", 0), site=0)
         self._graph, self._graph_noise, self.use_graph = None, None, True
         self._const = {}
 
@@ -328,7 +309,7 @@ class TilingSviEngine(AutogradSviEngine):
         conc_m = (alpha_pi + eps / A) / (alpha_pi.sum(-1, keepdim=True) + eps) * self.pi_a0[:, None]
         conc_m = torch.where(conc_m < eps, torch.full_like(conc_m, eps), conc_m)
         injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None  # cast to the concentration's dtype
-        pi = _DirichletRsample.apply(conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1), injected, self.gen)
+        pi = dirichlet_rsample(conc_g, R, self.pi_stream, injected).unsqueeze(1)  # (R, 1, G, A): bean_dirichlet_rsample_*
         # model `pi` Dirichlet + reporter Multinomial - guide `pi` Dirichlet, all under repguide_mask: one kernel
         model_lp = model_lp + pi_sites(conc_g, conc_m, pi, self.pi_data)
 

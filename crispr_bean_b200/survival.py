@@ -24,7 +24,8 @@ import torch
 from ._lib import BeanError
 from .collective import ShardedDirichletRsample, global_sum, sharded_dirichlet_log_prob
 from .device_pack import DeviceScreen
-from .generic import EPS, AutogradSviEngine, _DirichletRsample
+from .dirichlet import dirichlet_rsample
+from .generic import EPS, AutogradSviEngine
 from .latent_sites import LatentPrior, latent_sites
 from .ll_function import count_log_likelihood
 from .pi_sites import PiSiteData, pi_sites
@@ -35,7 +36,7 @@ class SurvivalSviEngine(AutogradSviEngine):
     def __init__(self, data, model: str = "MixtureNormal", device="cuda", dtype=torch.float32, use_bcmatch=True,
                  num_steps=2000, initial_lr=0.01, gamma=0.1, seed=101, alpha_prior=1.0, mask_thres=10,
                  prior_params: Optional[dict] = None, mu_negctrl=(0.0, 0.1), scale_by_accessibility: bool = False,
-                 fit_noise: bool = False, epsilon: float = EPS, group=None):
+                 fit_noise: bool = False, epsilon: float = EPS, group=None, guide_offset: int = 0):
         """`group`: torch.distributed process group over which the guides are sharded (variant blocks, `dist.shard_data`);
         the default (None) is the WORLD group when torch.distributed is initialised, otherwise a single rank.  The
         Dirichlet over all guides is then evaluated with one all-reduce of n_reps numbers per sum (collective.py)."""
@@ -46,6 +47,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         if not getattr(data, "is_survival", False):
             raise ValueError("SurvivalSviEngine needs a *SurvivalScreenData object")
         self.model, self.device, self.dtype = model, torch.device(device), dtype
+        self.guide_offset = int(guide_offset)  # global index of this shard's first guide: the `pi` draws are keyed by global ids
         kw = dict(device=self.device, dtype=dtype)
         use_bcmatch = bool(use_bcmatch) and getattr(data, "X_bcmatch_masked", None) is not None
         self.screen = DeviceScreen(data, self.device, dtype=dtype, use_bcmatch=use_bcmatch, mask_thres=mask_thres)
@@ -156,7 +158,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         pi_a_scaled = alpha_pi / alpha_pi.sum(-1, keepdim=True) * self.pi_a0[:, None]
         conc_g, conc_m = pi_a_scaled.clamp(min=1e-5), pi_a_scaled  # (G, 2)
         injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None
-        pi = _DirichletRsample.apply(conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1), injected, self.gen)
+        pi = dirichlet_rsample(conc_g, R, self.pi_stream, injected).unsqueeze(1)  # (R, 1, G, 2): bean_dirichlet_rsample_*
         # model `pi` + Multinomial(control counts; pi exp(mu t_c)) under repguide_mask, minus the guide's `pi` density
         model_lp = model_lp + pi_sites(conc_g, conc_m, pi, self.pi_data, growth=mu, work_dtype=self.pi_dtype)
         if self.acc:  # survival_model.py:347-351
@@ -182,7 +184,7 @@ class SurvivalSviEngine(AutogradSviEngine):
         conc_m = (alpha_pi + eps / A) / (alpha_pi.sum(-1, keepdim=True) + eps) * self.pi_a0[:, None]
         conc_m = torch.where(conc_m < eps, torch.full_like(conc_m, eps), conc_m)
         injected = noise["pi"].to(self.device) if (noise is not None and "pi" in noise) else None
-        pi = _DirichletRsample.apply(conc_g.unsqueeze(0).unsqueeze(0).expand(R, 1, -1, -1), injected, self.gen)
+        pi = dirichlet_rsample(conc_g, R, self.pi_stream, injected).unsqueeze(1)  # (R, 1, G, A)
         model_lp = model_lp + pi_sites(conc_g, conc_m, pi, self.pi_data, growth=mu, work_dtype=self.pi_dtype)
         if self.acc:
             pi, m_lp, g_lp = self._acc_apply(pi, noise)

@@ -359,6 +359,35 @@ int bean_clipped_adam_f32(const BeanAdamArgs* args, void* stream);
 int bean_clipped_adam_f64(const BeanAdamArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * bean_dirichlet_rsample_{f32,f64} / bean_dirichlet_rsample_grad_{f32,f64}: reparameterised draws of the editing-rate
+ * site `pi` and their pathwise derivative.
+ * Replaces  dist.Dirichlet(concentration).rsample()  in the guides of the programs that run on torch autograd around
+ * bean_ll_* (bean/model/model.py:942-950 MultiMixtureNormalGuide; bean/model/survival_model.py:699-712, :822-833), i.e.
+ * torch._sample_dirichlet forward and torch._dirichlet_grad (`_Dirichlet_backward`) backward:
+ *   forward : x[r][g][:] ~ Dirichlet(conc[g][:])  (gamma draws normalised, clamped to [tiny, 1 - eps/2])
+ *   backward: d_conc[g][a] = sum_r D(x[r][g][a]; conc[g][a], sum_b conc[g][b]) * (grad_x[r][g][a] - sum_b x[r][g][b] grad_x[r][g][b])
+ * Counter-based noise (Philox4x32-10 keyed by `seed`; counter = (guide_offset + g, r | a << 8, step, site)): reproducible,
+ * independent of launch geometry and of how guides are sharded over GPUs.  `step` is a DEVICE pointer (or NULL: then
+ * `step_value` is used), so the launch can be captured in a CUDA graph whose replays advance the step on the device.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BeanDirichletArgs {
+  int32_t n_guides, n_reps, n_alleles;
+  uint32_t site;             /* distinguishes several Dirichlet sites of one program (separate noise streams) */
+  const void* conc;          /* real [G][A] concentrations (> 0) */
+  void* x;                   /* real [R][G][A]: out (forward), in (backward) */
+  const void* grad_x;        /* real [R][G][A] upstream d L / d x (backward only) */
+  void* d_conc;              /* real [G][A] out (backward only) */
+  uint64_t seed;
+  uint32_t guide_offset;     /* global index of this shard's first guide */
+  const int64_t* step;       /* device i64 [1] or NULL */
+  int64_t step_value;
+} BeanDirichletArgs;
+int bean_dirichlet_rsample_f32(const BeanDirichletArgs* args, void* stream);
+int bean_dirichlet_rsample_f64(const BeanDirichletArgs* args, void* stream);
+int bean_dirichlet_rsample_grad_f32(const BeanDirichletArgs* args, void* stream);
+int bean_dirichlet_rsample_grad_f64(const BeanDirichletArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement aid (no reference counterpart): register-only evaluation of the Dirichlet-Multinomial row
  * maths of `n_rows_per_guide` rows of `n_bins` bins for `n_guides` guides -- the empirical FP32/SFU ceiling
  * bench.py quotes next to the HBM roofline.  out: float [ceil(n_guides / 128)] (checksum sink).

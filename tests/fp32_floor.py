@@ -45,5 +45,17 @@ def reference_fp32_floor(name: str):
     return {"loss": loss64, "grads": grads64}, floor
 
 
+# Cases whose float32 draws sit ON the sampler's clamps (pi = float32 tiny / 1 - eps/2: low-depth guides, the 231-allele raw
+# tiling table): there float32 and float64 do not evaluate the same function -- torch's Multinomial clamps probabilities at
+# the eps of their dtype and log(1.17e-38) is representable only because the draw was clamped at float32's tiny -- so a
+# float64 evaluation on the float32 draws is not "the truth" of the float32 run (alpha_pi gradients differ by factors).
+# For these the fp32 kernels are compared with the reference's float32 results directly.
+DTYPE_DEPENDENT = ("mixture_ragged_lowdepth", "tiling_real_mini", "tiling_real_mini_acc")
+
+
+def same_function(name: str) -> bool:
+    return name not in DTYPE_DEPENDENT
+
+
 def fp32_tolerance(floor: float) -> float:
     return max(NORTH_STAR_FP32, 2.0 * floor)
