@@ -42,7 +42,7 @@ class BeanLLArgs(C.Structure):
 class BeanSviConfig(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("sd_is_sqrt", C.c_int32), ("mu_prior_normal", C.c_int32), ("apply_update", C.c_int32),
-        ("phases", C.c_int32), ("fit_noise", C.c_int32),
+        ("phases", C.c_int32), ("fit_noise", C.c_int32), ("force_generic", C.c_int32), ("reserved_", C.c_int32),
         ("mu_prior_loc", C.c_double), ("mu_prior_scale", C.c_double),
         ("sd_prior_loc", C.c_double), ("sd_prior_scale", C.c_double),
         ("lr0", C.c_double), ("lrd", C.c_double),
@@ -122,8 +122,20 @@ class BeanDirichletArgs(C.Structure):
                 ("seed", C.c_uint64), ("guide_offset", C.c_uint32), ("step", C.c_void_p), ("step_value", C.c_int64)]
 
 
+class BeanSurvivalState(C.Structure):
+    _fields_ = [("n_controls", C.c_int32), ("prime", C.c_int32), ("n_guides_total", C.c_int64),
+                ("control_time", C.POINTER(C.c_double)), ("negctrl_loc", C.c_double), ("negctrl_scale", C.c_double),
+                ("log_obs", C.c_void_p), ("q0_u", C.c_void_p), ("q0_m", C.c_void_p), ("q0_v", C.c_void_p), ("q0_grad", C.c_void_p),
+                ("gamma", C.c_void_p * 2), ("sums", C.c_void_p * 2), ("abund_partial", C.c_void_p)]
+
+
+class BeanSurvivalNoise(C.Structure):
+    _fields_ = [("eps_negctrl", C.c_void_p), ("q0", C.c_void_p)]
+
+
+SURV_PRIME_NONE, SURV_PRIME_AND_RUN, SURV_PRIME_ONLY = 0, 1, 2
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 8  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 10  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -142,6 +154,12 @@ _PROTOTYPES = {
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
     "bean_svi_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSviConfig),
                                    C.POINTER(BeanSviNoise), C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_svi_survival_run_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSurvivalState),
+                                            C.POINTER(BeanSviConfig), C.POINTER(BeanSviNoise), C.POINTER(BeanSurvivalNoise),
+                                            C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_svi_survival_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSurvivalState),
+                                            C.POINTER(BeanSviConfig), C.POINTER(BeanSviNoise), C.POINTER(BeanSurvivalNoise),
+                                            C.c_int32, C.c_int32, C.c_void_p]),
     "bean_pi_sites_f32": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
     "bean_pi_sites_f64": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
     "bean_latent_sites_num_partials": (C.c_int, [C.c_int64]),

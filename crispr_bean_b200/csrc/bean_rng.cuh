@@ -159,6 +159,25 @@ __device__ __forceinline__ real beta_grad_alpha_small(real x, real alpha, real b
   return isnan(result) ? real(0) : result;
 }
 
+// double: torch's expression AS WRITTEN (factor + 1 / (alpha + i) with factor = psi(alpha) - psi(alpha + beta) - ln x).  For
+// tiny concentrations (non-existent tiling alleles: ~1e-7) its cancellation costs the reference ~1e-9 of relative accuracy,
+// and fp64 parity means reproducing that number, not the better one.
+template <>
+__device__ __forceinline__ double beta_grad_alpha_small<double>(double x, double alpha, double beta) {
+  const double factor = digamma_f64(alpha) - digamma_f64(alpha + beta) - ::log(x);
+  double numer = 1.0;
+  double series = numer / alpha * (factor + 1.0 / alpha);
+#pragma unroll 1
+  for (int i = 1; i <= 10; ++i) {
+    const double ci = (double)i;
+    numer *= (ci - beta) * x / ci;
+    const double denom = alpha + ci;
+    series += numer / denom * (factor + 1.0 / denom);
+  }
+  const double result = x * ::pow(1.0 - x, -beta) * series;
+  return isnan(result) ? 0.0 : result;
+}
+
 // x near 0, derivative w.r.t. beta (torch: _beta_grad_beta_small)
 template <typename real>
 __device__ __forceinline__ real beta_grad_beta_small(real x, real alpha, real beta) {

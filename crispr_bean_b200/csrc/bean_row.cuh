@@ -50,8 +50,9 @@ __device__ __forceinline__ real dm_row_kl_scalar(int nb, const real (&x)[NB], co
       const real e = fma(a[b], N, -p);
       const real num = fma(x[b], A, -p) - e;
       const real t = num * iu;
-      const real L2 = -log1p_ratio(-t * iA);
-      const real L1 = -log1p_ratio(t * iN);
+      const real Uu = U * iu;
+      const real L2 = -log1p_ratio(-t * iA, a[b] * iA * Uu);  // -ln(a U / (u A))
+      const real L1 = -log1p_ratio(t * iN, x[b] * iN * Uu);   // -ln(x U / (u N)); x = 0: +inf, discarded below
       V += x[b] > real(0) ? fma(x[b], L1, a[b] * L2) : a[b] * L2;
       sumL2 += L2;
       csum += cvu - cva;
@@ -88,7 +89,13 @@ __device__ __forceinline__ float dm_row_kl_packed(int nb, const float (&x)[NB], 
       const float e = fmaf(a[b], N, -p);
       const float num = fmaf(x[b], A, -p) - e;
       const float t = num * iz.y;
-      const float2 L = log1p_ratio2(make_float2(-t * iA, t * iN));  // (-L2, -L1)
+      const float2 y = make_float2(-t * iA, t * iN);
+      float2 L = log1p_ratio_series2(y);  // (-L2, -L1) = (ln(a U / (u A)), ln(x U / (u N)))
+      if (!(log1p_ratio_in_range(y.x) && log1p_ratio_in_range(y.y))) {  // outlier bin: rare, one branch for the pair
+        const float Uu = U * iz.y;
+        if (!log1p_ratio_in_range(y.x)) L.x = log_ftz(a[b] * iA * Uu);
+        if (!log1p_ratio_in_range(y.y)) L.y = log_ftz(x[b] * iN * Uu);  // x = 0: -inf, discarded below
+      }
       const float L2 = -L.x;
       V += x[b] > 0.0f ? fmaf(-x[b], L.y, a[b] * L2) : a[b] * L2;
       sumL2 += L2;

@@ -16,127 +16,33 @@
 //       variant range (no atomics; guides of a variant are contiguous, data_class.py:511-532), prior and
 //       entropy terms, ClippedAdam on (mu_loc, mu_scale, sd_loc, sd_scale), and -- in the last CTA to
 //       finish -- the deterministic reduction of all ELBO partials into loss[t].
-#include "bean_common.cuh"
-#include "bean_math.cuh"
-#include "bean_rng.cuh"
-#include "bean_row.cuh"
+#include "bean_svi_shared.cuh"
 
 namespace bean {
-
-constexpr int SVI_THREADS = 128;
-constexpr int SVI_MIN_CTAS = 4;        // fused guide step: <= 128 registers, 16 warps/SM (more CTAs measured +-2 %)
-#ifndef BEAN_GUIDE_MIN_CTAS
-#define BEAN_GUIDE_MIN_CTAS 8
-#endif
-constexpr int SVI_MIN_CTAS_SPLIT = BEAN_GUIDE_MIN_CTAS;  // split guide step and the Normal models: 64 registers, 32 warps/SM
-                                       // (MixtureNormal 4: 1.17, 6: 1.11, 8: 1.08 ms/step; Normal 4: 0.64, 8: 0.58; final kernel 7: 0.650, 8: 0.640 ms)
-// ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
-// so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
-constexpr int SVI_WARP = 32;
-constexpr int VAR_THREADS = 256;
-constexpr int VAR_LANES = 8;  // lanes cooperating on one variant
-constexpr int VAR_PER_CTA = VAR_THREADS / VAR_LANES;
-
-template <typename real>
-struct SviParams {
-  int G, R, B, L, T;
-  int mixture, sd_is_sqrt, mu_prior_normal, apply_update, fit_noise;
-  uint32_t step, guide_offset, variant_offset;
-  uint64_t seed;
-  real mask_thres;
-  // screen
-  const real* x;
-  const real* a0;
-  const uint8_t* row_mask;
-  const int32_t* guide_variant;
-  const int32_t* variant_ptr;
-  const real* allele_counts;
-  const real* pi_a0;
-  // parameters + Adam state
-  real* var_params;
-  real* var_m;
-  real* var_v;
-  real* alpha_u;
-  real* alpha_m;
-  real* alpha_v;
-  const real* acc_k;
-  real* noise_u;
-  real* noise_m;
-  real* noise_v;
-  real* noise_grad;
-  // scratch / outputs
-  real* d_guide;
-  real* var_grad;
-  real* alpha_grad;
-  real* pw;      // split path: [R][G][4] = (pi0, pi1, w0, w1) of every draw, written by the guide kernel
-  real* dconc;   // split path: [G][4]    = (dcm0, dcm1, dcg0, dcg1) without the pathwise part
-  double* partial;
-  uint32_t* counter;
-  double* loss;
-  int n_partial_guide, n_partial_var;
-  // injected noise (parity runs)
-  const real* eps_mu;
-  const real* eps_sd;
-  const real* pi_in;
-  const real* eps_noise;
-  real* eps_out;
-  real* pi_out;
-  // priors / optimiser scalars of this step
-  real mu_prior_loc, mu_prior_scale, sd_prior_loc, sd_prior_scale;
-  const real* mu_prior_loc_v;
-  const real* mu_prior_scale_v;
-  const real* sd_prior_loc_v;
-  const real* sd_prior_scale_v;
-  real step_size, beta1, beta2, adam_eps, clip, prob_eps;
-  double ll_const;
-  real p_wt[BEAN_MAX_BINS];  // bin masses of the wild-type allele N(0, 1)
-  SampleTables<real> t;
-};
-
-// pyro.optim.ClippedAdam on one unconstrained scalar; step_size carries
-// lr_t * sqrt(1 - beta2^t) / (1 - beta1^t).
-template <typename real>
-__device__ __forceinline__ void clipped_adam(const SviParams<real>& p, real grad, real& theta, real& m, real& v) {
-  const real g = Num<real>::fmin(Num<real>::fmax(grad, -p.clip), p.clip);
-  m = p.beta1 * m + (real(1) - p.beta1) * g;
-  v = p.beta2 * v + (real(1) - p.beta2) * g * g;
-  theta -= p.step_size * m / (Num<real>::sqrt(v) + p.adam_eps);
-}
-
-// reparameterised draw of the variant's (mu, sd) -- recomputed wherever needed instead of stored
-template <typename real>
-__device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, real& mu_t, real& sd_t, real& eps_mu,
-                                             real& eps_sd, real& mu_scale, real& sd_scale, real& log_sd) {
-  const real mu_loc = p.var_params[v];
-  mu_scale = Num<real>::exp(p.var_params[p.T + v]);
-  const real sd_loc = p.var_params[2 * p.T + v];
-  sd_scale = Num<real>::exp(p.var_params[3 * p.T + v]);
-  if (p.eps_mu) {
-    eps_mu = p.eps_mu[v];
-    eps_sd = p.eps_sd[v];
-  } else {
-    float e0, e1;
-    variant_noise(p.seed, (uint32_t)v + p.variant_offset, p.step, e0, e1);
-    eps_mu = real(e0);
-    eps_sd = real(e1);
-  }
-  mu_t = mu_loc + mu_scale * eps_mu;   // Normal(mu_loc, mu_scale).rsample()          model.py:810
-  log_sd = sd_loc + sd_scale * eps_sd;  // LogNormal(sd_loc, sd_scale).rsample()       model.py:811
-  sd_t = Num<real>::exp(log_sd);
-}
 
 // SPLIT: the pathwise Dirichlet derivative and the alpha_pi update run in `svi_alpha_kernel` instead; this kernel hands
 // over every draw with its upstream weights (16 B per replicate) and the rest of the concentration gradient.  Two small
 // instruction footprints instead of one large one (the I-cache is 32 KB per SM), at +0.26 GB of HBM traffic per step.
-template <typename real, int NB, bool MIXTURE, bool ACC, bool SPLIT>
+//
+// FAST: the screen has exactly NB bins and no masked sample (sample_mask all ones: every screen without `bean qc` sample
+// drops).  The bin loops then carry no `b < B` predicates, the per-sample size factors come from a shared-memory table as
+// one 128-bit load per row instead of NB constant-bank loads with computed addresses, and the sample-mask multiplies are
+// gone -- together a third of the instructions of the get_alpha section (profiles/r2b_guide_source_top.txt: that section,
+// not the special functions, was the largest single block of the kernel after the round-2 instruction diet).
+template <typename real, int NB, bool MIXTURE, bool ACC, bool SPLIT, bool FAST>
 __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(real) == 4) ? SVI_MIN_CTAS_SPLIT : SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
   __shared__ TailQueue<real> tail_queues[SPLIT ? 1 : SVI_THREADS / SVI_WARP];
+  __shared__ __align__(16) real s_sf[FAST ? BEAN_MAX_LAYERS * BEAN_MAX_RB : 1];  // [l][r][b] size factors
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
-  const int R = p.R, B = p.B;
+  const int R = p.R, B = FAST ? NB : p.B;
   const real eps = real(1e-5);
   double elbo = 0.0;
   const int lane = threadIdx.x & 31;
   const unsigned wmask = __ballot_sync(0xffffffffu, g < p.G);  // lanes that own a guide: the warp-collective set below
+  if (FAST) {
+    for (int i = threadIdx.x; i < p.L * R * NB; i += SVI_THREADS) s_sf[i] = p.t.sf[i / (R * NB)][i % (R * NB)];
+    __syncthreads();
+  }
   if (g < p.G) {
     TailQueue<real>& tq = tail_queues[SPLIT ? 0 : threadIdx.x / SVI_WARP];
     int n_tail = 0;
@@ -147,10 +53,13 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
     // bin masses of the edited allele now; their (mu, sd) derivatives are recomputed in the epilogue (two exp per bin)
     // instead of being carried through the replicate loop in 2 NB registers
     real P1[NB], dP[NB];
+    {
+      BinMasses<real> bm(mu_t, sigma);
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      P1[b] = dP[b] = real(0);
-      if (b < B) P1[b] = bin_mass_sorting(p.t.thr_u[b], p.t.thr_l[b], mu_t, sigma);
+      for (int b = 0; b < NB; ++b) {
+        P1[b] = dP[b] = real(0);
+        if (b < B) P1[b] = bm.next(p.t.thr_u[b], p.t.thr_l[b], b > 0 && p.t.thr_l[b] == p.t.thr_u[b > 0 ? b - 1 : 0]);
+      }
     }
     // editing-rate concentrations (model.py:449 / :835): model = alpha/sum*pi_a0, guide = clamp(model, 1e-5)
     real al[2] = {real(1), real(1)}, cm[2] = {real(1), real(1)}, cg[2] = {real(1), real(1)};
@@ -242,7 +151,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         // x[l][r][g][b]: the rows of 32 consecutive guides are contiguous, so a warp's loads coalesce; with B = 4 a row
         // is one 128-bit load
         const real* xr = p.x + (((size_t)l * R + r) * p.G + g) * B;
-        real xb[NB], pb[NB], ab[NB], frac[NB], gb[NB];
+        real xb[NB], sfb[NB], smb[NB], pb[NB], ab[NB], frac[NB], gb[NB];
         bool live[NB];
         real N = real(0), S = real(0);
         if (NB == 4 && B == 4) {
@@ -252,10 +161,18 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
 #pragma unroll
           for (int b = 0; b < NB; ++b) xb[b] = b < B ? xr[b] : real(0);
         }
+        if (FAST && NB == 4) {
+          const typename Vec4<real>::type q = reinterpret_cast<const typename Vec4<real>::type*>(s_sf)[l * R + r];
+          sfb[0] = q.x; sfb[1] = q.y; sfb[2] = q.z; sfb[3] = q.w;
+        } else {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) sfb[b] = FAST ? s_sf[(l * R + r) * NB + b] : (b < B ? p.t.sf[l][r * B + b] : real(0));
+        }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
+          smb[b] = FAST ? real(1) : (b < B ? p.t.smask[r * B + b] : real(0));
           N += xb[b];
-          pb[b] = b < B ? e[b] * p.t.sf[l][r * B + b] : real(0);
+          pb[b] = e[b] * sfb[b];
           S += pb[b];
         }
         if (!(rmask && N > p.mask_thres)) continue;  // poutine.mask: the row contributes nothing
@@ -265,7 +182,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           frac[b] = (pb[b] + eps / real(B)) * inv;  // utils.py:19-23
-          const real raw = frac[b] * a0 * p.t.smask[r * B + b];
+          const real raw = FAST ? frac[b] * a0 : frac[b] * a0 * smb[b];
           live[b] = raw >= eps;
           ab[b] = (b < B) ? (live[b] ? raw : eps) : real(0);
           Asum += ab[b];
@@ -274,13 +191,13 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         real dot = real(0);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          gb[b] = (b < B && live[b]) ? gb[b] * p.t.smask[r * B + b] : real(0);
+          gb[b] = (b < B && live[b]) ? (FAST ? gb[b] : gb[b] * smb[b]) : real(0);
           dot += gb[b] * frac[b];
         }
         const real c = a0 * inv;
 #pragma unroll
         for (int b = 0; b < NB; ++b)
-          if (b < B) de[b] += p.t.sf[l][r * B + b] * c * (gb[b] - dot);
+          if (b < B) de[b] += sfb[b] * c * (gb[b] - dot);
       }
       if (MIXTURE) {
         // d ELBO / d pi from the likelihood
@@ -297,22 +214,33 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
           go1 = gq * dq1_dpi1;
           go0 = real(0);
         }
-        const real lp0 = Num<real>::log(pi0), lp1 = Num<real>::log(pi1);
-        const real ip0 = Num<real>::rcp(pi0), ip1 = Num<real>::rcp(pi1);
-        // guide site: -log Dirichlet(pi; cg), unmasked (model.py:837-847)
-        elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
-        go0 -= (cg[0] - real(1)) * ip0;
-        go1 -= (cg[1] - real(1)) * ip1;
-        dcg[0] -= dgd_cg[0] + lp0;
-        dcg[1] -= dgd_cg[1] + lp1;
+        // The two Dirichlet sites on pi -- the guide's, unmasked, with concentration cg = clamp(cm, 1e-5) (model.py:837-847),
+        // and the model's prior under poutine.mask(repguide_mask) with cm (model.py:454-463) -- are accumulated as their
+        // DIFFERENCE: for an unclamped guide inside the mask (nearly all) they cancel identically, value and gradients, so
+        // nothing is computed and no rounding residue of two large equal terms reaches the alpha_pi gradient.
+        const bool same_conc = cg[0] == cm[0] && cg[1] == cm[1];
+        real lp0 = real(0), lp1 = real(0);
+        if (!(rmask && same_conc)) {
+          lp0 = Num<real>::log(pi0);
+          lp1 = Num<real>::log(pi1);
+          const real ip0 = Num<real>::rcp(pi0), ip1 = Num<real>::rcp(pi1);
+          // guide site: -log Dirichlet(pi; cg)
+          elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
+          go0 -= (cg[0] - real(1)) * ip0;
+          go1 -= (cg[1] - real(1)) * ip1;
+          dcg[0] -= dgd_cg[0] + lp0;
+          dcg[1] -= dgd_cg[1] + lp1;
+          if (rmask) {  // model site (clamped guide: the two concentrations differ)
+            elbo_g += lg_cm + (cm[0] - real(1)) * lp0 + (cm[1] - real(1)) * lp1;
+            go0 += (cm[0] - real(1)) * ip0;
+            go1 += (cm[1] - real(1)) * ip1;
+            dcm[0] += dgd_cm[0] + lp0;
+            dcm[1] += dgd_cm[1] + lp1;
+          }
+        }
         if (rmask) {
-          // model sites under poutine.mask(repguide_mask): Dirichlet prior on pi and Multinomial reporter
-          // counts (model.py:454-474); torch Multinomial normalises probs and clamps them to [eps, 1-eps]
-          elbo_g += lg_cm + (cm[0] - real(1)) * lp0 + (cm[1] - real(1)) * lp1;
-          go0 += (cm[0] - real(1)) * ip0;
-          go1 += (cm[1] - real(1)) * ip1;
-          dcm[0] += dgd_cm[0] + lp0;
-          dcm[1] += dgd_cm[1] + lp1;
+          // Multinomial reporter counts under the mask (model.py:464-474); torch Multinomial normalises probs and clamps
+          // them to [eps, 1-eps]
           const typename Vec2<real>::type ac = reinterpret_cast<const typename Vec2<real>::type*>(p.allele_counts)[(size_t)r * p.G + g];
           const real x0 = ac.x, x1 = ac.y;
           const real Sp = pi0 + pi1, iSp = Num<real>::rcp(Sp), pn0 = pi0 * iSp, pn1 = pi1 * iSp;
@@ -320,11 +248,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
           // (float64 out of the fit even on the float32 path): the host passes the eps that applies (BeanSviConfig)
           const real lo = p.prob_eps, hi = real(1) - p.prob_eps;
           const real c0 = Num<real>::fmin(Num<real>::fmax(pn0, lo), hi), c1 = Num<real>::fmin(Num<real>::fmax(pn1, lo), hi);
-          // log(pi_a / Sp) = log pi_a - log1p(Sp - 1): Sp = 1 up to rounding of the draw, so two of the replicate's four
-          // accurate logs are saved; a clamped probability (never, for float draws, with the float64 eps) takes the log itself
-          const real ds = Sp - real(1), lSp = ds - real(0.5) * ds * ds;
-          const real l0 = (c0 == pn0 && Num<real>::fabs(ds) < real(1e-3)) ? lp0 - lSp : Num<real>::log(c0);
-          const real l1 = (c1 == pn1 && Num<real>::fabs(ds) < real(1e-3)) ? lp1 - lSp : Num<real>::log(c1);
+          const real l0 = log_unit(c0), l1 = log_unit(c1);
           elbo_g += x0 * l0 + x1 * l1;
           const real h0 = (pn0 >= lo && pn0 <= hi) ? Num<real>::div(x0, c0) : real(0), h1 = (pn1 >= lo && pn1 <= hi) ? Num<real>::div(x1, c1) : real(0);
           const real hbar = h0 * pn0 + h1 * pn1;
@@ -431,187 +355,21 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
   if ((threadIdx.x & 31) == 0) p.partial[(blockIdx.x * SVI_THREADS + threadIdx.x) / SVI_WARP] = tot;
 }
 
-// concentration gradients -> log alpha_pi gradient -> ClippedAdam (alpha_pi is per guide)
-template <typename real>
-__device__ __forceinline__ void alpha_update(const SviParams<real>& p, int g, real al0, real al1, real pa0, real cm0, real cm1,
-                                             real dcm0, real dcm1, real dcg0, real dcg1) {
-  const real eps = real(1e-5);
-  const real asum = al0 + al1;
-  // clamp(min) passes the gradient where its input >= 1e-5
-  const real dC0 = dcm0 + (cm0 >= eps ? dcg0 : real(0));
-  const real dC1 = dcm1 + (cm1 >= eps ? dcg1 : real(0));
-  const real k = pa0 / (asum * asum);
-  const real dal0 = k * (dC0 * (asum - al0) - dC1 * al1);
-  const real dal1 = k * (dC1 * (asum - al1) - dC0 * al0);
-  const real gl0 = -dal0 * al0, gl1 = -dal1 * al1;  // loss = -ELBO, unconstrained (log) space
-  if (p.alpha_grad) {
-    p.alpha_grad[2 * (size_t)g] = gl0;
-    p.alpha_grad[2 * (size_t)g + 1] = gl1;
-  }
-  if (p.apply_update) {
-    real th0 = p.alpha_u[2 * (size_t)g], th1 = p.alpha_u[2 * (size_t)g + 1];
-    real m0 = p.alpha_m[2 * (size_t)g], m1 = p.alpha_m[2 * (size_t)g + 1];
-    real v0 = p.alpha_v[2 * (size_t)g], v1 = p.alpha_v[2 * (size_t)g + 1];
-    clipped_adam(p, gl0, th0, m0, v0);
-    clipped_adam(p, gl1, th1, m1, v1);
-    p.alpha_u[2 * (size_t)g] = th0; p.alpha_u[2 * (size_t)g + 1] = th1;
-    p.alpha_m[2 * (size_t)g] = m0;  p.alpha_m[2 * (size_t)g + 1] = m1;
-    p.alpha_v[2 * (size_t)g] = v0;  p.alpha_v[2 * (size_t)g + 1] = v1;
-  }
-}
-
-template <typename real> struct SaddleOf;
-template <> struct SaddleOf<float> { typedef SaddlePairF type; };
-template <> struct SaddleOf<double> { typedef SaddlePair type; };
-
-// Second half of the split guide step: pathwise Dirichlet derivative of every draw (saddle-point pairs in place, the other
-// regimes through the per-warp queue), alpha_pi gradient and its ClippedAdam update.  One thread per guide.
-constexpr int ALPHA_THREADS = 128;
-template <typename real>
-__global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviParams<real> p) {
-  __shared__ TailQueue<real> tail_queues[ALPHA_THREADS / SVI_WARP];
-  const int g = blockIdx.x * ALPHA_THREADS + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const real eps = real(1e-5);
-  const unsigned wmask = __ballot_sync(0xffffffffu, g < p.G);
-  if (g >= p.G) return;
-  TailQueue<real>& tq = tail_queues[threadIdx.x / SVI_WARP];
-  const real al0 = Num<real>::exp(p.alpha_u[2 * (size_t)g]), al1 = Num<real>::exp(p.alpha_u[2 * (size_t)g + 1]);
-  const real asum = al0 + al1, pa0 = p.pi_a0[g];
-  const real cm0 = al0 / asum * pa0, cm1 = al1 / asum * pa0;
-  const real cg0 = Num<real>::fmax(cm0, eps), cg1 = Num<real>::fmax(cm1, eps);
-  const typename Vec4<real>::type dc = reinterpret_cast<const typename Vec4<real>::type*>(p.dconc)[g];
-  real dcg0 = dc.z, dcg1 = dc.w;
-  int n_tail = 0;
-  // saddle-point regime: float kernels use the cancellation-free single-precision form, double kernels torch's expression
-  typename SaddleOf<real>::type sp;
-  sp.init(cg0, cg1);
-  const typename Vec4<real>::type* pw = reinterpret_cast<const typename Vec4<real>::type*>(p.pw) + g;
-  typename Vec4<real>::type nxt = pw[0];
-  for (int r = 0; r < p.R; ++r) {
-    const typename Vec4<real>::type rec = nxt;
-    if (r + 1 < p.R) nxt = pw[(size_t)(r + 1) * p.G];  // the next draw's record is in flight while this one is evaluated
-    const bool saddle = dirichlet_pair_is_saddle((double)rec.x, (double)rec.y, (double)cg0, (double)cg1);
-    if (saddle) {
-      real dg0, dg1;
-      sp.eval(rec.x, rec.y, dg0, dg1);
-      dcg0 += dg0 * rec.z;
-      dcg1 += dg1 * rec.w;
-    }
-    n_tail = tail_queue_push(tq, n_tail, wmask, lane, !saddle, rec.x, rec.y, cg0, cg1, rec.z, rec.w);
-    if (n_tail >= 32) {
-      tail_queue_flush(tq, n_tail, wmask, lane, dcg0, dcg1);
-      n_tail = 0;
-    }
-  }
-  if (n_tail > 0) tail_queue_flush(tq, n_tail, wmask, lane, dcg0, dcg1);
-  alpha_update(p, g, al0, al1, pa0, cm0, cm1, dc.x, dc.y, dcg0, dcg1);
-}
-
-template <typename real>
-__global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParams<real> p) {
-  __shared__ double red[32];
-  __shared__ bool is_last;
-  const int v = blockIdx.x * VAR_PER_CTA + threadIdx.x / VAR_LANES;
-  const int sub = threadIdx.x % VAR_LANES;
-  const bool valid = v < p.T;
-  // segmented reduction of the guide gradients over the variant's contiguous guide range
-  real dmu = real(0), dsd = real(0);
-  if (valid) {
-    const int beg = p.variant_ptr[v], end = p.variant_ptr[v + 1];
-    for (int j = beg + sub; j < end; j += VAR_LANES) {
-      dmu += p.d_guide[j];
-      dsd += p.d_guide[(size_t)p.G + j];
-    }
-  }
-#pragma unroll
-  for (int o = VAR_LANES / 2; o > 0; o >>= 1) {
-    dmu += __shfl_xor_sync(0xffffffffu, dmu, o);
-    dsd += __shfl_xor_sync(0xffffffffu, dsd, o);
-  }
-  double elbo = 0.0;
-  if (valid && sub == 0) {
-    real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y;
-    variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y);
-    if (p.eps_out) {
-      p.eps_out[v] = e_mu;
-      p.eps_out[p.T + v] = e_sd;
-    }
-    const real HL2PI = real(0.91893853320467274178);
-    // model priors (model.py:41-65 / :405-428; ControlNormal :178-179)
-    real lp_mu, dlp_mu;
-    if (p.mu_prior_normal) {
-      const real loc = p.mu_prior_loc_v ? p.mu_prior_loc_v[v] : p.mu_prior_loc;
-      const real scale = p.mu_prior_scale_v ? p.mu_prior_scale_v[v] : p.mu_prior_scale;
-      const real z = (mu_t - loc) / scale;
-      lp_mu = -Num<real>::log(scale) - HL2PI - real(0.5) * z * z;
-      dlp_mu = -z / scale;
-    } else {  // Laplace(0, 1)
-      lp_mu = -real(0.69314718055994530942) - (mu_t < real(0) ? -mu_t : mu_t);
-      dlp_mu = mu_t > real(0) ? real(-1) : (mu_t < real(0) ? real(1) : real(0));
-    }
-    const real sloc = p.sd_prior_loc_v ? p.sd_prior_loc_v[v] : p.sd_prior_loc;
-    const real sscale = p.sd_prior_scale_v ? p.sd_prior_scale_v[v] : p.sd_prior_scale;
-    const real zs = (y - sloc) / sscale;
-    const real lp_sd = -y - Num<real>::log(sscale) - HL2PI - real(0.5) * zs * zs;
-    const real dlp_sd = (-real(1) - zs / sscale) / sd_t;
-    // guide densities (entropy side)
-    const real lq_mu = -Num<real>::log(mu_scale) - HL2PI - real(0.5) * e_mu * e_mu;
-    const real lq_sd = -y - Num<real>::log(sd_scale) - HL2PI - real(0.5) * e_sd * e_sd;
-    elbo = (double)lp_mu + (double)lp_sd - (double)lq_mu - (double)lq_sd;
-    const real dE_mu = dmu + dlp_mu;
-    const real dE_sd = dsd + dlp_sd;
-    // gradient of the LOSS (-ELBO) w.r.t. the unconstrained parameters
-    real grad[4];
-    grad[0] = -dE_mu;
-    grad[1] = -(dE_mu * e_mu * mu_scale + real(1));
-    grad[2] = -(dE_sd * sd_t + real(1));
-    grad[3] = -((dE_sd * sd_t * e_sd + e_sd) * sd_scale + real(1));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t i = (size_t)k * p.T + v;
-      if (p.var_grad) p.var_grad[i] = grad[k];
-      if (p.apply_update) {
-        real th = p.var_params[i], m = p.var_m[i], vv = p.var_v[i];
-        clipped_adam(p, grad[k], th, m, vv);
-        p.var_params[i] = th;
-        p.var_m[i] = m;
-        p.var_v[i] = vv;
-      }
-    }
-  }
-  const double tot = block_sum(elbo, red);
-  if (threadIdx.x == 0) {
-    p.partial[p.n_partial_guide + blockIdx.x] = tot;
-    __threadfence();
-    const uint32_t done = atomicAdd(p.counter, 1u);
-    is_last = (done == (uint32_t)gridDim.x - 1u);
-  }
-  __syncthreads();
-  if (is_last) {
-    // last CTA: fixed-order reduction of every partial of this step -> loss[t] = -ELBO
-    __threadfence();
-    double acc = 0.0;
-    const int n = p.n_partial_guide + p.n_partial_var;
-    for (int i = threadIdx.x; i < n; i += VAR_THREADS) acc += p.partial[i];
-    const double all = block_sum(acc, red);
-    if (threadIdx.x == 0) {
-      p.loss[p.step] = -(all + p.ll_const);
-      *p.counter = 0u;
-    }
-  }
-}
-
 template <typename real, bool MIXTURE, bool ACC, bool SPLIT>
-static void launch_guide(const SviParams<real>& p, cudaStream_t st, bool guide, bool alpha) {
+static void launch_guide(const SviParams<real>& p, cudaStream_t st, bool guide, bool alpha, bool fast) {
   const int grid = (p.G + SVI_THREADS - 1) / SVI_THREADS;
+  constexpr bool HAS_FAST = SPLIT || !MIXTURE;  // the fused (non-split) mixture step is the legacy path: generic only
   if (!guide) {
-  } else if (p.B <= 4)
-    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT><<<grid, SVI_THREADS, 0, st>>>(p);
+  } else if (HAS_FAST && fast && p.B == 4)
+    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, HAS_FAST><<<grid, SVI_THREADS, 0, st>>>(p);
+  else if (HAS_FAST && fast && p.B == 5)
+    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, HAS_FAST><<<grid, SVI_THREADS, 0, st>>>(p);
+  else if (p.B <= 4)
+    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, false><<<grid, SVI_THREADS, 0, st>>>(p);
   else if (p.B == 5)
-    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, false><<<grid, SVI_THREADS, 0, st>>>(p);
   else
-    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC, SPLIT><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC, SPLIT, false><<<grid, SVI_THREADS, 0, st>>>(p);
   // (one thread per (guide, replicate) with a shuffle reduction was tried for this kernel: 0.42 vs 0.27 ms)
   if (MIXTURE && SPLIT && alpha) svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
 }
@@ -667,6 +425,8 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.noise_v = static_cast<real*>(state->noise_v);
   p.noise_grad = static_cast<real*>(state->noise_grad);
   p.fit_noise = cfg->fit_noise;
+  p.has_sd = 1;
+  p.sums_next = nullptr; p.abund_partial = nullptr; p.n_abund_partial = 0;
   p.d_guide = static_cast<real*>(state->d_guide);
   p.var_grad = static_cast<real*>(state->var_grad);
   p.alpha_grad = static_cast<real*>(state->alpha_grad);
@@ -704,6 +464,9 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
     p.p_wt[b] = real(m);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // FAST kernels: exactly 4 or 5 bins and no masked sample
+  bool fast = (s->n_bins == 4 || s->n_bins == 5) && !cfg->force_generic;
+  for (int i = 0; i < s->n_reps * s->n_bins; ++i) fast = fast && s->sample_mask[i] == 1.0;
   for (int i = 0; i < n_steps; ++i) {
     const int t = first_step + i;  // 0-based step; ClippedAdam's state["step"] = t + 1
     p.step = (uint32_t)t;
@@ -715,9 +478,9 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
     const bool do_guide = ph & 1, do_alpha = ph & 4;
     if (do_guide || do_alpha) {
       const bool split = mix && p.pw != nullptr && p.dconc != nullptr;
-      if (mix && p.acc_k) { if (split) launch_guide<real, true, true, true>(p, st, do_guide, do_alpha); else launch_guide<real, true, true, false>(p, st, do_guide, false); }
-      else if (mix) { if (split) launch_guide<real, true, false, true>(p, st, do_guide, do_alpha); else launch_guide<real, true, false, false>(p, st, do_guide, false); }
-      else launch_guide<real, false, false, false>(p, st, do_guide, false);
+      if (mix && p.acc_k) { if (split) launch_guide<real, true, true, true>(p, st, do_guide, do_alpha, fast); else launch_guide<real, true, true, false>(p, st, do_guide, false, fast); }
+      else if (mix) { if (split) launch_guide<real, true, false, true>(p, st, do_guide, do_alpha, fast); else launch_guide<real, true, false, false>(p, st, do_guide, false, fast); }
+      else launch_guide<real, false, false, false>(p, st, do_guide, false, fast);
     }
     if (ph & 2) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
   }

@@ -1,0 +1,315 @@
+// bean_svi_shared.cuh -- what the fused SVI steps of the sorting (bean_svi.cu) and survival (bean_svi_survival.cu) programs share:
+// the kernel argument block, ClippedAdam, the variant draw, the alpha_pi kernel (pathwise Dirichlet derivative + update) and
+// the per-variant kernel (segmented reduction, prior / entropy terms, update, loss).
+#pragma once
+#include "bean_common.cuh"
+#include "bean_math.cuh"
+#include "bean_rng.cuh"
+#include "bean_row.cuh"
+
+#define BEAN_SURV_MAX_CTRL 4
+
+namespace bean {
+
+constexpr int SVI_THREADS = 128;
+constexpr int SVI_MIN_CTAS = 4;        // fused guide step: <= 128 registers, 16 warps/SM (more CTAs measured +-2 %)
+#ifndef BEAN_GUIDE_MIN_CTAS
+#define BEAN_GUIDE_MIN_CTAS 8
+#endif
+constexpr int SVI_MIN_CTAS_SPLIT = BEAN_GUIDE_MIN_CTAS;  // split guide step and the Normal models: 64 registers, 32 warps/SM
+                                       // (MixtureNormal 4: 1.17, 6: 1.11, 8: 1.08 ms/step; Normal 4: 0.64, 8: 0.58; final kernel 7: 0.650, 8: 0.640 ms)
+// ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
+// so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
+constexpr int SVI_WARP = 32;
+constexpr int VAR_THREADS = 256;
+constexpr int VAR_LANES = 8;  // lanes cooperating on one variant
+constexpr int VAR_PER_CTA = VAR_THREADS / VAR_LANES;
+
+template <typename real>
+struct SviParams {
+  int G, R, B, L, T;
+  int mixture, sd_is_sqrt, mu_prior_normal, apply_update, fit_noise;
+  uint32_t step, guide_offset, variant_offset;
+  uint64_t seed;
+  real mask_thres;
+  // screen
+  const real* x;
+  const real* a0;
+  const uint8_t* row_mask;
+  const int32_t* guide_variant;
+  const int32_t* variant_ptr;
+  const real* allele_counts;
+  const real* pi_a0;
+  // parameters + Adam state
+  real* var_params;
+  real* var_m;
+  real* var_v;
+  real* alpha_u;
+  real* alpha_m;
+  real* alpha_v;
+  const real* acc_k;
+  real* noise_u;
+  real* noise_m;
+  real* noise_v;
+  real* noise_grad;
+  // scratch / outputs
+  real* d_guide;
+  real* var_grad;
+  real* alpha_grad;
+  real* pw;      // split path: [R][G][4] = (pi0, pi1, w0, w1) of every draw, written by the guide kernel
+  real* dconc;   // split path: [G][4]    = (dcm0, dcm1, dcg0, dcg1) without the pathwise part
+  double* partial;
+  uint32_t* counter;
+  double* loss;
+  int n_partial_guide, n_partial_var;
+  // injected noise (parity runs)
+  const real* eps_mu;
+  const real* eps_sd;
+  const real* pi_in;
+  const real* eps_noise;
+  real* eps_out;
+  real* pi_out;
+  // priors / optimiser scalars of this step
+  real mu_prior_loc, mu_prior_scale, sd_prior_loc, sd_prior_scale;
+  const real* mu_prior_loc_v;
+  const real* mu_prior_scale_v;
+  const real* sd_prior_loc_v;
+  const real* sd_prior_scale_v;
+  real step_size, beta1, beta2, adam_eps, clip, prob_eps;
+  double ll_const;
+  real p_wt[BEAN_MAX_BINS];  // bin masses of the wild-type allele N(0, 1)
+  SampleTables<real> t;
+  // ---- survival MixtureNormal step (bean_svi_survival.cu); has_sd = 0 there (no sd_targets site) ----
+  int has_sd;
+  int n_ctrl;                           // control conditions of the reporter Multinomial
+  real t_ctrl[BEAN_SURV_MAX_CTRL];      // their (normalised) timepoints
+  real negctrl_loc, negctrl_scale;      // mu_negctrl ~ Normal(loc, scale): parameter-free prior draw per guide
+  double n_guides_total;                // guides of ALL shards (the abundance Dirichlet spans the whole library)
+  const real* log_obs;                  // [R][G] log of the observed initial abundance
+  real* q0_u; real* q0_m; real* q0_v; real* q0_grad;   // [G] log q0 + Adam state (+ gradient out)
+  const real* gamma_cur;                // [R][G] unnormalised gamma draws of THIS step's abundance sample
+  real* gamma_next;                     // [R][G] ... of the next step's (drawn after the q0 update)
+  const double* sums_cur;               // [R + 1] sum_g gamma[r][g] (r < R), sum_g q0[g]
+  double* sums_next;
+  double* abund_partial;                // [warps][R + 1] per-warp partial sums behind sums_next
+  int n_abund_partial;
+  const real* eps_negctrl;              // injected noise (parity runs)
+  const real* q0_in;                    // [R][G] injected abundance draw (already normalised)
+};
+
+// pyro.optim.ClippedAdam on one unconstrained scalar; step_size carries
+// lr_t * sqrt(1 - beta2^t) / (1 - beta1^t).
+template <typename real>
+__device__ __forceinline__ void clipped_adam(const SviParams<real>& p, real grad, real& theta, real& m, real& v) {
+  const real g = Num<real>::fmin(Num<real>::fmax(grad, -p.clip), p.clip);
+  m = p.beta1 * m + (real(1) - p.beta1) * g;
+  v = p.beta2 * v + (real(1) - p.beta2) * g * g;
+  theta -= p.step_size * m / (Num<real>::sqrt(v) + p.adam_eps);
+}
+
+// reparameterised draw of the variant's (mu, sd) -- recomputed wherever needed instead of stored
+template <typename real>
+__device__ __forceinline__ void variant_draw(const SviParams<real>& p, int v, real& mu_t, real& sd_t, real& eps_mu,
+                                             real& eps_sd, real& mu_scale, real& sd_scale, real& log_sd) {
+  const real mu_loc = p.var_params[v];
+  mu_scale = Num<real>::exp(p.var_params[p.T + v]);
+  const real sd_loc = p.var_params[2 * p.T + v];
+  sd_scale = Num<real>::exp(p.var_params[3 * p.T + v]);
+  if (p.eps_mu) {
+    eps_mu = p.eps_mu[v];
+    eps_sd = p.eps_sd ? p.eps_sd[v] : real(0);
+  } else {
+    float e0, e1;
+    variant_noise(p.seed, (uint32_t)v + p.variant_offset, p.step, e0, e1);
+    eps_mu = real(e0);
+    eps_sd = real(e1);
+  }
+  mu_t = mu_loc + mu_scale * eps_mu;   // Normal(mu_loc, mu_scale).rsample()          model.py:810
+  log_sd = sd_loc + sd_scale * eps_sd;  // LogNormal(sd_loc, sd_scale).rsample()       model.py:811
+  sd_t = Num<real>::exp(log_sd);
+}
+
+// concentration gradients -> log alpha_pi gradient -> ClippedAdam (alpha_pi is per guide)
+template <typename real>
+__device__ __forceinline__ void alpha_update(const SviParams<real>& p, int g, real al0, real al1, real pa0, real cm0, real cm1,
+                                             real dcm0, real dcm1, real dcg0, real dcg1) {
+  const real eps = real(1e-5);
+  const real asum = al0 + al1;
+  // clamp(min) passes the gradient where its input >= 1e-5
+  const real dC0 = dcm0 + (cm0 >= eps ? dcg0 : real(0));
+  const real dC1 = dcm1 + (cm1 >= eps ? dcg1 : real(0));
+  const real k = pa0 / (asum * asum);
+  const real dal0 = k * (dC0 * (asum - al0) - dC1 * al1);
+  const real dal1 = k * (dC1 * (asum - al1) - dC0 * al0);
+  const real gl0 = -dal0 * al0, gl1 = -dal1 * al1;  // loss = -ELBO, unconstrained (log) space
+  if (p.alpha_grad) {
+    p.alpha_grad[2 * (size_t)g] = gl0;
+    p.alpha_grad[2 * (size_t)g + 1] = gl1;
+  }
+  if (p.apply_update) {
+    real th0 = p.alpha_u[2 * (size_t)g], th1 = p.alpha_u[2 * (size_t)g + 1];
+    real m0 = p.alpha_m[2 * (size_t)g], m1 = p.alpha_m[2 * (size_t)g + 1];
+    real v0 = p.alpha_v[2 * (size_t)g], v1 = p.alpha_v[2 * (size_t)g + 1];
+    clipped_adam(p, gl0, th0, m0, v0);
+    clipped_adam(p, gl1, th1, m1, v1);
+    p.alpha_u[2 * (size_t)g] = th0; p.alpha_u[2 * (size_t)g + 1] = th1;
+    p.alpha_m[2 * (size_t)g] = m0;  p.alpha_m[2 * (size_t)g + 1] = m1;
+    p.alpha_v[2 * (size_t)g] = v0;  p.alpha_v[2 * (size_t)g + 1] = v1;
+  }
+}
+
+template <typename real> struct SaddleOf;
+template <> struct SaddleOf<float> { typedef SaddlePairF type; };
+template <> struct SaddleOf<double> { typedef SaddlePair type; };
+
+// Second half of the split guide step: pathwise Dirichlet derivative of every draw (saddle-point pairs in place, the other
+// regimes through the per-warp queue), alpha_pi gradient and its ClippedAdam update.  One thread per guide.
+constexpr int ALPHA_THREADS = 128;
+template <typename real>
+__global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviParams<real> p) {
+  __shared__ TailQueue<real> tail_queues[ALPHA_THREADS / SVI_WARP];
+  const int g = blockIdx.x * ALPHA_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const real eps = real(1e-5);
+  const unsigned wmask = __ballot_sync(0xffffffffu, g < p.G);
+  if (g >= p.G) return;
+  TailQueue<real>& tq = tail_queues[threadIdx.x / SVI_WARP];
+  const real al0 = Num<real>::exp(p.alpha_u[2 * (size_t)g]), al1 = Num<real>::exp(p.alpha_u[2 * (size_t)g + 1]);
+  const real asum = al0 + al1, pa0 = p.pi_a0[g];
+  const real cm0 = al0 / asum * pa0, cm1 = al1 / asum * pa0;
+  const real cg0 = Num<real>::fmax(cm0, eps), cg1 = Num<real>::fmax(cm1, eps);
+  const typename Vec4<real>::type dc = reinterpret_cast<const typename Vec4<real>::type*>(p.dconc)[g];
+  real dcg0 = dc.z, dcg1 = dc.w;
+  int n_tail = 0;
+  // saddle-point regime: float kernels use the cancellation-free single-precision form, double kernels torch's expression
+  typename SaddleOf<real>::type sp;
+  sp.init(cg0, cg1);
+  const typename Vec4<real>::type* pw = reinterpret_cast<const typename Vec4<real>::type*>(p.pw) + g;
+  typename Vec4<real>::type nxt = pw[0];
+  for (int r = 0; r < p.R; ++r) {
+    const typename Vec4<real>::type rec = nxt;
+    if (r + 1 < p.R) nxt = pw[(size_t)(r + 1) * p.G];  // the next draw's record is in flight while this one is evaluated
+    const bool saddle = dirichlet_pair_is_saddle((double)rec.x, (double)rec.y, (double)cg0, (double)cg1);
+    if (saddle) {
+      real dg0, dg1;
+      sp.eval(rec.x, rec.y, dg0, dg1);
+      dcg0 += dg0 * rec.z;
+      dcg1 += dg1 * rec.w;
+    }
+    n_tail = tail_queue_push(tq, n_tail, wmask, lane, !saddle, rec.x, rec.y, cg0, cg1, rec.z, rec.w);
+    if (n_tail >= 32) {
+      tail_queue_flush(tq, n_tail, wmask, lane, dcg0, dcg1);
+      n_tail = 0;
+    }
+  }
+  if (n_tail > 0) tail_queue_flush(tq, n_tail, wmask, lane, dcg0, dcg1);
+  alpha_update(p, g, al0, al1, pa0, cm0, cm1, dc.x, dc.y, dcg0, dcg1);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParams<real> p) {
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  const int v = blockIdx.x * VAR_PER_CTA + threadIdx.x / VAR_LANES;
+  const int sub = threadIdx.x % VAR_LANES;
+  const bool valid = v < p.T;
+  // segmented reduction of the guide gradients over the variant's contiguous guide range
+  real dmu = real(0), dsd = real(0);
+  if (valid) {
+    const int beg = p.variant_ptr[v], end = p.variant_ptr[v + 1];
+    for (int j = beg + sub; j < end; j += VAR_LANES) {
+      dmu += p.d_guide[j];
+      if (p.has_sd) dsd += p.d_guide[(size_t)p.G + j];
+    }
+  }
+#pragma unroll
+  for (int o = VAR_LANES / 2; o > 0; o >>= 1) {
+    dmu += __shfl_xor_sync(0xffffffffu, dmu, o);
+    dsd += __shfl_xor_sync(0xffffffffu, dsd, o);
+  }
+  double elbo = 0.0;
+  if (valid && sub == 0) {
+    real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y;
+    variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y);
+    if (p.eps_out) {
+      p.eps_out[v] = e_mu;
+      p.eps_out[p.T + v] = e_sd;
+    }
+    const real HL2PI = real(0.91893853320467274178);
+    // model priors (model.py:41-65 / :405-428; ControlNormal :178-179)
+    real lp_mu, dlp_mu;
+    if (p.mu_prior_normal) {
+      const real loc = p.mu_prior_loc_v ? p.mu_prior_loc_v[v] : p.mu_prior_loc;
+      const real scale = p.mu_prior_scale_v ? p.mu_prior_scale_v[v] : p.mu_prior_scale;
+      const real z = (mu_t - loc) / scale;
+      lp_mu = -Num<real>::log(scale) - HL2PI - real(0.5) * z * z;
+      dlp_mu = -z / scale;
+    } else {  // Laplace(0, 1)
+      lp_mu = -real(0.69314718055994530942) - (mu_t < real(0) ? -mu_t : mu_t);
+      dlp_mu = mu_t > real(0) ? real(-1) : (mu_t < real(0) ? real(1) : real(0));
+    }
+    const real sloc = p.sd_prior_loc_v ? p.sd_prior_loc_v[v] : p.sd_prior_loc;
+    const real sscale = p.sd_prior_scale_v ? p.sd_prior_scale_v[v] : p.sd_prior_scale;
+    const real zs = (y - sloc) / sscale;
+    const real lp_sd = -y - Num<real>::log(sscale) - HL2PI - real(0.5) * zs * zs;
+    const real dlp_sd = (-real(1) - zs / sscale) / sd_t;
+    // guide densities (entropy side)
+    const real lq_mu = -Num<real>::log(mu_scale) - HL2PI - real(0.5) * e_mu * e_mu;
+    const real lq_sd = -y - Num<real>::log(sd_scale) - HL2PI - real(0.5) * e_sd * e_sd;
+    elbo = (double)lp_mu - (double)lq_mu + (p.has_sd ? (double)lp_sd - (double)lq_sd : 0.0);
+    const real dE_mu = dmu + dlp_mu;
+    const real dE_sd = dsd + dlp_sd;
+    // gradient of the LOSS (-ELBO) w.r.t. the unconstrained parameters
+    real grad[4];
+    grad[0] = -dE_mu;
+    grad[1] = -(dE_mu * e_mu * mu_scale + real(1));
+    grad[2] = -(dE_sd * sd_t + real(1));
+    grad[3] = -((dE_sd * sd_t * e_sd + e_sd) * sd_scale + real(1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k >= 2 && !p.has_sd) break;
+      const size_t i = (size_t)k * p.T + v;
+      if (p.var_grad) p.var_grad[i] = grad[k];
+      if (p.apply_update) {
+        real th = p.var_params[i], m = p.var_m[i], vv = p.var_v[i];
+        clipped_adam(p, grad[k], th, m, vv);
+        p.var_params[i] = th;
+        p.var_m[i] = m;
+        p.var_v[i] = vv;
+      }
+    }
+  }
+  const double tot = block_sum(elbo, red);
+  if (threadIdx.x == 0) {
+    p.partial[p.n_partial_guide + blockIdx.x] = tot;
+    __threadfence();
+    const uint32_t done = atomicAdd(p.counter, 1u);
+    is_last = (done == (uint32_t)gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (is_last) {
+    // last CTA: fixed-order reduction of every partial of this step -> loss[t] = -ELBO
+    __threadfence();
+    double acc = 0.0;
+    const int n = p.n_partial_guide + p.n_partial_var;
+    for (int i = threadIdx.x; i < n; i += VAR_THREADS) acc += p.partial[i];
+    const double all = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      p.loss[p.step] = -(all + p.ll_const);
+      *p.counter = 0u;
+    }
+    // survival: the library-wide sums of the NEXT step's abundance draw (sum_g gamma[r][g], sum_g q0[g]) from the per-warp
+    // partials the guide kernel left; fixed order.  With guides sharded over GPUs the host all-reduces these R + 1 numbers.
+    if (p.sums_next) {
+      for (int j = 0; j <= p.R; ++j) {
+        double a = 0.0;
+        for (int i = threadIdx.x; i < p.n_abund_partial; i += VAR_THREADS) a += p.abund_partial[(size_t)i * (p.R + 1) + j];
+        const double tot_j = block_sum(a, red);
+        if (threadIdx.x == 0) p.sums_next[j] = tot_j;
+      }
+    }
+  }
+}
+
+
+}  // namespace bean

@@ -41,6 +41,13 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
                          fit_noise=bool(gkw.get("fit_noise", False)))
         if name == "MultiMixtureNormal":
             extra["epsilon"] = float(mkw.get("epsilon", 1e-5))
+        if name == "MixtureNormal" and not extra["scale_by_accessibility"]:
+            from .survival_fused import SurvivalFusedEngine  # the whole step as three CUDA kernels
+
+            return SurvivalFusedEngine(data, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps,
+                                       initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
+                                       mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"),
+                                       mu_negctrl=mkw["mu_negctrl"])
         return SurvivalSviEngine(data, name, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps,
                                  initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
                                  mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"), **extra)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 8
+#define BEAN_ABI_VERSION 10
 
 enum {
   BEAN_OK = 0,
@@ -175,6 +175,9 @@ typedef struct BeanSviConfig {
                                (split guide step only) -- so a benchmark can time each kernel with CUDA events */
   int32_t fit_noise;        /* --scale-by-acc only: 1 = guide Normal(noise_loc, noise_scale) on logit_pi_noise
                                (utils.py:145-155), 0 = drawn from the prior Normal(0, 0.655)           */
+  int32_t force_generic;    /* 1: never pick the specialised kernels (exactly 4 / 5 bins, no masked sample); tests use it
+                               to check that both code paths give the same numbers                      */
+  int32_t reserved_;
   double mu_prior_loc, mu_prior_scale;
   double sd_prior_loc, sd_prior_scale; /* LogNormal prior on sd_targets: (0, 0.01); ControlNormal (0, 1) */
   double lr0, lrd;          /* ClippedAdam: lr_t = lr0 * lrd^t, lrd = gamma^(1/num_steps) (run.py:367) */
@@ -239,6 +242,51 @@ int bean_svi_run_f32(const BeanScreen* screen, const BeanSviState* state, const 
                      const BeanSviNoise* noise, int32_t first_step, int32_t n_steps, void* stream);
 int bean_svi_run_f64(const BeanScreen* screen, const BeanSviState* state, const BeanSviConfig* cfg,
                      const BeanSviNoise* noise, int32_t first_step, int32_t n_steps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bean_svi_survival_run_{f32,f64}: n_steps complete SVI steps of the SURVIVAL MixtureNormal program on the device.
+ *
+ * One step = `svi.step(data)` (bean/model/run.py:376-380) for bean/model/survival_model.py:215-424 (MixtureNormalModel) and
+ * :651-739 (MixtureNormalGuide): guide draws (`initial_abundance` ~ Dirichlet(q0) over ALL guides per replicate, `mu_targets`,
+ * `pi`), the model-only latent `mu_negctrl`, exp(mu t) allele masses, allele mixture, get_alpha + Dirichlet-Multinomial
+ * sites of the count layers, the observed `initial_abundance` Dirichlet, `pi` Dirichlet and `control_allele_count`
+ * Multinomial on pi exp(mu t_c), Trace_ELBO loss and gradient, ClippedAdam.  Three launches per step: a per-guide kernel,
+ * the alpha_pi kernel and the per-variant kernel of bean_svi_run_* (BeanSviState is shared: var_params rows 2, 3 -- the
+ * sd site -- are unused, d_guide is [G]).  The screen must be in BEAN_MODE_SURVIVAL.
+ *
+ * The Dirichlet over all guides needs, per replicate, sum_g gamma[r][g] of the gamma draws and sum_g q0[g]: `sums`.  They
+ * are produced on the device (per-warp partials by the guide kernel of the step before, reduced by the last CTA of the
+ * per-variant kernel).  With guides SHARDED over GPUs these R + 1 doubles are the one exchange step of the path: call with
+ * n_steps = 1 and all-reduce `sums[(t + 1) & 1]` between steps (prime = BEAN_SURV_PRIME_ONLY first, all-reduce
+ * `sums[t & 1]`, then prime = BEAN_SURV_PRIME_NONE).
+ * ---------------------------------------------------------------------------------------------- */
+enum { BEAN_SURV_PRIME_NONE = 0, BEAN_SURV_PRIME_AND_RUN = 1, BEAN_SURV_PRIME_ONLY = 2 };
+typedef struct BeanSurvivalState {
+  int32_t n_controls;            /* C: control conditions of the reporter Multinomial (BeanSviState.allele_counts is [R][C][G][2]) */
+  int32_t prime;                 /* BEAN_SURV_PRIME_*: draw the abundance gammas of `first_step` from the current q0 first
+                                    (first call of a run, or after q0 was changed from outside) */
+  int64_t n_guides_total;        /* guides of ALL shards (0 = n_guides) */
+  const double* control_time;    /* HOST double [C]: normalised timepoints of the control conditions */
+  double negctrl_loc, negctrl_scale; /* mu_negctrl ~ Normal(loc, scale) (cli/run.py:258-268; default (0, 0.1)) */
+  const void* log_obs;           /* real [R][G] log((X[r][0][g] + 1) / sum over ALL guides) (survival_model.py:306-311) */
+  void* q0_u;                    /* real [G] log q0 */
+  void* q0_m;
+  void* q0_v;
+  void* q0_grad;                 /* real [G] out or NULL */
+  void* gamma[2];                /* real [R][G] x 2: unnormalised abundance draws of even / odd steps */
+  double* sums[2];               /* f64 [R + 1] x 2: sum_g gamma[r][g] (r < R), sum_g q0[g] */
+  double* abund_partial;         /* f64 [ceil(G / 128) * 4][R + 1] scratch */
+} BeanSurvivalState;
+typedef struct BeanSurvivalNoise { /* optional injected noise of the survival-only sites (parity runs) */
+  const void* eps_negctrl;       /* real [G] standard-normal draw behind mu_negctrl */
+  const void* q0;                /* real [R][G] the guide's abundance draw (on the simplex over all guides) */
+} BeanSurvivalNoise;
+int bean_svi_survival_run_f32(const BeanScreen* screen, const BeanSviState* state, const BeanSurvivalState* survival,
+                              const BeanSviConfig* cfg, const BeanSviNoise* noise, const BeanSurvivalNoise* survival_noise,
+                              int32_t first_step, int32_t n_steps, void* stream);
+int bean_svi_survival_run_f64(const BeanScreen* screen, const BeanSviState* state, const BeanSurvivalState* survival,
+                              const BeanSviConfig* cfg, const BeanSviNoise* noise, const BeanSurvivalNoise* survival_noise,
+                              int32_t first_step, int32_t n_steps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Editing-rate sites of the MultiMixtureNormal (tiling) and survival MixtureNormal programs: forward value and local

@@ -6,9 +6,9 @@
 #   gpurun_out/prof_TAG_alpha.ncu-rep  the same for svi_alpha_kernel
 TAG=${1:-r1}
 set -x
-python bench.py --steps 3 --warmup 3 --burn-in 0 --no-cpu-baseline > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || exit 1
+python bench.py --steps 3 --warmup 3 --burn-in 0 --no-cpu-baseline --full-run-steps 0 > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 3 --warmup 3 --burn-in 0 --no-cpu-baseline > gpurun_out/ncu1_$TAG.log 2>&1
+    python bench.py --steps 3 --warmup 3 --burn-in 0 --no-cpu-baseline --full-run-steps 0 > gpurun_out/ncu1_$TAG.log 2>&1
 python profiles/steady_state.py 600 > gpurun_out/steady_$TAG.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:svi_guide_kernel -s 500 -c 1 -f -o gpurun_out/prof_${TAG}_guide \
     python profiles/steady_state.py 600 > gpurun_out/ncu2_$TAG.log 2>&1

@@ -23,8 +23,11 @@ def _stream(dev, seed=5, step=0, offset=0, site=0):
 def test_draws_have_beta_marginals(cuda_device, dtype, A):
     g = torch.Generator().manual_seed(A)
     G, R = 6000, 4
-    # concentrations across the sampler's regimes: boosted (< 1), moderate, large
-    conc = torch.exp(torch.empty((G, A)).uniform_(np.log(0.05), np.log(60.0), generator=g)).to(dtype)
+    # concentrations across the sampler's regimes: boosted (< 1), moderate, large.  float32 draws are clamped to
+    # [1.2e-38, 1 - 6e-8] like torch's: with concentrations below ~0.3 a visible share of the mass sits beyond those clamps
+    # (atoms in the transform), so the float32 case starts at 0.3
+    lo_c = 0.05 if dtype == torch.float64 else 0.3
+    conc = torch.exp(torch.empty((G, A)).uniform_(np.log(lo_c), np.log(60.0), generator=g)).to(dtype)
     x = dirichlet_rsample(conc.to(cuda_device), R, _stream(cuda_device)).cpu().double()
     assert x.shape == (R, G, A)
     assert torch.allclose(x.sum(-1), torch.ones(R, G, dtype=torch.float64), atol=1e-5 if dtype == torch.float32 else 1e-12)
@@ -35,7 +38,8 @@ def test_draws_have_beta_marginals(cuda_device, dtype, A):
     for lo, hi in ((0.05, 0.5), (0.5, 1.0), (1.0, 6.0), (6.0, 60.0)):
         sel = ((c >= lo) & (c < hi)).numpy()[None].repeat(R, 0)
         ub = u[sel]
-        assert ub.size > 2000
+        if ub.size < 2000:
+            continue
         # KS critical value at alpha = 0.01 is 1.63 / sqrt(n); the draws of one row are weakly dependent (they share the row
         # sum), hence the slack
         assert stats.kstest(ub, "uniform").statistic < 1.5 * 1.63 / np.sqrt(ub.size), (A, lo, hi)
@@ -68,8 +72,10 @@ def test_backward_is_torchs_dirichlet_backward(cuda_device, dtype, tol, A):
     out = dirichlet_rsample(c, R, _stream(cuda_device), injected=x.to(dtype))
     out.backward(gout.to(cuda_device, dtype))
     got = c.grad.double().cpu()
-    err = ((got - ref).abs() / (ref.abs() + ref.abs().mean())).max().item()
-    assert err <= tol, err
+    err = ((got - ref).abs() / (ref.abs() + ref.abs().mean()))
+    i = int(err.argmax())
+    assert err.max().item() <= tol, (err.max().item(), got.reshape(-1)[i].item(), ref.reshape(-1)[i].item(), conc.reshape(-1)[i].item(),
+                                     conc[i // A].sum().item(), x[:, i // A, i % A].tolist())
 
 
 def test_capturable_and_step_read_from_device(cuda_device):

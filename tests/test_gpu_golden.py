@@ -24,7 +24,7 @@ def rel(got, ref):
     return float((np.abs(got - ref) / (np.abs(ref) + np.abs(ref).mean() + 1e-300)).max())
 
 
-def make_engine(z, data, cuda_device, dtype, num_steps):
+def make_engine(z, data, cuda_device, dtype, num_steps, autograd_engine=False):
     kw = oracle_kwargs(z)
     model = str(z["meta/oracle_model"])
     acc = dict(scale_by_accessibility=kw.get("scale_by_accessibility", False), fit_noise=kw.get("fit_noise", False))
@@ -32,6 +32,10 @@ def make_engine(z, data, cuda_device, dtype, num_steps):
         from crispr_bean_b200.survival import SurvivalSviEngine
 
         extra = acc if model in ("MixtureNormal", "MultiMixtureNormal") else {}
+        if model == "MixtureNormal" and not acc["scale_by_accessibility"] and not autograd_engine:
+            from crispr_bean_b200.survival_fused import SurvivalFusedEngine  # what run_inference uses: the fused three-kernel step
+
+            return SurvivalFusedEngine(data, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True))
         return SurvivalSviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True), **extra)
     if getattr(data, "sample_covariates", None) is not None:
         from crispr_bean_b200.generic import CovariateNormalEngine

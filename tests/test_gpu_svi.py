@@ -331,3 +331,23 @@ def test_sampler_distribution_probability_integral_transform(cuda_device):
         assert abs(got - expect) <= 4 * np.sqrt(var) + 2, (thr, got, expect)
     eps = eng.eps_used.double().cpu().numpy().reshape(-1)
     assert stats.kstest(eps, "norm").statistic < 0.02
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("bulk_bin", [True, False])
+def test_specialised_and_generic_guide_kernels_agree(cuda_device, dtype, bulk_bin):
+    """Screens with exactly 4 / 5 bins and no masked sample run the specialised guide kernel (no bin predicates, size factors
+    from shared memory, no sample-mask multiplies); `force_generic` sends the same screen through the generic one.  The two
+    differ only by multiplications with 1.0 and by where constants are read from: same losses, same parameters."""
+    data = H.make_small_mixture_data(n_variants=60, n_reps=4, seed=23, with_bulk_bin=bulk_bin)
+    assert data.n_condits == (5 if bulk_bin else 4) and bool((data.sample_mask == 1).all())
+    runs = []
+    for generic in (0, 1):
+        eng = SviEngine(data, "MixtureNormal", cuda_device, dtype=dtype, num_steps=10, seed=3)
+        eng.cfg.force_generic = generic
+        eng.run(6)
+        runs.append((eng.losses(), {k: v.cpu() for k, v in eng.params().items()}))
+    tol = 1e-12 if dtype == torch.float64 else 1e-6
+    torch.testing.assert_close(runs[0][0], runs[1][0], rtol=tol, atol=0)
+    for k, v in runs[0][1].items():
+        torch.testing.assert_close(v, runs[1][1][k], rtol=tol * 10, atol=tol * 1e-2)
