@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(DIR_THREADS) dirichlet_rsample_kernel(const Di
 }
 
 // d L / d conc[g][a] = sum_r D(x_ra; c_a, C) (gout_ra - sum_b x_rb gout_rb),  D = torch._dirichlet_grad  (torch:
-// _Dirichlet_backward).  The saddle-point regime is evaluated in double also on the float path, like torch's CPU kernel.
+// _Dirichlet_backward).  Evaluated in double also on the float path, like torch's CPU kernel (accscalar_t = double).
 template <typename real, int W>
 __global__ void __launch_bounds__(DIR_THREADS) dirichlet_rsample_grad_kernel(const DirichletParams<real> p) {
   const int tid = blockIdx.x * DIR_THREADS + threadIdx.x;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(DIR_THREADS) dirichlet_rsample_grad_kernel(con
     dot = group_sum<W>(dot, mask);
     for (int a = sub; a < p.A; a += W) {
       const double c = (double)p.conc[(size_t)g * p.A + a];
-      const double D = dirichlet_grad_any<sizeof(real) == 4>((double)p.x[row + a], c, total - c);
+      const double D = dirichlet_grad_one_f64((double)p.x[row + a], c, total);  // double also on the float path (not a hot kernel)
       p.d_conc[(size_t)g * p.A + a] += real(D * ((double)p.grad_x[row + a] - dot));
     }
   }

@@ -246,6 +246,42 @@ __device__ __forceinline__ real beta_grad_alpha_mid(real x, real alpha, real bet
   return stirling * (-x * rs) * term1234;
 }
 
+// double: torch's expression AS WRITTEN (ATen/native/Distributions.h: _beta_grad_alpha_mid).  Its two leading terms cancel
+// from O((x - mean)^-2) to O(1), so a regrouped evaluation -- though algebraically identical -- differs from torch's number at
+// the 1e-9 level for large total concentrations (many-allele tiling guides); fp64 parity means the same rounding.
+template <>
+__device__ __forceinline__ double beta_grad_alpha_mid<double>(double x, double alpha, double beta) {
+  const double total = alpha + beta;
+  const double mean = alpha / total;
+  const double sd = ::sqrt(alpha * beta / (total + 1.0)) / total;
+  if (mean - 0.1 * sd <= x && x <= mean + 0.1 * sd) {
+    const double poly = 47.0 * x * (beta * beta) * (beta * beta) +
+                        alpha * ((43.0 + 20.0 * (16.0 + 27.0 * beta) * x) * (beta * beta) * beta +
+                                 alpha * (3.0 * (59.0 + 180.0 * beta - 90.0 * x) * (beta * beta) +
+                                          alpha * ((453.0 + 1620.0 * beta * (1.0 - x) - 455.0 * x) * beta +
+                                                   alpha * (8.0 * (1.0 - x) * (135.0 * beta - 11.0)))));
+    const double prefactor_num = (1.0 + 12.0 * alpha) * (1.0 + 12.0 * beta) / (total * total);
+    const double prefactor_den = 12960.0 * alpha * alpha * alpha * beta * beta * (1.0 + 12.0 * total);
+    return prefactor_num / (1.0 - x) * poly / prefactor_den;
+  }
+  const double prefactor = -x / ::sqrt(2.0 * alpha * beta / total);
+  const double stirling = (1.0 + 1.0 / (12.0 * alpha) + 1.0 / (288.0 * alpha * alpha)) *
+                          (1.0 + 1.0 / (12.0 * beta) + 1.0 / (288.0 * beta * beta)) /
+                          (1.0 + 1.0 / (12.0 * total) + 1.0 / (288.0 * total * total));
+  const double term1_num = 2.0 * (alpha * alpha) * (x - 1.0) + alpha * beta * (x - 1.0) - x * (beta * beta);
+  const double axbx = alpha * (x - 1.0) + beta * x;
+  const double term1_den = ::sqrt(2.0 * alpha / beta) * ::pow(total, 1.5) * axbx * axbx;
+  const double term1 = term1_num / term1_den;
+  const double term2 = 0.5 * ::log(alpha / (total * x));
+  const double term3_num = ::sqrt(8.0 * alpha * beta / total);
+  const double term3_den = beta * x + alpha * (x - 1.0);
+  const double term3 = term3_num / term3_den;
+  const double term4_base = beta * ::log(beta / (total * (1.0 - x))) + alpha * ::log(alpha / (total * x));
+  const double term4 = ::pow(term4_base, -1.5);
+  const double term1234 = term1 + term2 * (term3 + (x < mean ? term4 : -term4));
+  return prefactor * stirling * term1234;
+}
+
 // -(d/dalpha cdf(x; alpha, total - alpha)) / pdf / (1 - x): what torch._dirichlet_grad evaluates per element.
 template <typename real>
 __device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real total) {
@@ -421,8 +457,8 @@ struct SaddlePair {
 // ---- the saddle-point regime in FLOAT ------------------------------------------------------------------------------
 // torch's expression cancels twice: term1 against term2 * term4 at O(delta^-2), and what is left against the rest of
 // term1 at O(delta^-1) (delta = x - mean).  Both cancellations are removed analytically here, so single precision is
-// enough (worst 3e-5 relative against torch's double evaluation over alpha, beta in [6.5, 3000], |z| in [0.1, 6];
-// typically 1e-6 -- the fp32 path's budget for this gradient is 2e-4).  With m = alpha / T, u = delta / m,
+// enough (worst 9e-7 relative against torch's double evaluation over alpha, beta in [6.2, 5000], |z| in [0.1, 8],
+// tests/test_saddle_float_form.py -- given delta itself to 1e-7, see eval()).  With m = alpha / T, u = delta / m,
 // v = -delta / (1 - m):
 //   log(m / x) = -u l(u),                      l(y) = log1p(y) / y           = 1 + l1(y)
 //   T KL(m || x) = T delta^2 / (2 m (1 - m)) G,  G = (1 - m) g(u) + m g(v),  g(y) = 2 (y - log1p(y)) / y^2 = 1 + g1(y)
@@ -473,7 +509,12 @@ struct SaddlePairF {
     c1b = h * (2.0f * b - a);
   }
   __device__ __forceinline__ void eval(float x0, float x1, float& g0, float& g1) const {
-    const float d = x0 - m;
+    // delta = x0 - a / T.  Formed as x0 - m it inherits the rounding of m: 6e-8 m, which for a lopsided pair (m ~ 1, std
+    // ~ 1e-3) is 1e-4 of delta -- and the result is linear in delta (this was the whole 3e-5 worst case of round 1).
+    // Instead delta = (x0 b - (1 - x0) a) / T with error-free products and the exact split 1 - x0 = hi + lo: ~1e-7 relative.
+    const float hi = 1.0f - x0, lo = (1.0f - hi) - x0;
+    const float pa = hi * a, ea = fmaf(hi, a, -pa);
+    const float d = fmaf(-lo, a, fmaf(x0, b, -pa) - ea) * iT;
     if (d * d <= lim_w) {  // |x - mean| <= 0.1 std: torch's polynomial (all terms positive for beta > 6: float is fine)
       g0 = beta_grad_mid_near_mean(x0, a, b, iT);
       g1 = beta_grad_mid_near_mean(x1, b, a, iT);

@@ -21,7 +21,9 @@ FUSED_MODELS = ("Normal", "ControlNormal", "MixtureNormal")
 
 
 def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, device="cuda", dtype=torch.float32,
-                seed=101):
+                seed=101, guide_offset=0, variant_offset=0):
+    """The device-resident SVI engine of a (model, guide) pair.  `guide_offset` / `variant_offset`: global index of the first
+    guide / variant of `data` when it is one shard of a larger screen (the noise counters use global ids)."""
     name, mkw = resolve(model)
     gname, gkw = resolve(guide)
     if name != gname:
@@ -47,10 +49,11 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
             return SurvivalFusedEngine(data, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps,
                                        initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
                                        mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"),
-                                       mu_negctrl=mkw["mu_negctrl"])
+                                       mu_negctrl=mkw["mu_negctrl"], guide_offset=guide_offset, variant_offset=variant_offset)
         return SurvivalSviEngine(data, name, device=device, dtype=dtype, use_bcmatch=use_bcmatch, num_steps=num_steps,
                                  initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
-                                 mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"), **extra)
+                                 mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"),
+                                 guide_offset=guide_offset, **extra)
     if name == "MultiMixtureNormal":
         from .generic import TilingSviEngine
 
@@ -78,12 +81,41 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
         mask_thres=int(mkw.get("mask_thres", 10)), prior_params=mkw.get("prior_params"),
         scale_by_accessibility=bool(mkw.get("scale_by_accessibility", False)),
         # only the GUIDE's fit_noise matters: the model is never given it
-        fit_noise=bool(gkw.get("fit_noise", False)))
+        fit_noise=bool(gkw.get("fit_noise", False)), guide_offset=guide_offset, variant_offset=variant_offset)
+
+
+def shards_over_ranks(model, data) -> bool:
+    """Whether a (model, screen) pair is split over the ranks of torch.distributed: the variant designs
+    shard by contiguous variant blocks; ControlNormal (a handful of global scalars over ~100 control guides), the covariate
+    Normal model (replicate-level parameters) and the tiling designs (edits shared between overlapping guides) run as
+    replicas -- every rank fits the whole screen and returns the same result."""
+    name, _ = resolve(model)
+    if name in ("ControlNormal", "MultiMixtureNormal"):
+        return False
+    if getattr(data, "sample_covariates", None) is not None or not hasattr(data, "target_lengths"):
+        return False
+    return int(data.n_targets) >= 2
 
 
 def run_inference(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, autoguide=False, device="cuda",
                   dtype=torch.float32, seed=101, log_every=100):
-    """Run SVI (one-particle Trace_ELBO + ClippedAdam, lr decaying by `gamma` over the run)."""
+    """Run SVI (one-particle Trace_ELBO + ClippedAdam, lr decaying by `gamma` over the run).
+
+    Same signature and return value as bean/model/run.py:347-396.  When torch.distributed is initialised with more than one
+    rank (one process per GPU, e.g. under torchrun), every rank passes the SAME tensorised screen: the variants -- with all
+    their guides -- are split over the ranks (`dist.shard_data`), each rank fits its block on its own GPU, the per-step ELBO
+    scalars are summed and the parameters gathered, so that every rank returns the result of the whole screen."""
+    import torch.distributed as tdist
+
+    from .dist import run_sharded
+
+    world = tdist.get_world_size() if (tdist.is_available() and tdist.is_initialized()) else 1
+    if world > 1 and shards_over_ranks(model, data):
+        def make(sub, guide_offset, variant_offset):
+            return make_engine(model, guide, sub, initial_lr, gamma, num_steps, device, dtype, seed, guide_offset, variant_offset)
+
+        params, loss = run_sharded(make, data, num_steps, tdist.get_rank(), world, log_every=log_every)
+        return params, {"loss": loss.tolist(), "params": {k: v.detach().cpu() for k, v in params.items()}}
     eng = make_engine(model, guide, data, initial_lr, gamma, num_steps, device, dtype, seed)
     done = 0
     while done < num_steps:

@@ -57,7 +57,10 @@ def test_draws_depend_on_global_ids_only(cuda_device):
         assert not torch.equal(full, dirichlet_rsample(conc, 3, other))
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-5)])
+# fp64 tolerance: torch's saddle-point expression cancels from O((x - mean)^-2) to O(1), which amplifies the 1-ulp differences
+# between glibc's and libdevice's log / pow by up to ~1e5 (observed 4e-10 at total concentration 170); 1e-10 holds for the small
+# totals of variant designs (A = 2), 1e-8 is asserted for all
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-5)])
 @pytest.mark.parametrize("A", [2, 5, 33])
 def test_backward_is_torchs_dirichlet_backward(cuda_device, dtype, tol, A):
     g = torch.Generator().manual_seed(10 + A)

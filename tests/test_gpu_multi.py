@@ -83,3 +83,95 @@ def test_survival_models_sharded_over_two_gpus_equal_single_gpu(tmp_path):
                 ref = f[vb:ve] if f.shape[0] == (r["full"]["mu_loc"].shape[0]) and k.startswith("mu_") else f[gb:ge]
                 scale = f.abs().mean().item() + 1e-300
                 assert (g.double() - ref.double()).abs().max().item() <= tol * 50 * scale, (model, dtype, k)
+
+
+def _fused_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from crispr_bean_b200.dist import shard_data
+    from crispr_bean_b200.survival_fused import SurvivalFusedEngine
+
+    solo = dist.new_group([rank], use_local_synchronization=True)
+    data = _data("MixtureNormal")
+    sub, off = shard_data(data, rank, world)
+    res = {}
+    for dtype in (torch.float64, torch.float32):
+        # sharded over the two ranks: the library-wide sums of the abundance Dirichlet are all-reduced every step
+        eng = SurvivalFusedEngine(sub, f"cuda:{rank}", dtype=dtype, num_steps=12, seed=4, guide_offset=off["guide_offset"],
+                                  variant_offset=off["variant_offset"])
+        eng.run(12)
+        loss = eng.losses().to(f"cuda:{rank}")
+        dist.all_reduce(loss)
+        full = SurvivalFusedEngine(data, f"cuda:{rank}", dtype=dtype, num_steps=12, seed=4, group=solo)  # unsharded, same seed
+        full.run(12)
+        res[str(dtype)] = {"loss": loss.cpu(), "full_loss": full.losses(), "off": off,
+                           "got": {k: v.cpu() for k, v in eng.params().items()}, "full": {k: v.cpu() for k, v in full.params().items()}}
+    torch.save(res, f"{out_dir}/f{rank}.pt")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_survival_run_sharded_over_two_gpus_equals_single_gpu(tmp_path):
+    """12 free-running steps (Philox draws keyed by global guide / variant ids): the two shards together reproduce the
+    single-GPU run -- same losses, same parameters (the library-wide sums differ only in summation order)."""
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_fused_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        res = torch.load(f"{tmp_path}/f{rank}.pt")
+        for dtype, r in res.items():
+            tol = 1e-9 if "64" in dtype else 1e-4
+            torch.testing.assert_close(r["loss"], r["full_loss"], rtol=tol, atol=0)
+            off = r["off"]
+            gb, ge = off["guide_offset"], off["guide_offset"] + off["n_guides"]
+            vb, ve = off["variant_offset"], off["variant_offset"] + off["n_variants"]
+            for k, g in r["got"].items():
+                f = r["full"][k][vb:ve] if k.startswith("mu_") else r["full"][k][gb:ge]
+                torch.testing.assert_close(g.double(), f.double(), rtol=tol * 10, atol=tol * 10 * f.abs().mean().item())
+
+
+def _run_inference_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from crispr_bean_b200 import model as sorting_model
+    from crispr_bean_b200 import survival_model
+    from crispr_bean_b200.run import run_inference
+    from tests import helpers as H
+
+    out = {}
+    data = H.make_small_mixture_data(n_variants=40, n_reps=3, seed=5)
+    params, hist = run_inference(sorting_model.MixtureNormalModel, sorting_model.MixtureNormalGuide, data, num_steps=20,
+                                 device=f"cuda:{rank}", seed=7)
+    out["sorting"] = {"loss": torch.tensor(hist["loss"]), "params": hist["params"]}
+    sdata = _data("MixtureNormal")
+    params, hist = run_inference(survival_model.MixtureNormalModel, survival_model.MixtureNormalGuide, sdata, num_steps=20,
+                                 device=f"cuda:{rank}", seed=7)
+    out["survival"] = {"loss": torch.tensor(hist["loss"]), "params": hist["params"]}
+    torch.save(out, f"{out_dir}/ri{rank}.pt")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_run_inference_shards_over_the_ranks_of_torch_distributed(tmp_path):
+    """`run_inference` under 2 ranks == `run_inference` in one process (sorting: bit for bit in the parameters -- no data-path
+    collective; survival: up to the summation order of the two library-wide sums), on every rank."""
+    from crispr_bean_b200 import model as sorting_model
+    from crispr_bean_b200 import survival_model
+    from crispr_bean_b200.run import run_inference
+    from tests import helpers as H
+
+    port = 29800 + os.getpid() % 90
+    mp.spawn(_run_inference_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    data = H.make_small_mixture_data(n_variants=40, n_reps=3, seed=5)
+    _, solo = run_inference(sorting_model.MixtureNormalModel, sorting_model.MixtureNormalGuide, data, num_steps=20, device="cuda:0", seed=7)
+    _, ssolo = run_inference(survival_model.MixtureNormalModel, survival_model.MixtureNormalGuide, _data("MixtureNormal"), num_steps=20,
+                             device="cuda:0", seed=7)
+    for rank in range(2):
+        res = torch.load(f"{tmp_path}/ri{rank}.pt")
+        torch.testing.assert_close(res["sorting"]["loss"], torch.tensor(solo["loss"]), rtol=1e-6, atol=0)
+        for k, v in solo["params"].items():
+            assert torch.equal(res["sorting"]["params"][k], v), k
+        torch.testing.assert_close(res["survival"]["loss"], torch.tensor(ssolo["loss"]), rtol=1e-4, atol=0)
+        for k, v in ssolo["params"].items():
+            torch.testing.assert_close(res["survival"]["params"][k], v, rtol=1e-3, atol=1e-3 * v.abs().mean().item())
