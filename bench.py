@@ -29,11 +29,16 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (n_variants, guides_per_variant, n_reps) ; 4 sort bins, bulk used for the reporter only
+    # name: (n_variants, guides_per_variant, n_reps); sorting: 4 sort bins, bulk used for the reporter only
     "c5_genome_scale": (200_000, 5, 8),
     "c2_ldlc_variant": (690, 5, 4),
     "tiny": (2_000, 5, 8),
+    # BASELINE.json config 4: proliferation / survival variant screen (MixtureNormal survival program), 3 replicates x
+    # 3 timepoints (D0, D7, D14; control D7 stays selected), at the c5 guide count so that 1/2/4/8 GPUs have work to split
+    "c4_survival": (200_000, 5, 3),
+    "c4_survival_small": (690, 5, 3),
 }
+SURVIVAL = ("c4_survival", "c4_survival_small")
 BASELINE_MD_PUBLISHED = None  # BASELINE.md holds no published number for this metric -> vs_baseline null
 LOSS_BATCH = 100              # steps per ELBO all-reduce (reference print cadence, bean/model/run.py:378)
 GUIDE_PROFILE = os.path.join(ROOT, "profiles", "r2_guide_metrics.txt")  # ncu --set full capture of the dominant kernel
@@ -59,10 +64,12 @@ def alpha_kernel_bytes_per_guide(R, itemsize=4):
 
 
 def build_data(workload, seed):
-    from crispr_bean_b200.data_class import VariantSortingReporterScreenData
-    from crispr_bean_b200.synth import make_sorting_screen
+    from crispr_bean_b200.data_class import VariantSortingReporterScreenData, VariantSurvivalReporterScreenData
+    from crispr_bean_b200.synth import make_sorting_screen, make_survival_screen
 
     nv, gpv, nr = WORKLOADS[workload]
+    if workload in SURVIVAL:
+        return VariantSurvivalReporterScreenData(make_survival_screen(nv, gpv, n_reps=nr, seed=seed), control_condition="D7")
     scr = make_sorting_screen(nv, gpv, n_reps=nr, seed=seed)
     # 4 sort bins; the bulk sample only feeds the reporter editing-rate sites ("c5")
     return VariantSortingReporterScreenData(scr, control_can_be_selected=False)
@@ -133,18 +140,35 @@ def run_with_loss_exchange(engine, steps, world):
         done += n
 
 
-def oracle_step_time(data, steps, warmup=1, anomaly=True):
-    """Seconds per SVI step of the CPU oracle (plain-torch restatement of the reference's MixtureNormal program)."""
+def make_bench_engine(workload, data, dev, dtype, num_steps, seed, off):
+    if workload in SURVIVAL:
+        from crispr_bean_b200.survival_fused import SurvivalFusedEngine
+
+        return SurvivalFusedEngine(data, dev, dtype=dtype, num_steps=num_steps, seed=seed, guide_offset=off["guide_offset"],
+                                   variant_offset=off["variant_offset"])
+    from crispr_bean_b200.svi import SviEngine
+
+    return SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=num_steps, seed=seed, guide_offset=off["guide_offset"],
+                     variant_offset=off["variant_offset"])
+
+
+def oracle_step_time(data, steps, warmup=1, anomaly=True, max_seconds=240.0):
+    """Seconds per SVI step of the CPU oracle (plain-torch restatement of the reference's MixtureNormal program); stops early
+    (after at least one timed step) once `max_seconds` have gone by."""
     from oracle import bean_oracle as O
 
+    elbo_fn = O.elbo_survival_mixture_normal if getattr(data, "is_survival", False) else O.elbo_mixture_normal
     ps = O.ParamStore()
     opt = O.ClippedAdam(lr=0.01, lrd=0.1 ** (1 / 2000))
     times = []
     torch.autograd.set_detect_anomaly(anomaly)  # the reference switches it on for good (model.py:399; SURVEY App. B6)
+    began = time.perf_counter()
     try:
         for t in range(warmup + steps):
+            if times and time.perf_counter() - began > max_seconds:
+                break
             t0 = time.perf_counter()
-            loss, _ = O.elbo_mixture_normal(data, ps)
+            loss, _ = elbo_fn(data, ps)
             ps.zero_grad()
             loss.backward()
             opt.step(ps.unconstrained)
@@ -180,7 +204,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     nv, gpv, nr = WORKLOADS[args.workload]
-    R, B, L = nr, 4, 2
+    survival = args.workload in SURVIVAL
+    R, B, L = nr, (3 if survival else 4), 2
+    program = "MixtureNormal survival (3 timepoints, control D7)" if survival else "MixtureNormal sorting"
     G_total = nv * gpv * (world if args.scaling == "weak" else 1)
     cells_per_step = G_total * R * B
     scaling = args.scaling if world > 1 else "strong"  # at N = 1 both are the same workload
@@ -188,12 +214,20 @@ def main():
         shard_txt = f"ONE screen of {nv * gpv} guides / {nv} variants split into {world} contiguous variant block(s) (strong scaling)"
     else:
         shard_txt = f"{world} independent screen(s) of {nv * gpv} guides, one per GPU (weak scaling)"
-    config = {"workload": f"{args.workload}: MixtureNormal sorting, {G_total} guides x {R} reps x {B} bins in total, "
+    # L2 rule: where a rank's step footprint is below twice the L2 (strong scaling at N >= 4) the timed steps are separated by
+    # an untimed overwrite of a 256 MB buffer, so that every timed step reads its inputs from HBM
+    footprint = 700.0 * nv * gpv / (world if args.scaling == "strong" else 1)
+    flush = footprint < 2 * 126e6
+    exchange = (f"per-step ELBO scalars all-reduced over NCCL every {LOSS_BATCH} steps" +
+                (f" + the {R + 1} library-wide sums of the abundance Dirichlet all-reduced EVERY step" if survival else "") +
+                ", inside the timed region")
+    config = {"workload": f"{args.workload}: {program}, {G_total} guides x {R} reps x {B} bins in total, "
                           f"bcmatch layer + reporter edits",
-              "l2": "per-step inputs (0.36 GB per 1M guides) exceed the 126 MB L2 down to 8 shards x 45 MB + scratch; the kernels "
-                    "stream every buffer once per step, so nothing is served from a previous step's L2 lines at N <= 4; no flush",
+              "l2": (f"per-rank step footprint ~{footprint / 1e6:.0f} MB (~0.7 KB per guide: inputs + parameter state + hand-over scratch); " +
+                     ("below 2x the 126 MB L2: a 256 MB buffer is overwritten between timed steps (untimed), every step timed by its own "
+                      "CUDA events" if flush else "more than 2x the 126 MB L2: nothing of a previous step survives in cache, no flush")),
               "sharding": shard_txt,
-              "exchange": f"per-step ELBO scalars all-reduced over NCCL every {LOSS_BATCH} steps inside the timed region" if world > 1 else "none (one GPU)"}
+              "exchange": exchange if world > 1 else "none (one GPU)"}
 
     # ------------------------------------------------------------------------------------------
     if args.impl == "reference":
@@ -208,7 +242,7 @@ def main():
         sec_off = oracle_step_time(data, min(steps, 3), warmup=1, anomaly=False)
         cells = data.n_guides * R * B
         value = cells / sec
-        sample = (f"{'all' if data.n_guides == nv * gpv else 'first'} {data.n_guides} guides of the workload, {steps} timed SVI steps of the "
+        sample = (f"{'all' if data.n_guides == nv * gpv else 'first'} {data.n_guides} guides of the workload, <= {steps} timed SVI steps (240 s cap) of the "
                   f"plain-torch oracle port on {torch.get_num_threads()} threads, torch anomaly mode ON as the reference leaves it "
                   f"(model.py:399): {sec * 1e3:.0f} ms/step; anomaly mode off: {sec_off * 1e3:.0f} ms/step; pyro itself is not "
                   "installable (no poutine overhead in this number)")
@@ -235,7 +269,6 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     from crispr_bean_b200.dist import shard_data
-    from crispr_bean_b200.svi import SviEngine
 
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     if args.scaling == "strong":
@@ -248,8 +281,7 @@ def main():
     G_rank = data.n_guides
     total_steps = args.warmup + args.steps
     burn_in = max(args.burn_in, 0)
-    eng = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=max(2000, burn_in + 4 * total_steps + 64), seed=101,
-                    guide_offset=off["guide_offset"], variant_offset=off["variant_offset"])
+    eng = make_bench_engine(args.workload, data, dev, dtype, max(2000, burn_in + 4 * total_steps + 64), 101, off)
 
     def barrier():
         if world > 1:
@@ -266,28 +298,47 @@ def main():
     # --- device-resident throughput: inputs already in HBM --------------------------------------
     run_with_loss_exchange(eng, burn_in, world)  # untimed: reach the steady-state regime of a long run (see --burn-in)
     run_with_loss_exchange(eng, args.warmup, world)
+    scrub = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    run_with_loss_exchange(eng, args.steps, world)
-    stop.record()
-    barrier()
+    if not flush:
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        run_with_loss_exchange(eng, args.steps, world)
+        stop.record()
+        barrier()
+        ms_local = start.elapsed_time(stop)
+    else:
+        evs = []
+        for t in range(args.steps):
+            scrub.fill_(t & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            losses = eng.run(1)
+            if world > 1 and ((t + 1) % LOSS_BATCH == 0 or t + 1 == args.steps):
+                lo = eng.step - 1 - (t % LOSS_BATCH)
+                dist.all_reduce(eng.loss[lo:eng.step])
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms_local = sum(a.elapsed_time(b) for a, b in evs)
     sampler.stop_flag = True
     sampler.join()
-    ms = max_over_ranks(start.elapsed_time(stop))
+    ms = max_over_ranks(ms_local)
     steps_per_sec = args.steps / (ms * 1e-3)
     value = cells_per_step * steps_per_sec
     final_loss = float(eng.loss[eng.step - 1].item())
 
     # --- per-kernel timing for the roofline: each kernel alone, same launches, CUDA events --------
     ms_guide = max_over_ranks(time_steps(eng, args.steps, phases=1) / args.steps)
-    ms_alpha = max_over_ranks(time_steps(eng, args.steps, phases=4) / args.steps) if eng.split else 0.0
+    split = getattr(eng, "split", True)
+    ms_alpha = max_over_ranks(time_steps(eng, args.steps, phases=4) / args.steps) if split else 0.0
     ms_var = max_over_ranks(time_steps(eng, args.steps, phases=2) / args.steps)
     itemsize = 4 if dtype == torch.float32 else 8
-    bytes_launch = algorithmic_bytes_per_guide(R, B, L, gpv, itemsize) * G_rank
-    handover = handover_bytes_per_guide(R, itemsize) * G_rank if eng.split else 0.0
+    # survival: + log obs R + gamma R in, gamma R out, q0 (param, m, v) read + written 6, control allele counts as the reporter's
+    bytes_launch = (algorithmic_bytes_per_guide(R, B, L, gpv, itemsize) + (3 * R + 6) * itemsize * survival) * G_rank
+    handover = handover_bytes_per_guide(R, itemsize) * G_rank if split else 0.0
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
@@ -311,7 +362,7 @@ def main():
     # DRAM traffic, instruction count and pipe utilisation of one launch, from the committed ncu --set full capture
     traffic = warp_inst = None
     note = "no ncu capture of this configuration committed"
-    if os.path.exists(GUIDE_PROFILE) and args.workload == "c5_genome_scale" and dtype == torch.float32 and world == 1:
+    if os.path.exists(GUIDE_PROFILE) and args.workload == "c5_genome_scale" and dtype == torch.float32 and world == 1:  # noqa: E501
         m = {}
         for ln in open(GUIDE_PROFILE):
             if " = " in ln:
@@ -331,7 +382,7 @@ def main():
                     f"{m.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', float('nan')):.1f} % of peak")
     clk = (sampler.summary()["sm_mhz"] or 1965) * 1e6
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    roofline = {"bound": "hbm", "kernel": "svi_guide_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "surv_guide_kernel" if survival else "svi_guide_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": os.path.relpath(GUIDE_PROFILE, ROOT) + " (ncu --set full, one launch)" if traffic else None,
                 "peak_source": peak_src,
@@ -356,8 +407,7 @@ def main():
     e2e_steps = args.steps
     loss_host = torch.zeros(e2e_steps, dtype=torch.float64).pin_memory()
     t0.record()
-    eng2 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=e2e_steps, seed=7,  # H2D of the whole shard
-                     guide_offset=off["guide_offset"], variant_offset=off["variant_offset"])
+    eng2 = make_bench_engine(args.workload, data, dev, dtype, e2e_steps, 7, off)  # H2D of the whole shard
     for t in range(e2e_steps):
         eng2.run(1)
         if world == 1:
@@ -372,7 +422,7 @@ def main():
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
     scr = eng2.screen
     h2d = (scr.x.numel() + scr.a0.numel()) * itemsize + scr.row_mask.numel() + (eng2.allele_counts.numel() + eng2.pi_a0.numel()) * itemsize \
-        + eng2.guide_variant.numel() * 4 + eng2.variant_ptr.numel() * 4
+        + eng2.guide_variant.numel() * 4 + eng2.variant_ptr.numel() * 4 + (eng2.log_obs.numel() * itemsize if survival else 0)
     d2h = 8 * e2e_steps + sum(v.numel() * v.element_size() for v in params_host.values())
     e2e_value = cells_per_step * e2e_steps / (ms_e2e * 1e-3)
     assert torch.isfinite(loss_host).all()
@@ -381,8 +431,7 @@ def main():
     # --- the north_star's run: a complete SVI fit of `--full-run-steps` steps from step 0 --------
     full_run = None
     if args.full_run_steps > 0:
-        eng3 = SviEngine(data, "MixtureNormal", dev, dtype=dtype, num_steps=args.full_run_steps, seed=101,
-                         guide_offset=off["guide_offset"], variant_offset=off["variant_offset"])
+        eng3 = make_bench_engine(args.workload, data, dev, dtype, args.full_run_steps, 101, off)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
@@ -412,7 +461,7 @@ def main():
                 "what": f"SviEngine built from PINNED HOST tensors (this rank's shard: upload + re-tiling + data-only constants inside the "
                         f"timed region), {e2e_steps} steps from step 0, losses copied to pinned host memory (every step at N = 1, per "
                         f"{LOSS_BATCH}-step all-reduce batch at N > 1), final parameters copied to host; per-rank bytes"},
-        "gpu_launches": (3 if eng.split else 2) * args.steps,
+        "gpu_launches": (3 if split else 2) * args.steps,
         "roofline": roofline,
         "final_loss": final_loss,
     }

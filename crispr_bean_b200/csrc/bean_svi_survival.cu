@@ -386,12 +386,17 @@ static int survival_run(const BeanScreen* s, const BeanSviState* state, const Be
     p.sums_cur = sv->sums[cur];
     p.gamma_next = cfg->apply_update ? static_cast<real*>(sv->gamma[cur ^ 1]) : nullptr;
     p.sums_next = cfg->apply_update ? sv->sums[cur ^ 1] : nullptr;
-    if (p.B <= 4)
-      surv_guide_kernel<real, 4><<<grid, SVI_THREADS, 0, st>>>(p);
-    else
-      surv_guide_kernel<real, BEAN_MAX_BINS><<<grid, SVI_THREADS, 0, st>>>(p);
-    svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
-    svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
+    // phases: 0 = the whole step; otherwise a bit mask (1 guide kernel, 2 variant kernel, 4 alpha kernel) so that a benchmark
+    // can time each kernel alone with CUDA events
+    const int ph = cfg->phases == 0 ? 7 : cfg->phases;
+    if (ph & 1) {
+      if (p.B <= 4)
+        surv_guide_kernel<real, 4><<<grid, SVI_THREADS, 0, st>>>(p);
+      else
+        surv_guide_kernel<real, BEAN_MAX_BINS><<<grid, SVI_THREADS, 0, st>>>(p);
+    }
+    if (ph & 4) svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
+    if (ph & 2) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
   }
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;

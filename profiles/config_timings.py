@@ -64,7 +64,9 @@ def main():
                  TilingSviEngine(d, dev, num_steps=100), O.elbo_multi_mixture_normal, {}))
     d = dc.VariantSurvivalReporterScreenData(make_survival_screen(690, "lognormal", n_reps=3, seed=21, n_negctrl_guides=101),
                                              control_condition="D7")
-    rows.append((f"c4 survival MixtureNormal ({d.n_guides} guides x 3 x 3)", d, SurvivalSviEngine(d, "MixtureNormal", dev, num_steps=100),
+    from crispr_bean_b200.survival_fused import SurvivalFusedEngine
+
+    rows.append((f"c4 survival MixtureNormal ({d.n_guides} guides x 3 x 3), fused step", d, SurvivalFusedEngine(d, dev, num_steps=100),
                  O.elbo_survival_mixture_normal, {}))
     for name, data, eng, fn, kw in rows:
         g, c = gpu_ms(eng), cpu_ms(fn, data, **kw)

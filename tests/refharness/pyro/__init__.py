@@ -109,6 +109,35 @@ def sample(name, fn, obs=None, infer=None):
     return msg["value"]
 
 
+class _Unit:
+    """pyro.distributions.Unit: a trivial distribution over the empty tensor whose log_prob IS the given log factor."""
+
+    has_rsample = False
+
+    def __init__(self, log_factor):
+        self.log_factor = log_factor
+        self.batch_shape, self.event_shape = tuple(log_factor.shape), (0,)
+
+    def expand(self, batch_shape):
+        return _Unit(self.log_factor.expand(tuple(batch_shape)))
+
+    def sample(self, sample_shape=()):
+        return self.log_factor.new_empty(tuple(self.log_factor.shape) + (0,))
+
+    def log_prob(self, value):
+        return self.log_factor
+
+
+def factor(name, log_factor, *, has_rsample=None):
+    """pyro.factor: adds an arbitrary log-probability term to the model (`sample(name, Unit(log_factor), obs=empty)` in
+    pyro.primitives); plates and masks apply to it like to any other site."""
+    import torch
+
+    log_factor = torch.as_tensor(log_factor)
+    unit = _Unit(log_factor)
+    sample(name, unit, obs=unit.sample(), infer={"is_auxiliary": True})
+
+
 def plate(name, size=None, subsample_size=None, subsample=None, dim=None):
     if subsample_size is not None or subsample is not None:
         raise NotImplementedError("subsampling plates are not used by the reference")

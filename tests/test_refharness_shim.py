@@ -193,3 +193,21 @@ def test_dirichlet_multinomial_log_prob_is_the_compound_pmf():
     got = dist.DirichletMultinomial(a, validate_args=False).log_prob(x)
     ref = [dirichlet_multinomial.logpmf(x[i].numpy().astype(int), a[i].numpy(), int(x[i].sum())) for i in range(2)]
     assert torch.allclose(got, torch.tensor(ref, dtype=torch.float64), atol=1e-12)
+
+
+def test_factor_adds_its_log_factor_to_the_model_side_of_the_elbo():
+    """pyro.factor(name, t) contributes exactly t (summed) to the model log-density and differentiates through it."""
+    def model():
+        w = pyro.param("w", torch.tensor(2.0))
+        pyro.sample("z", dist.Normal(0.0, 1.0))
+        pyro.factor("extra", -3.0 * w * w)
+
+    def guide():
+        pyro.sample("z", dist.Normal(0.0, 1.0))
+
+    pyro.clear_param_store()
+    torch.manual_seed(0)
+    loss = pyro.infer.Trace_ELBO().differentiable_loss(model, guide)
+    assert abs(float(loss) - 12.0) < 1e-12  # -(log p(z) - 3 w^2 - log q(z)) = 3 w^2
+    loss.backward()
+    assert abs(float(pyro.get_param_store().unconstrained("w").grad) - 12.0) < 1e-12
