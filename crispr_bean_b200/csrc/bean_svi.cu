@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
 template <typename real, bool MIXTURE, bool ACC, bool SPLIT>
 static void launch_guide(const SviParams<real>& p, cudaStream_t st, bool guide, bool alpha, bool fast) {
   const int grid = (p.G + SVI_THREADS - 1) / SVI_THREADS;
-  constexpr bool HAS_FAST = SPLIT || !MIXTURE;  // the fused (non-split) mixture step is the legacy path: generic only
+  constexpr bool HAS_FAST = true;
   if (!guide) {
   } else if (HAS_FAST && fast && p.B == 4)
     svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, HAS_FAST><<<grid, SVI_THREADS, 0, st>>>(p);

@@ -31,6 +31,16 @@ __device__ __forceinline__ real abundance_gamma(uint64_t seed, uint32_t g, uint3
   GammaMT<real> mt;
   mt.init(c);
   const uint2 key = seed_key(seed);
+  real boost = real(1);
+  if (mt.inv_alpha != real(0)) {
+    // alpha < 1: Gamma(a) = Gamma(a + 1) U^(1/a).  With a = q0 ~ 1/G the factor underflows for all but ~1e-4 of the draws:
+    // its logarithm is looked at FIRST, and a draw that cannot reach `tiny` (Gamma(a + 1) < e^12 with probability
+    // 1 - 1e-5 ... it is clamped to tiny either way) skips the Marsaglia-Tsang loop altogether
+    const uint4 w = philox4x32_10(make_uint4(g, r, step, STREAM_ABUND), key);
+    const real lb = Num<real>::flog(real(1) - real(u01(w.x))) * mt.inv_alpha;
+    if (lb < real(sizeof(real) == 4 ? -100.0 : -720.0)) return Lim<real>::tiny();
+    boost = Num<real>::exp(lb);
+  }
   real out = real(0);
   bool ok = false;
   for (uint32_t k = 0; k < 16u && !ok; ++k) {
@@ -40,11 +50,7 @@ __device__ __forceinline__ real abundance_gamma(uint64_t seed, uint32_t g, uint3
     ok = mt.attempt(n0, 1.0f - u01(w.z), out);
     if (!ok) ok = mt.attempt(n1, 1.0f - u01(w.w), out);
   }
-  if (mt.inv_alpha != real(0)) {
-    const uint4 w = philox4x32_10(make_uint4(g, r, step, STREAM_ABUND), key);
-    out *= Num<real>::pow(real(1) - real(u01(w.x)), mt.inv_alpha);
-  }
-  return Num<real>::fmax(out, Lim<real>::tiny());
+  return Num<real>::fmax(out * boost, Lim<real>::tiny());
 }
 
 // standard normal behind mu_negctrl of guide g at `step`
@@ -93,10 +99,11 @@ __global__ void __launch_bounds__(VAR_THREADS) surv_sums_kernel(const SviParams<
   }
 }
 
-template <typename real, int NB>
+// EXACT: the screen has exactly NB timepoints (no `b < B` predicates in the bin loops).
+template <typename real, int NB, bool EXACT>
 __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_guide_kernel(const SviParams<real> p) {
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
-  const int R = p.R, B = p.B;
+  const int R = p.R, B = EXACT ? NB : p.B;
   const real eps = real(1e-5);
   const bool owns = g < p.G;
   double elbo = 0.0;
@@ -153,6 +160,16 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
     const real c = Num<real>::exp(p.q0_u[g]);
     const double Csum = p.sums_cur[R];
     real d_c = real(0), dmu1 = real(0);
+    // float: psi(c + 1) - psi(sum q0), the guide-only part of the pathwise derivative of a draw at the lower clamp (below)
+    real psi_diff = real(0);
+    if (sizeof(real) == 4) psi_diff = digamma_full(c + real(1)) - digamma_full(real(Csum));
+    // growth of the two alleles up to each control condition (survival_model.py:326-333): per guide, not per replicate
+    real wc0[BEAN_SURV_MAX_CTRL], wc1[BEAN_SURV_MAX_CTRL];
+#pragma unroll
+    for (int ci = 0; ci < BEAN_SURV_MAX_CTRL; ++ci) {
+      wc0[ci] = ci < p.n_ctrl ? Num<real>::exp(mu0 * p.t_ctrl[ci]) : real(0);
+      wc1[ci] = ci < p.n_ctrl ? Num<real>::exp(mu1 * p.t_ctrl[ci]) : real(0);
+    }
     for (int r = 0; r < R; ++r) {
       const bool rmask = p.row_mask[(size_t)r * p.G + g] != 0;
       // ---- initial abundance: guide draw x ~ Dirichlet(q0) over all guides, model observes `obs` under the same Dirichlet
@@ -167,8 +184,15 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
         const real lx = Num<real>::log(xq);
         const real dl = p.log_obs[(size_t)r * p.G + g] - lx;
         elbo_g += (c - real(1)) * dl;
-        // pathwise derivative of the draw w.r.t. q0 (torch _Dirichlet_backward with sum_h x_h gout_h = -(C - G))
-        const double D = dirichlet_grad_any<sizeof(real) == 4>((double)xq, (double)c, Csum - (double)c);
+        // pathwise derivative of the draw w.r.t. q0 (torch _Dirichlet_backward with sum_h x_h gout_h = -(C - G)).  With q0 ~ 1/G
+        // nearly every draw sits at the sampler's lower clamp (1.2e-38): torch's small-x series then reduces to its first term,
+        // x / c (psi(c + 1) - psi(C) - ln x) to 1e-12 relative, whose guide-only part is hoisted (float path; the double
+        // kernels evaluate torch's expression as written)
+        double D;
+        if (sizeof(real) == 4 && xq < real(1e-12) && Csum * (double)xq < 2.5)
+          D = (double)(xq / c * (psi_diff - lx));
+        else
+          D = dirichlet_grad_any<false>((double)xq, (double)c, Csum - (double)c);
         d_c += dl + real(D * (-(double)(c - real(1)) / (double)xq + (Csum - p.n_guides_total)));
       }
       // ---- pi ~ Dirichlet(cg) (a Beta draw)
@@ -233,38 +257,43 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
         go1 += de[b] * P1[b];
         dP1[b] += de[b] * pi1;
       }
-      const real lp0 = Num<real>::log(pi0), lp1 = Num<real>::log(pi1);
-      const real ip0 = Num<real>::rcp(pi0), ip1 = Num<real>::rcp(pi1);
-      // guide site: -log Dirichlet(pi; cg), unmasked (survival_model.py:699-712)
-      elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
-      go0 -= (cg[0] - real(1)) * ip0;
-      go1 -= (cg[1] - real(1)) * ip1;
-      dcg[0] -= dgd_cg[0] + lp0;
-      dcg[1] -= dgd_cg[1] + lp1;
+      // the guide's Dirichlet(pi; cg) (unmasked, survival_model.py:699-712) and the model's Dirichlet(pi; cm) (under repguide_mask,
+      // :313-322) as their DIFFERENCE: identically zero -- value and gradients -- for an unclamped guide inside the mask
+      if (!(rmask && cg[0] == cm[0] && cg[1] == cm[1])) {
+        const real lp0 = Num<real>::log(pi0), lp1 = Num<real>::log(pi1);
+        const real ip0 = Num<real>::rcp(pi0), ip1 = Num<real>::rcp(pi1);
+        elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
+        go0 -= (cg[0] - real(1)) * ip0;
+        go1 -= (cg[1] - real(1)) * ip1;
+        dcg[0] -= dgd_cg[0] + lp0;
+        dcg[1] -= dgd_cg[1] + lp1;
+        if (rmask) {
+          elbo_g += lg_cm + (cm[0] - real(1)) * lp0 + (cm[1] - real(1)) * lp1;
+          go0 += (cm[0] - real(1)) * ip0;
+          go1 += (cm[1] - real(1)) * ip1;
+          dcm[0] += dgd_cm[0] + lp0;
+          dcm[1] += dgd_cm[1] + lp1;
+        }
+      }
       if (rmask) {
-        // model sites under repguide_mask: Dirichlet prior on pi (:313-322), Multinomial on pi exp(mu t_c) (:323-346)
-        elbo_g += lg_cm + (cm[0] - real(1)) * lp0 + (cm[1] - real(1)) * lp1;
-        go0 += (cm[0] - real(1)) * ip0;
-        go1 += (cm[1] - real(1)) * ip1;
-        dcm[0] += dgd_cm[0] + lp0;
-        dcm[1] += dgd_cm[1] + lp1;
+        // Multinomial on pi exp(mu t_c) under repguide_mask (survival_model.py:323-346)
         const real lo = p.prob_eps, hi = real(1) - p.prob_eps;
-        for (int ci = 0; ci < p.n_ctrl; ++ci) {
+#pragma unroll
+        for (int ci = 0; ci < BEAN_SURV_MAX_CTRL; ++ci) {
+          if (ci >= p.n_ctrl) break;
           const typename Vec2<real>::type ac =
               reinterpret_cast<const typename Vec2<real>::type*>(p.allele_counts)[((size_t)r * p.n_ctrl + ci) * p.G + g];
-          const real tc = p.t_ctrl[ci];
-          const real w0 = Num<real>::exp(mu0 * tc), w1 = Num<real>::exp(mu1 * tc);
-          const real q0 = pi0 * w0, q1 = pi1 * w1;
-          const real iSq = real(1) / (q0 + q1), n0 = q0 * iSq, n1 = q1 * iSq;
+          const real q0 = pi0 * wc0[ci], q1 = pi1 * wc1[ci];
+          const real iSq = Num<real>::rcp(q0 + q1), n0 = q0 * iSq, n1 = q1 * iSq;
           const real c0 = Num<real>::fmin(Num<real>::fmax(n0, lo), hi), c1 = Num<real>::fmin(Num<real>::fmax(n1, lo), hi);
-          if (ac.x != real(0)) elbo_g += ac.x * Num<real>::log(c0);
-          if (ac.y != real(0)) elbo_g += ac.y * Num<real>::log(c1);
-          const real h0 = (n0 >= lo && n0 <= hi) ? ac.x / n0 : real(0), h1 = (n1 >= lo && n1 <= hi) ? ac.y / n1 : real(0);
+          if (ac.x != real(0)) elbo_g += ac.x * log_unit(c0);
+          if (ac.y != real(0)) elbo_g += ac.y * log_unit(c1);
+          const real h0 = (n0 >= lo && n0 <= hi) ? Num<real>::div(ac.x, n0) : real(0), h1 = (n1 >= lo && n1 <= hi) ? Num<real>::div(ac.y, n1) : real(0);
           const real hbar = h0 * n0 + h1 * n1;
           const real dq0 = (h0 - hbar) * iSq, dq1 = (h1 - hbar) * iSq;
-          go0 += dq0 * w0;
-          go1 += dq1 * w1;
-          dmu1 += dq1 * q1 * tc;
+          go0 += dq0 * wc0[ci];
+          go1 += dq1 * wc1[ci];
+          dmu1 += dq1 * q1 * p.t_ctrl[ci];
         }
       }
       // hand the draw with its upstream weights to svi_alpha_kernel (pathwise derivative w.r.t. the guide concentration)
@@ -390,10 +419,12 @@ static int survival_run(const BeanScreen* s, const BeanSviState* state, const Be
     // can time each kernel alone with CUDA events
     const int ph = cfg->phases == 0 ? 7 : cfg->phases;
     if (ph & 1) {
-      if (p.B <= 4)
-        surv_guide_kernel<real, 4><<<grid, SVI_THREADS, 0, st>>>(p);
+      if (p.B == 3)
+        surv_guide_kernel<real, 3, true><<<grid, SVI_THREADS, 0, st>>>(p);
+      else if (p.B <= 4)
+        surv_guide_kernel<real, 4, false><<<grid, SVI_THREADS, 0, st>>>(p);
       else
-        surv_guide_kernel<real, BEAN_MAX_BINS><<<grid, SVI_THREADS, 0, st>>>(p);
+        surv_guide_kernel<real, BEAN_MAX_BINS, false><<<grid, SVI_THREADS, 0, st>>>(p);
     }
     if (ph & 4) svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
     if (ph & 2) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
