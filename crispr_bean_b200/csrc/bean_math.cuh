@@ -243,14 +243,26 @@ __device__ __forceinline__ void gamma_corr(double z, double& cv, double& dl, dou
 }
 __device__ __forceinline__ double log1p_ratio(double y, double /*ratio*/) { return ::log1p(y); }
 
-// full lgamma / digamma of one argument (off the hot row loop: Dirichlet normalisers)
+// full lgamma / digamma of one argument (off the hot row loop: Dirichlet normalisers).  The out-of-line body returns its
+// two results BY VALUE, in registers: with reference parameters (stack slots in the caller's frame) the float build of
+// surv_guide_kernel was observed on B200 to hand the first call's digamma slot the lgamma of the same call once two more calls
+// were added to the kernel (psi of the abundance site): nvcc 12.9, sm_100a, profiles/README.md "aliasing of out-parameters".
+template <typename real> struct LgDg { real lg, dg; };
 template <typename real>
-__device__ __noinline__ void lgamma_digamma(real z, real& lg, real& dg) {
+__device__ __noinline__ LgDg<real> lgamma_digamma_value(real z) {
   real cv, dl;
   gamma_corr(z, cv, dl);
   const real lz = Num<real>::log(z);
-  lg = (z - real(0.5)) * lz - z + real(0.91893853320467274178) + cv;
-  dg = lz + dl;
+  LgDg<real> out;
+  out.lg = (z - real(0.5)) * lz - z + real(0.91893853320467274178) + cv;
+  out.dg = lz + dl;
+  return out;
+}
+template <typename real>
+__device__ __forceinline__ void lgamma_digamma(real z, real& lg, real& dg) {
+  const LgDg<real> v = lgamma_digamma_value(z);
+  lg = v.lg;
+  dg = v.dg;
 }
 
 // ---- Normal CDF pieces ----------------------------------------------------------------------------
@@ -370,6 +382,10 @@ template <> struct BinMasses<double> {
 // absolute error is relative); ~12 instructions against ~45 through the out-of-line logf
 __device__ __forceinline__ float log_unit(float c) { return c > 0.4f ? log1p_ratio_series(c - 1.0f) : log_ftz(c); }
 __device__ __forceinline__ double log_unit(double c) { return ::log(c); }
+// log of any positive float, inline: the series of log1p_ratio around 1, the MUFU log elsewhere (absolute error 2^-22 ln 2 of
+// |log| >= 0.9: <= 2e-7 relative)
+__device__ __forceinline__ float log_pos(float x) { return (x > 0.4f && x < 2.5f) ? log1p_ratio_series(x - 1.0f) : log_ftz(x); }
+__device__ __forceinline__ double log_pos(double x) { return ::log(x); }
 
 // ---- block reduction of a double (deterministic order) ------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

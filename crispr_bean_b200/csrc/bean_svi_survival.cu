@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
           xq = real((double)p.gamma_cur[(size_t)r * p.G + g] / p.sums_cur[r]);
           xq = Num<real>::fmin(Num<real>::fmax(xq, Lim<real>::tiny()), Lim<real>::one_minus());
         }
-        const real lx = Num<real>::log(xq);
+        const real lx = log_pos(xq);
         const real dl = p.log_obs[(size_t)r * p.G + g] - lx;
         elbo_g += (c - real(1)) * dl;
         // pathwise derivative of the draw w.r.t. q0 (torch _Dirichlet_backward with sum_h x_h gout_h = -(C - G)).  With q0 ~ 1/G
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
       // the guide's Dirichlet(pi; cg) (unmasked, survival_model.py:699-712) and the model's Dirichlet(pi; cm) (under repguide_mask,
       // :313-322) as their DIFFERENCE: identically zero -- value and gradients -- for an unclamped guide inside the mask
       if (!(rmask && cg[0] == cm[0] && cg[1] == cm[1])) {
-        const real lp0 = Num<real>::log(pi0), lp1 = Num<real>::log(pi1);
+        const real lp0 = log_pos(pi0), lp1 = log_pos(pi1);
         const real ip0 = Num<real>::rcp(pi0), ip1 = Num<real>::rcp(pi1);
         elbo_g -= lg_cg + (cg[0] - real(1)) * lp0 + (cg[1] - real(1)) * lp1;
         go0 -= (cg[0] - real(1)) * ip0;
