@@ -358,6 +358,18 @@ def main():
     c1.record()
     torch.cuda.synchronize()
     ms_ceiling = c0.elapsed_time(c1) / 20
+    # the same maths in the north_star's lane = (row, bin) mapping (4 bins only): the A/B of the two mappings at the maths level
+    ms_ceiling_lanes = None
+    if B == 4:
+        sink2 = torch.empty(4 * torch.cuda.get_device_properties(dev).multi_processor_count, device=dev, dtype=torch.float32)
+        for _ in range(3):
+            L_.check(L_.lib().bean_row_ceiling_lanes_f32(G_rank, R * L, sink2.data_ptr(), st), "bean_row_ceiling_lanes_f32")
+        c0.record()
+        for _ in range(20):
+            L_.check(L_.lib().bean_row_ceiling_lanes_f32(G_rank, R * L, sink2.data_ptr(), st), "bean_row_ceiling_lanes_f32")
+        c1.record()
+        torch.cuda.synchronize()
+        ms_ceiling_lanes = c0.elapsed_time(c1) / 20
     achieved = bytes_launch / (ms_guide * 1e-3) / 1e9
     # DRAM traffic, instruction count and pipe utilisation of one launch, from the committed ncu --set full capture
     traffic = warp_inst = None
@@ -396,6 +408,10 @@ def main():
                             f"({R * L} rows x {B} bins per guide: {2 * B + 2} lgamma/digamma corrections + {2 * B} log1p per row) with "
                             "no memory traffic at the same launch geometry: the measured FP32/SFU floor of the step's row work",
                     "row_math_ceiling_ms": ms_ceiling, "frac": ms_ceiling / ms_guide,
+                    "row_math_ceiling_lane_per_cell_ms": ms_ceiling_lanes,
+                    "mapping_note": "thread per guide (rows and bins in registers) against lane per (row, bin) cell with 4-lane shuffle "
+                                    "reductions (the north_star's mapping): same maths, the second spends its issue slots on the row-level "
+                                    "terms four times over",
                     "warp_instructions_per_launch": warp_inst,
                     "issue_floor_ms": (warp_inst / (4 * n_sm * clk) * 1e3) if warp_inst else None},
                 "note": note}

@@ -174,6 +174,7 @@ _PROTOTYPES = {
     "bean_dirichlet_rsample_grad_f32": (C.c_int, [C.POINTER(BeanDirichletArgs), C.c_void_p]),
     "bean_dirichlet_rsample_grad_f64": (C.c_int, [C.POINTER(BeanDirichletArgs), C.c_void_p]),
     "bean_row_ceiling_f32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bean_row_ceiling_lanes_f32": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -207,6 +207,13 @@ __device__ __forceinline__ void gamma_corr2(float2 z, float2& cv, float2& dl, fl
   }
 }
 
+// both components inside the series' range (-0.6, 1.5)  <=>  max |y - 0.45| < 1.05: one packed add, one max of absolute
+// values, one compare
+__device__ __forceinline__ bool log1p_ratio_in_range2(float2 y) {
+  const float2 d = add2(y, splat2(-0.45f));
+  return fmaxf(fabsf(d.x), fabsf(d.y)) < 1.05f;
+}
+
 // series of (log1p(y.x), log1p(y.y)); the caller replaces out-of-range components by the log of the ratio itself
 __device__ __forceinline__ float2 log1p_ratio_series2(float2 y) {
   const float2 d = add2(y, splat2(2.0f));

@@ -545,7 +545,7 @@ __device__ __forceinline__ double dirichlet_grad_any(double x, double alpha, dou
 }
 
 #ifndef BEAN_FLOAT_TAILS
-#define BEAN_FLOAT_TAILS 0
+#define BEAN_FLOAT_TAILS 1
 #endif
 
 // Per-warp queue of deferred (non-saddle) draws.  Entry: the draw (x0, x1), the guide's concentrations (a, b), the
@@ -576,8 +576,9 @@ static __device__ __noinline__ void tail_queue_flush(TailQueue<real>& q, int n, 
   const int rank = __popc(wmask & ((1u << lane) - 1u)), width = __popc(wmask);
   for (int j = rank; j < n; j += width) {
     const double x0 = (double)q.x0[j], x1 = (double)q.x1[j], a = (double)q.a[j], b = (double)q.b[j];
-    // double also on the float path (BEAN_FLOAT_TAILS = 1 switches the three cancellation-free regimes to float: their rational
-    // correction is then only ~2e-5 accurate, measured 3.7e-5 on the alpha_pi gradient of the reference's var_mini screen)
+    // float kernels: the three cancellation-free regimes in float.  BEAN_FLOAT_TAILS = 0 (double) was measured on B200: the
+    // alpha kernel goes from 0.185 to 0.291 ms per step at c5 while the worst alpha_pi error of the golden cases only moves
+    // from 3.7e-5 to 3.0e-5 (it is not in these regimes), so float stays
     const double g0 = dirichlet_grad_any<(sizeof(real) == 4) && BEAN_FLOAT_TAILS>(x0, a, b);
     const double g1 = dirichlet_grad_any<(sizeof(real) == 4) && BEAN_FLOAT_TAILS>(x1, b, a);
     q.w0[j] = real(g0 * (double)q.w0[j]);

@@ -91,7 +91,7 @@ __device__ __forceinline__ float dm_row_kl_packed(int nb, const float (&x)[NB], 
       const float t = num * iz.y;
       const float2 y = make_float2(-t * iA, t * iN);
       float2 L = log1p_ratio_series2(y);  // (-L2, -L1) = (ln(a U / (u A)), ln(x U / (u N)))
-      if (!(log1p_ratio_in_range(y.x) && log1p_ratio_in_range(y.y))) {  // outlier bin: rare, one branch for the pair
+      if (!log1p_ratio_in_range2(y)) {  // outlier bin: rare, one branch for the pair
         const float Uu = U * iz.y;
         if (!log1p_ratio_in_range(y.x)) L.x = log_ftz(a[b] * iA * Uu);
         if (!log1p_ratio_in_range(y.y)) L.y = log_ftz(x[b] * iN * Uu);  // x = 0: -inf, discarded below

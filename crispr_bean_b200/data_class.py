@@ -27,6 +27,9 @@ def _as_list(control_condition):
     return control_condition.split(",") if isinstance(control_condition, str) else list(control_condition)
 
 
+ACCESSIBILITY_LOOKUP = None  # callable(bw_path, guides) -> tensor: reader of --acc-bw-path tracks, supplied by the caller
+
+
 class ScreenData:
     """Base tensoriser (reference: `ScreenData`, data_class.py:35-263)."""
 
@@ -126,9 +129,12 @@ class ScreenData:
         if self.accessibility_col is not None:
             self.guide_accessibility = torch.as_tensor(self.screen.guides[self.accessibility_col].to_numpy().copy())
         elif self.accessibility_bw_path is not None:  # data_class.py:130-133
-            from .accessibility import get_accessibility_guides
-
-            self.guide_accessibility = get_accessibility_guides(self.accessibility_bw_path, self.screen.guides)
+            # the bigWig lookup of --acc-bw-path is pre-processing, out of scope of the hot path (pyBigWig in the reference):
+            # the caller plugs a reader in (tests: tests/support/accessibility.py)
+            if ACCESSIBILITY_LOOKUP is None:
+                raise NotImplementedError("accessibility_bw_path needs a bigWig reader: set data_class.ACCESSIBILITY_LOOKUP = "
+                                          "callable(bw_path, guides_dataframe) -> per-guide accessibility, or pass accessibility_col")
+            self.guide_accessibility = ACCESSIBILITY_LOOKUP(self.accessibility_bw_path, self.screen.guides)
         else:
             self.guide_accessibility = None
         if self.sample_mask_column is not None and self.sample_mask_column in sel.samples.columns:

@@ -441,6 +441,9 @@ int bean_dirichlet_rsample_grad_f64(const BeanDirichletArgs* args, void* stream)
  * bench.py quotes next to the HBM roofline.  out: float [ceil(n_guides / 128)] (checksum sink).
  * ---------------------------------------------------------------------------------------------- */
 int bean_row_ceiling_f32(int32_t n_guides, int32_t n_rows_per_guide, int32_t n_bins, void* out, void* stream);
+/* the same maths (4 bins) with one lane per (row, bin) cell and 4-lane shuffle reductions -- the mapping of the north_star,
+ * timed against the thread-per-guide mapping above; out: float [4 * number of SMs] */
+int bean_row_ceiling_lanes_f32(int32_t n_guides, int32_t n_rows_per_guide, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -157,7 +157,7 @@ def real_cases(ns):
     # `--scale-by-acc --acc-bw-path tests/data/accessibility_signal.bw` (tests/test_run.py:85): the signal is looked up with
     # this repo's bigWig reader and handed to BOTH tensorisers as a guide column (the reference's own pyBigWig wrapper cannot
     # run here); tests/test_bigwig_accessibility.py ties that lookup to the reference's per-guide function
-    from crispr_bean_b200.accessibility import get_accessibility_guides
+    from tests.support.accessibility import get_accessibility_guides
 
     til_acc = til.copy()
     til_acc.guides["accessibility"] = get_accessibility_guides(ref_data + "accessibility_signal.bw", til_acc.guides).numpy()

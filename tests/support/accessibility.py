@@ -1,7 +1,7 @@
 """Guide accessibility from a bigWig ATAC / DNase track (`bean run --scale-by-acc --acc-bw-path`).
 
 Host-side mirror of bean/preprocessing/utils.py:70-146 (`_get_accessibility_single`, `get_accessibility_guides`) on the
-pure-Python reader `crispr_bean_b200/bigwig.py` instead of pyBigWig: the geometric mean of (signal + 1) over the
+pure-Python reader `tests/support/bigwig.py` instead of pyBigWig: the geometric mean of (signal + 1) over the
 `half_window_size` bases either side of the guide's `genomic_pos` (NaN bases ignored), NaN guides filled with the median.
 """
 from __future__ import annotations

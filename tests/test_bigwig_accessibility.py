@@ -1,5 +1,5 @@
-"""`--acc-bw-path`: the pure-Python bigWig reader (crispr_bean_b200/bigwig.py) and the guide-accessibility lookup
-(crispr_bean_b200/accessibility.py, mirror of bean/preprocessing/utils.py:70-146).
+"""`--acc-bw-path`: the pure-Python bigWig reader (tests/support/bigwig.py) and the guide-accessibility lookup
+(tests/support/accessibility.py, mirror of bean/preprocessing/utils.py:70-146).
 
 The reader is checked against what each bigWig says about itself (the header's total summary: covered bases, min, max, sum
 of the full-resolution data) on the reference's two tracks, and on a bigWig written here byte by byte; the lookup is
@@ -15,8 +15,8 @@ import pandas as pd
 import pytest
 import torch
 
-from crispr_bean_b200 import bigwig
-from crispr_bean_b200.accessibility import _get_accessibility_single, get_accessibility_guides
+from tests.support import bigwig
+from tests.support.accessibility import _get_accessibility_single, get_accessibility_guides
 from tests.refharness import available, load_reference
 
 REF_DATA = "/root/reference/tests/data"
@@ -149,6 +149,7 @@ def test_tiling_data_class_takes_the_track(tmp_path):
 
     z = np.load(os.path.join(GOLDEN, "ref_tiling_real_mini.npz"))
     kw = ast.literal_eval(str(z["meta/data_kwargs"]))
+    dc.ACCESSIBILITY_LOOKUP = get_accessibility_guides
     data = dc.TilingSortingReporterScreenData(screen_from_arrays(z), accessibility_bw_path=f"{REF_DATA}/accessibility_signal.bw", **kw)
     acc = data.guide_accessibility
     assert acc.shape == (data.n_guides,) and torch.isfinite(acc).all() and (acc >= 1).all() and acc.std() > 0

@@ -42,7 +42,9 @@ def draw_noise(model, data, params, gen):
         noise["eps_mu"], noise["eps_sd"] = rn(E), rn(E)
         alpha = torch.where(data.allele_mask, params["alpha_pi"].double(), torch.full((G, A), 1e-5, dtype=torch.float64))
         conc = alpha / alpha.sum(-1, keepdim=True) * data.pi_a0.double()[:, None]  # guide: not clamped (model.py:938-950)
-        noise["pi"] = torch._sample_dirichlet(conc.expand(R, 1, G, A).contiguous(), gen)  # float64, as in the reference's run
+        # drawn in the dtype pi has in the reference's own run = dtype of pi_a0 (float64 out of the fit, float32 with the fallback
+        # coefficients): draws of non-existent alleles sit at that dtype's smallest normal number
+        noise["pi"] = torch._sample_dirichlet(conc.to(data.pi_a0.dtype).expand(R, 1, G, A).contiguous(), gen).double()
         return noise
     T = data.n_targets
     noise["eps_mu"] = rn(T, 1)

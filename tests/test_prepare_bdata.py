@@ -1,4 +1,4 @@
-"""`prepare_bdata` (crispr_bean_b200/prepare.py) against the reference's own function (bean/preprocessing/utils.py:24-67 +
+"""`prepare_bdata` (tests/support/prepare.py) against the reference's own function (bean/preprocessing/utils.py:24-67 +
 bean/qc/guide_qc.py:49-75, executed in place through tests/refharness where /root/reference is mounted) and against the
 behaviour it documents (portable checks)."""
 import os
@@ -8,7 +8,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from crispr_bean_b200.prepare import filter_no_info_target, prepare_bdata
+from tests.support.prepare import filter_no_info_target, prepare_bdata
 from crispr_bean_b200.screen import MiniScreen
 from crispr_bean_b200.synth import make_sorting_screen, make_survival_screen
 from tests.refharness import available, load_reference

@@ -10,7 +10,7 @@ import pandas as pd
 import pytest
 import torch
 
-from crispr_bean_b200 import run as mine
+from tests.support import run_helpers as mine
 from crispr_bean_b200.synth import make_sorting_screen, make_survival_screen, make_tiling_screen
 from tests.refharness import available, load_reference
 

@@ -1,4 +1,4 @@
-"""CSR versions of the per-variant summaries of the tiling result table (crispr_bean_b200/tiling_stats.py) against the
+"""CSR versions of the per-variant summaries of the tiling result table (tests/support/tiling_stats.py) against the
 reference's dense-tensor functions (bean/preprocessing/utils.py:254-310) run on the reference's own data class."""
 import ast
 import os
@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from crispr_bean_b200 import data_class as dc
-from crispr_bean_b200 import tiling_stats as ts
+from tests.support import tiling_stats as ts
 from crispr_bean_b200.synth import make_tiling_screen
 from tests.helpers import GOLDEN
 from tests.refharness import available, load_reference
