@@ -25,6 +25,19 @@ __device__ __forceinline__ float log_ftz(float x) {
   return r * 0.69314718055994530942f;
 }
 
+// Asynchronous global -> shared copies (LDGSTS): the data of the NEXT replicate is put in flight while the current one is
+// evaluated, without holding registers for it.  Each thread copies and later reads only its own slots, so no CTA barrier is
+// involved: cp.async.wait_group orders the thread's own copies.
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Library functions with long bodies are called through ONE out-of-line copy each: the SVI kernel is bound by
 // instruction issue AND by its instruction-cache footprint, and a call costs far less than a duplicated body.
 static __device__ __noinline__ float ool_logf(float x) { return logf(x); }

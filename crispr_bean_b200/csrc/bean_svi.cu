@@ -33,6 +33,17 @@ template <typename real, int NB, bool MIXTURE, bool ACC, bool SPLIT, bool FAST>
 __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(real) == 4) ? SVI_MIN_CTAS_SPLIT : SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
   __shared__ TailQueue<real> tail_queues[SPLIT ? 1 : SVI_THREADS / SVI_WARP];
   __shared__ __align__(16) real s_sf[FAST ? BEAN_MAX_LAYERS * BEAN_MAX_RB : 1];  // [l][r][b] size factors
+  // STAGE (float, 4 bins, mixture): the count rows and reporter counts of replicate r + 1 are copied global -> shared with
+  // cp.async while replicate r is evaluated, double-buffered per thread; a row is then one LDS.128 (~30 cycles) instead of an
+  // LDG.128 whose ~600-cycle latency sat in the middle of the replicate's dependency chain (ncu r2f: long-scoreboard stalls
+  // 3.0 per issue, the largest stall reason, with only 32 warps per SM to hide them)
+#ifdef BEAN_NO_STAGE
+  constexpr bool STAGE = false;
+#else
+  constexpr bool STAGE = FAST && MIXTURE && NB == 4 && sizeof(real) == 4;
+#endif
+  __shared__ __align__(16) float4 s_x[STAGE ? 2 * BEAN_MAX_LAYERS * SVI_THREADS : 1];  // [buffer][layer][thread]
+  __shared__ __align__(8) float2 s_ac[STAGE ? 2 * SVI_THREADS : 1];                    // [buffer][thread]
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = FAST ? NB : p.B;
   const real eps = real(1e-5);
@@ -110,8 +121,23 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
       mt1.init(cg[1]);
     }
     real elbo_g = real(0);
+    auto stage = [&](int r) {  // rows of both layers + reporter counts of replicate r -> buffer r & 1
+      const int buf = r & 1;
+      for (int l = 0; l < p.L; ++l)
+        cp_async_16(&s_x[(buf * BEAN_MAX_LAYERS + l) * SVI_THREADS + threadIdx.x], p.x + (((size_t)l * R + r) * p.G + g) * 4);
+      cp_async_8(&s_ac[buf * SVI_THREADS + threadIdx.x], p.allele_counts + ((size_t)r * p.G + g) * 2);
+    };
+    if (STAGE) {
+      stage(0);
+      cp_async_commit();
+    }
     for (int r = 0; r < R; ++r) {
       const bool rmask = p.row_mask[(size_t)r * p.G + g] != 0;  // replicate-major: a warp reads 32 consecutive bytes
+      if (STAGE) {
+        if (r + 1 < R) stage(r + 1);
+        cp_async_commit();   // one group per iteration (possibly empty), so that "all but the newest" = replicate r has landed
+        cp_async_wait<1>();
+      }
       real pi0 = real(0), pi1 = real(1);
       if (MIXTURE) {
         if (p.pi_in) {
@@ -154,7 +180,10 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         real xb[NB], sfb[NB], smb[NB], pb[NB], ab[NB], frac[NB], gb[NB];
         bool live[NB];
         real N = real(0), S = real(0);
-        if (NB == 4 && B == 4) {
+        if (STAGE) {
+          const float4 q = s_x[((r & 1) * BEAN_MAX_LAYERS + l) * SVI_THREADS + threadIdx.x];
+          xb[0] = q.x; xb[1] = q.y; xb[2] = q.z; xb[3] = q.w;
+        } else if (NB == 4 && B == 4) {
           const typename Vec4<real>::type q = *reinterpret_cast<const typename Vec4<real>::type*>(xr);
           xb[0] = q.x; xb[1] = q.y; xb[2] = q.z; xb[3] = q.w;
         } else {
@@ -241,8 +270,14 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         if (rmask) {
           // Multinomial reporter counts under the mask (model.py:464-474); torch Multinomial normalises probs and clamps
           // them to [eps, 1-eps]
-          const typename Vec2<real>::type ac = reinterpret_cast<const typename Vec2<real>::type*>(p.allele_counts)[(size_t)r * p.G + g];
-          const real x0 = ac.x, x1 = ac.y;
+          real x0, x1;
+          if (STAGE) {
+            const float2 ac = s_ac[(r & 1) * SVI_THREADS + threadIdx.x];
+            x0 = ac.x; x1 = ac.y;
+          } else {
+            const typename Vec2<real>::type ac = reinterpret_cast<const typename Vec2<real>::type*>(p.allele_counts)[(size_t)r * p.G + g];
+            x0 = ac.x; x1 = ac.y;
+          }
           const real Sp = pi0 + pi1, iSp = Num<real>::rcp(Sp), pn0 = pi0 * iSp, pn1 = pi1 * iSp;
           // torch clamps Multinomial probs to [eps, 1 - eps] of THEIR dtype; in the reference pi inherits pi_a0's dtype
           // (float64 out of the fit even on the float32 path): the host passes the eps that applies (BeanSviConfig)
