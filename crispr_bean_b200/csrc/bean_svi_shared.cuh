@@ -14,9 +14,9 @@ namespace bean {
 constexpr int SVI_THREADS = 128;
 constexpr int SVI_MIN_CTAS = 4;        // fused guide step: <= 128 registers, 16 warps/SM (more CTAs measured +-2 %)
 #ifndef BEAN_GUIDE_MIN_CTAS
-#define BEAN_GUIDE_MIN_CTAS 8
+#define BEAN_GUIDE_MIN_CTAS 7  // with the cp.async-staged rows: 6: 0.4243, 7: 0.4132, 8: 0.4235 ms per launch at c5 (profiles/r2h_phase_times.jsonl)
 #endif
-constexpr int SVI_MIN_CTAS_SPLIT = BEAN_GUIDE_MIN_CTAS;  // split guide step and the Normal models: 64 registers, 32 warps/SM
+constexpr int SVI_MIN_CTAS_SPLIT = BEAN_GUIDE_MIN_CTAS;  // split guide step and the Normal models: 72 registers, 28 warps/SM
                                        // (MixtureNormal 4: 1.17, 6: 1.11, 8: 1.08 ms/step; Normal 4: 0.64, 8: 0.58; final kernel 7: 0.650, 8: 0.640 ms)
 // ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
 // so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
