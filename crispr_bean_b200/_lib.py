@@ -133,9 +133,24 @@ class BeanSurvivalNoise(C.Structure):
     _fields_ = [("eps_negctrl", C.c_void_p), ("q0", C.c_void_p)]
 
 
+class BeanTilingState(C.Structure):
+    _fields_ = [("map", C.POINTER(BeanAlleleMap)), ("n_controls", C.c_int32), ("loss_capacity", C.c_int32),
+                ("allele_mask", C.c_void_p), ("pi_a0", C.c_void_p), ("counts", C.c_void_p),
+                ("edit_params", C.c_void_p), ("edit_m", C.c_void_p), ("edit_v", C.c_void_p), ("edit_grad", C.c_void_p),
+                ("alpha_u", C.c_void_p), ("alpha_m", C.c_void_p), ("alpha_v", C.c_void_p), ("alpha_grad", C.c_void_p),
+                ("mu_e", C.c_void_p), ("sd_e", C.c_void_p), ("d_slot", C.c_void_p),
+                ("partial", C.c_void_p), ("counter", C.c_void_p), ("loss", C.c_void_p),
+                ("mu_prior_loc_v", C.c_void_p), ("mu_prior_scale_v", C.c_void_p), ("sd_prior_loc_v", C.c_void_p), ("sd_prior_scale_v", C.c_void_p),
+                ("epsilon", C.c_double), ("pi_tiny", C.c_double)]
+
+
+class BeanTilingNoise(C.Structure):
+    _fields_ = [("eps_mu", C.c_void_p), ("eps_sd", C.c_void_p), ("pi", C.c_void_p), ("eps_out", C.c_void_p), ("pi_out", C.c_void_p)]
+
+
 SURV_PRIME_NONE, SURV_PRIME_AND_RUN, SURV_PRIME_ONLY = 0, 1, 2
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 10  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 11  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -160,6 +175,11 @@ _PROTOTYPES = {
     "bean_svi_survival_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSurvivalState),
                                             C.POINTER(BeanSviConfig), C.POINTER(BeanSviNoise), C.POINTER(BeanSurvivalNoise),
                                             C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_svi_tiling_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
+    "bean_svi_tiling_run_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanTilingState), C.POINTER(BeanSviConfig),
+                                          C.POINTER(BeanTilingNoise), C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_svi_tiling_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanTilingState), C.POINTER(BeanSviConfig),
+                                          C.POINTER(BeanTilingNoise), C.c_int32, C.c_int32, C.c_void_p]),
     "bean_pi_sites_f32": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
     "bean_pi_sites_f64": (C.c_int, [C.POINTER(BeanPiSitesArgs), C.c_void_p]),
     "bean_latent_sites_num_partials": (C.c_int, [C.c_int64]),

@@ -95,6 +95,9 @@ struct SviParams {
   int n_abund_partial;
   const real* eps_negctrl;              // injected noise (parity runs)
   const real* q0_in;                    // [R][G] injected abundance draw (already normalised)
+  // ---- tiling step (bean_svi_tiling.cu): the "variants" are edits, whose gradient entries sit in allele slots ----
+  const int32_t* gather_idx;            // [nnz] CSC: d_guide index of the j-th entry of a segment (NULL: j itself)
+  int dsd_times_sd;                     // d_guide's second row holds d/d(sd_allele) / sd_allele: multiply the sum by the edit's sd
 };
 
 // pyro.optim.ClippedAdam on one unconstrained scalar; step_size carries
@@ -218,8 +221,9 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
   if (valid) {
     const int beg = p.variant_ptr[v], end = p.variant_ptr[v + 1];
     for (int j = beg + sub; j < end; j += VAR_LANES) {
-      dmu += p.d_guide[j];
-      if (p.has_sd) dsd += p.d_guide[(size_t)p.G + j];
+      const int k = p.gather_idx ? p.gather_idx[j] : j;
+      dmu += p.d_guide[k];
+      if (p.has_sd) dsd += p.d_guide[(size_t)p.G + k];
     }
   }
 #pragma unroll
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
     const real lq_mu = -Num<real>::log(mu_scale) - HL2PI - real(0.5) * e_mu * e_mu;
     const real lq_sd = -y - Num<real>::log(sd_scale) - HL2PI - real(0.5) * e_sd * e_sd;
     elbo = (double)lp_mu - (double)lq_mu + (p.has_sd ? (double)lp_sd - (double)lq_sd : 0.0);
+    if (p.dsd_times_sd) dsd *= sd_t;  // sd_allele = sqrt(sum sd_edit^2): d sd_allele / d sd_edit = sd_edit / sd_allele
     const real dE_mu = dmu + dlp_mu;
     const real dE_sd = dsd + dlp_sd;
     // gradient of the LOSS (-ELBO) w.r.t. the unconstrained parameters

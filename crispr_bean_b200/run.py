@@ -56,7 +56,13 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
                                  guide_offset=guide_offset, **extra)
     if name == "MultiMixtureNormal":
         from .generic import TilingSviEngine
+        from . import tiling_fused
 
+        if tiling_fused.supports(data, bool(mkw.get("scale_by_accessibility", False))):  # <= 32 alleles per guide, no --scale-by-acc
+            return tiling_fused.TilingFusedEngine(data, device=device, dtype=dtype, use_bcmatch=True, num_steps=num_steps,
+                                                  initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
+                                                  sd_scale=float(mkw.get("sd_scale", 0.01)), epsilon=float(mkw.get("epsilon", 1e-5)),
+                                                  prior_params=mkw.get("prior_params"))
         return TilingSviEngine(data, device=device, dtype=dtype, use_bcmatch=True, num_steps=num_steps, initial_lr=initial_lr,
                                gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
                                sd_scale=float(mkw.get("sd_scale", 0.01)), epsilon=float(mkw.get("epsilon", 1e-5)),

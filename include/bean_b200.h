@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 10
+#define BEAN_ABI_VERSION 11
 
 enum {
   BEAN_OK = 0,
@@ -287,6 +287,60 @@ int bean_svi_survival_run_f32(const BeanScreen* screen, const BeanSviState* stat
 int bean_svi_survival_run_f64(const BeanScreen* screen, const BeanSviState* state, const BeanSurvivalState* survival,
                               const BeanSviConfig* cfg, const BeanSviNoise* noise, const BeanSurvivalNoise* survival_noise,
                               int32_t first_step, int32_t n_steps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bean_svi_tiling_run_{f32,f64}: n_steps complete SVI steps of the TILING sorting program (MultiMixtureNormal) on the device.
+ *
+ * One step = `svi.step(data)` (bean/model/run.py:376-380) for bean/model/model.py:550-751 (MultiMixtureNormalModel) and
+ * :878-962 (MultiMixtureNormalGuide): per-edit draws `mu_alleles`, `sd_alleles`; allele mean / sd from its edits
+ * (`allele_to_edit @ mu_edits`, norm of `allele_to_edit * sd_edits`, wild type (0, 1)); Normal-CDF bin masses per allele with
+ * non-existent alleles forced to 0; `pi` ~ Dirichlet over the alleles of a guide; allele mixture; get_alpha +
+ * Dirichlet-Multinomial sites; `pi` Dirichlet prior with the epsilon-regularised concentration, guide Dirichlet and
+ * `bulk_allele_count` Multinomial under repguide_mask; Trace_ELBO loss and gradient; ClippedAdam.  Three launches per step:
+ * per-edit draws, a warp-per-guide kernel with one lane per allele (so n_alleles <= 32: filtered allele tables; wider raw
+ * tables stay on the site-kernel engine), and the per-edit kernel that reduces the allele slots over the CSC map.
+ * Without --scale-by-acc.  Layouts: alpha_u / alpha_m / alpha_v / allele_mask [G][A]; counts [R][C][G][A]; pi [R][G][A].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BeanTilingState {
+  const BeanAlleleMap* map;      /* CSR slot -> edits, CSC edit -> slots (bean_allele_gather) */
+  int32_t n_controls;            /* C */
+  int32_t loss_capacity;
+  const uint8_t* allele_mask;    /* u8 [G][A]: 0 = the guide has no such allele */
+  const double* pi_a0;           /* f64 [G] */
+  const void* counts;            /* real [R][C][G][A] allele_counts_control */
+  void* edit_params;             /* real [4][E]: mu_loc, log mu_scale, sd_loc, log sd_scale */
+  void* edit_m;
+  void* edit_v;
+  void* edit_grad;               /* real [4][E] out or NULL */
+  void* alpha_u;                 /* real [G][A] log alpha_pi (entries of non-existent alleles are ignored: epsilon) */
+  void* alpha_m;
+  void* alpha_v;
+  void* alpha_grad;              /* real [G][A] out or NULL */
+  void* mu_e;                    /* real [E] scratch: this step's draws */
+  void* sd_e;
+  void* d_slot;                  /* real [2][G * (A - 1)] scratch */
+  double* partial;               /* f64 [bean_svi_tiling_num_partials(G, E)] scratch */
+  uint32_t* counter;             /* u32 [1], zero before the first call */
+  double* loss;                  /* f64 [loss_capacity] */
+  const void* mu_prior_loc_v;    /* real [E] per-edit priors or NULL (BeanSviConfig scalars apply) */
+  const void* mu_prior_scale_v;
+  const void* sd_prior_loc_v;
+  const void* sd_prior_scale_v;
+  double epsilon;                /* the model's epsilon (1e-5) */
+  double pi_tiny;                /* lower clamp of the pi draws = smallest normal number of the dtype pi has in the reference */
+} BeanTilingState;
+typedef struct BeanTilingNoise { /* all optional */
+  const void* eps_mu;            /* real [E] */
+  const void* eps_sd;            /* real [E] */
+  const double* pi;              /* f64 [R][G][A] */
+  void* eps_out;                 /* real [2][E] out */
+  double* pi_out;                /* f64 [R][G][A] out */
+} BeanTilingNoise;
+int bean_svi_tiling_num_partials(int32_t n_guides, int32_t n_edits);
+int bean_svi_tiling_run_f32(const BeanScreen* screen, const BeanTilingState* state, const BeanSviConfig* cfg, const BeanTilingNoise* noise,
+                            int32_t first_step, int32_t n_steps, void* stream);
+int bean_svi_tiling_run_f64(const BeanScreen* screen, const BeanTilingState* state, const BeanSviConfig* cfg, const BeanTilingNoise* noise,
+                            int32_t first_step, int32_t n_steps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Editing-rate sites of the MultiMixtureNormal (tiling) and survival MixtureNormal programs: forward value and local

@@ -60,7 +60,11 @@ def main():
                  O.elbo_mixture_normal, {}))
     d = dc.TilingSortingReporterScreenData(make_tiling_screen(n_guides=800, max_alleles=16, n_reps=4, seed=3),
                                            control_can_be_selected=True, allele_df_key="allele_counts")
-    rows.append((f"c3 tiling MultiMixtureNormal (800 guides x {d.n_max_alleles} alleles, {d.n_edits} edits)", d,
+    from crispr_bean_b200.tiling_fused import TilingFusedEngine
+
+    rows.append((f"c3 tiling MultiMixtureNormal (800 guides x {d.n_max_alleles} alleles, {d.n_edits} edits), fused step", d,
+                 TilingFusedEngine(d, dev, num_steps=100), O.elbo_multi_mixture_normal, {}))
+    rows.append((f"c3 tiling MultiMixtureNormal (800 guides x {d.n_max_alleles} alleles, {d.n_edits} edits), site-kernel engine (round 1)", d,
                  TilingSviEngine(d, dev, num_steps=100), O.elbo_multi_mixture_normal, {}))
     d = dc.VariantSurvivalReporterScreenData(make_survival_screen(690, "lognormal", n_reps=3, seed=21, n_negctrl_guides=101),
                                              control_condition="D7")

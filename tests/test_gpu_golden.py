@@ -42,8 +42,11 @@ def make_engine(z, data, cuda_device, dtype, num_steps, autograd_engine=False):
 
         return CovariateNormalEngine(data, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True))
     if getattr(data, "is_tiling", False):
+        from crispr_bean_b200 import tiling_fused
         from crispr_bean_b200.generic import TilingSviEngine
 
+        if tiling_fused.supports(data, acc["scale_by_accessibility"]) and not autograd_engine:  # what run_inference uses
+            return tiling_fused.TilingFusedEngine(data, cuda_device, dtype=dtype, num_steps=num_steps)
         return TilingSviEngine(data, cuda_device, dtype=dtype, num_steps=num_steps, **acc)
     return SviEngine(data, model, cuda_device, dtype=dtype, num_steps=num_steps, use_bcmatch=kw.get("use_bcmatch", True),
                      scale_by_accessibility=kw.get("scale_by_accessibility", False), fit_noise=kw.get("fit_noise", False),
