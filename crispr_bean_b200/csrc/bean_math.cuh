@@ -241,15 +241,26 @@ __device__ __forceinline__ float2 log1p_ratio_series2(float2 y) {
 }
 
 __device__ __forceinline__ double digamma_f64(double z) {
-  // recurrence up to z >= 10, then the asymptotic series (7 Bernoulli terms)
-  double sub = 0.0, zs = z;
-  while (zs < 10.0) {
-    sub += 1.0 / zs;
-    zs += 1.0;
+  // Cephes psi for z > 0 -- recurrence up to 10, then the asymptotic series with 7 Bernoulli terms -- summed IN THE ORDER
+  // torch's CPU digamma sums it (the negative recurrence terms first, then + log - 1/2x - series, left to right).  The order is
+  // part of fp64 parity: for the ~1e-7 concentrations of non-existent tiling alleles psi is ~ -1e7 (ulp 1.9e-9) and the
+  // reference's pathwise Dirichlet derivative forms psi(a) + 1/a from it (model.py:937-938 through torch._dirichlet_grad), so
+  // a differently ordered -- even a more accurate -- sum moves alpha_pi's gradient by ~2e-9.
+  double result = 0.0, x = z;
+  while (x < 10.0) {
+    result -= 1.0 / x;
+    x += 1.0;
   }
-  const double rz = 1.0 / zs, r2 = rz * rz;
-  const double s = r2 * (1.0 / 12 + r2 * (-1.0 / 120 + r2 * (1.0 / 252 + r2 * (-1.0 / 240 + r2 * (1.0 / 132 + r2 * (-691.0 / 32760 + r2 * (1.0 / 12)))))));
-  return ::log(zs) - 0.5 * rz - s - sub;
+  if (x == 10.0) return result + 2.25175258906672110764;
+  const double r2 = 1.0 / (x * x);
+  double poly = 1.0 / 12;
+  poly = poly * r2 + (-691.0 / 32760);
+  poly = poly * r2 + (1.0 / 132);
+  poly = poly * r2 + (-1.0 / 240);
+  poly = poly * r2 + (1.0 / 252);
+  poly = poly * r2 + (-1.0 / 120);
+  poly = poly * r2 + (1.0 / 12);
+  return result + ::log(x) - (0.5 / x) - r2 * poly;
 }
 
 __device__ __forceinline__ void gamma_corr(double z, double& cv, double& dl) {

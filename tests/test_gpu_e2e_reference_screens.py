@@ -94,12 +94,13 @@ def test_2000_step_fp32_fit_matches_the_float64_reference_programs(cuda_device, 
     with H.default_dtype(oracle_dtype):
         d64 = H.cast_data(data, torch.float64) if oracle_dtype == torch.float64 else data
         ps, opt = O.ParamStore(), O.ClippedAdam(lr=0.01, lrd=0.1 ** (1 / n_steps))
-        fn(d64, ps, noise=draw_noise(model, data, _initial(model, data), torch.Generator().manual_seed(1)), **kw)  # creates the parameters
+        cast = (lambda n: n) if oracle_dtype == torch.float64 else (lambda n: {k: v.to(oracle_dtype) for k, v in n.items()})
+        fn(d64, ps, noise=cast(draw_noise(model, data, _initial(model, data), torch.Generator().manual_seed(1))), **kw)  # creates the parameters
         ref_loss = []
         for t in range(n_steps):
             noise = draw_noise(model, data, ps.constrained(), gen)
             eng.run(1, noise=noise)
-            loss, _ = fn(d64, ps, noise=noise, **kw)
+            loss, _ = fn(d64, ps, noise=cast(noise), **kw)
             ps.zero_grad()
             loss.backward()
             opt.step(ps.unconstrained)
