@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbean_b200.so")
+# BEAN_B200_LIB: an A/B build of the same library (tools/build_variants.sh), for kernel experiments on the GPU box only
+LIB_PATH = os.environ.get("BEAN_B200_LIB") or os.path.join(_PKG, "libbean_b200.so")
 
 BEAN_OK = 0
 MODE_SORTING, MODE_SURVIVAL = 0, 1

@@ -29,7 +29,7 @@ namespace bean {
 // one 128-bit load per row instead of NB constant-bank loads with computed addresses, and the sample-mask multiplies are
 // gone -- together a third of the instructions of the get_alpha section (profiles/r2b_guide_source_top.txt: that section,
 // not the special functions, was the largest single block of the kernel after the round-2 instruction diet).
-template <typename real, int NB, bool MIXTURE, bool ACC, bool SPLIT, bool FAST>
+template <typename real, int NB, bool MIXTURE, bool ACC, bool SPLIT, int FAST>
 __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(real) == 4) ? SVI_MIN_CTAS_SPLIT : SVI_MIN_CTAS) svi_guide_kernel(const SviParams<real> p) {
   __shared__ TailQueue<real> tail_queues[SPLIT ? 1 : SVI_THREADS / SVI_WARP];
   __shared__ __align__(16) real s_sf[FAST ? BEAN_MAX_LAYERS * BEAN_MAX_RB : 1];  // [l][r][b] size factors
@@ -46,12 +46,14 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
   __shared__ __align__(8) float2 s_ac[STAGE ? 2 * SVI_THREADS : 1];                    // [buffer][thread]
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = FAST ? NB : p.B;
+  constexpr bool LFIX = FAST == 2;  // both count layers present (all reads + barcode-matched reads): L is a constant
+  const int L = LFIX ? 2 : p.L;
   const real eps = real(1e-5);
   double elbo = 0.0;
   const int lane = threadIdx.x & 31;
   const unsigned wmask = __ballot_sync(0xffffffffu, g < p.G);  // lanes that own a guide: the warp-collective set below
   if (FAST) {
-    for (int i = threadIdx.x; i < p.L * R * NB; i += SVI_THREADS) s_sf[i] = p.t.sf[i / (R * NB)][i % (R * NB)];
+    for (int i = threadIdx.x; i < L * R * NB; i += SVI_THREADS) s_sf[i] = p.t.sf[i / (R * NB)][i % (R * NB)];
     __syncthreads();
   }
   if (g < p.G) {
@@ -121,9 +123,20 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
       mt1.init(cg[1]);
     }
     real elbo_g = real(0);
+#ifdef BEAN_HOIST_A0
+    constexpr bool HOIST = LFIX;
+#else
+    constexpr bool HOIST = false;
+#endif
+    real a0h0 = real(0), a0h1 = real(0);  // prior precision of the guide's two rows: replicate-independent
+    if (HOIST) {
+      a0h0 = p.a0[g];
+      a0h1 = p.a0[(size_t)p.G + g];
+    }
     auto stage = [&](int r) {  // rows of both layers + reporter counts of replicate r -> buffer r & 1
       const int buf = r & 1;
-      for (int l = 0; l < p.L; ++l)
+#pragma unroll(LFIX ? 2 : 1)
+      for (int l = 0; l < L; ++l)
         cp_async_16(&s_x[(buf * BEAN_MAX_LAYERS + l) * SVI_THREADS + threadIdx.x], p.x + (((size_t)l * R + r) * p.G + g) * 4);
       cp_async_8(&s_ac[buf * SVI_THREADS + threadIdx.x], p.allele_counts + ((size_t)r * p.G + g) * 2);
     };
@@ -173,7 +186,12 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         e[b] = MIXTURE ? q0 * p.p_wt[b] + q1 * P1[b] : P1[b];  // model.py:495-499
         de[b] = real(0);
       }
-      for (int l = 0; l < p.L; ++l) {
+#ifdef BEAN_UNROLL_LAYERS
+#pragma unroll(LFIX ? 2 : 1)
+#else
+#pragma unroll 1
+#endif
+      for (int l = 0; l < L; ++l) {
         // x[l][r][g][b]: the rows of 32 consecutive guides are contiguous, so a warp's loads coalesce; with B = 4 a row
         // is one 128-bit load
         const real* xr = p.x + (((size_t)l * R + r) * p.G + g) * B;
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
           S += pb[b];
         }
         if (!(rmask && N > p.mask_thres)) continue;  // poutine.mask: the row contributes nothing
-        const real a0 = p.a0[(size_t)l * p.G + g];
+        const real a0 = HOIST ? (l == 0 ? a0h0 : a0h1) : p.a0[(size_t)l * p.G + g];
         const real inv = Num<real>::rcp(S + eps);
         real Asum = real(0);
 #pragma unroll
@@ -395,16 +413,18 @@ static void launch_guide(const SviParams<real>& p, cudaStream_t st, bool guide, 
   const int grid = (p.G + SVI_THREADS - 1) / SVI_THREADS;
   constexpr bool HAS_FAST = true;
   if (!guide) {
-  } else if (HAS_FAST && fast && p.B == 4)
-    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, HAS_FAST><<<grid, SVI_THREADS, 0, st>>>(p);
+  } else if (HAS_FAST && fast && p.B == 4 && p.L == 2)
+    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 2><<<grid, SVI_THREADS, 0, st>>>(p);
+  else if (HAS_FAST && fast && p.B == 4)
+    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 1><<<grid, SVI_THREADS, 0, st>>>(p);
   else if (HAS_FAST && fast && p.B == 5)
-    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, HAS_FAST><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, 1><<<grid, SVI_THREADS, 0, st>>>(p);
   else if (p.B <= 4)
-    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, false><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 0><<<grid, SVI_THREADS, 0, st>>>(p);
   else if (p.B == 5)
-    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, false><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, 0><<<grid, SVI_THREADS, 0, st>>>(p);
   else
-    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC, SPLIT, false><<<grid, SVI_THREADS, 0, st>>>(p);
+    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC, SPLIT, 0><<<grid, SVI_THREADS, 0, st>>>(p);
   // (one thread per (guide, replicate) with a shuffle reduction was tried for this kernel: 0.42 vs 0.27 ms)
   if (MIXTURE && SPLIT && alpha) svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
 }

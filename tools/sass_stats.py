@@ -9,7 +9,7 @@ import re
 import subprocess
 import sys
 
-so = "crispr_bean_b200/libbean_b200.so"
+so = __import__('os').environ.get('SO', 'crispr_bean_b200/libbean_b200.so')
 key = sys.argv[1]
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 blocks = re.split(r"\n\s*Function : ", txt)
