@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("BEAN_B200_LIB") or os.path.join(_PKG, "libbean_b200.s
 BEAN_OK = 0
 MODE_SORTING, MODE_SURVIVAL = 0, 1
 MAX_BINS, MAX_RB, MAX_ALLELES, MAX_LAYERS = 8, 64, 4096, 2
+SURV_FOLD_ROWS = 1024  # BEAN_SURV_FOLD_ROWS
 
 
 class BeanError(RuntimeError):
@@ -151,7 +152,7 @@ class BeanTilingNoise(C.Structure):
 
 SURV_PRIME_NONE, SURV_PRIME_AND_RUN, SURV_PRIME_ONLY = 0, 1, 2
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 11  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 12  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 

@@ -29,6 +29,26 @@ static __device__ __noinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// The same ten rounds with the round keys k + i (0x9E3779B9, 0xBB67AE85) handed in precomputed (by the host, in the kernel's
+// parameter block: each becomes a constant-bank operand of the round's LOP3), inlined: 4 instructions per round instead of 6
+// plus the call -- for the one call site that runs once per (guide, replicate).
+struct PhiloxKeys { uint32_t k[20]; };
+__device__ __forceinline__ uint4 philox4x32_10_keys(uint4 c, const PhiloxKeys& rk) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ rk.k[2 * i], lo1, hi0 ^ c.w ^ rk.k[2 * i + 1], lo0);
+  }
+  return c;
+}
+static inline void philox_round_keys(uint64_t seed, PhiloxKeys& rk) {
+  for (int i = 0; i < 10; ++i) {
+    rk.k[2 * i] = (uint32_t)seed + (uint32_t)i * 0x9E3779B9u;
+    rk.k[2 * i + 1] = (uint32_t)(seed >> 32) + (uint32_t)i * 0xBB67AE85u;
+  }
+}
+
 __device__ __forceinline__ uint2 seed_key(uint64_t seed) { return make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); }
 
 // uniform in (0, 1), 24 bits
@@ -104,7 +124,7 @@ template <> struct Lim<double> {
 // pi ~ Dirichlet(c0, c1) for guide g, replicate r at `step` (a Beta draw as two gammas).
 template <typename real>
 __device__ __forceinline__ void sample_pi2(uint64_t seed, uint32_t g, uint32_t r, uint32_t step, const GammaMT<real>& m0,
-                                           const GammaMT<real>& m1, real& pi0, real& pi1) {
+                                           const GammaMT<real>& m1, real& pi0, real& pi1, const PhiloxKeys* rk = nullptr) {
   const uint2 key = seed_key(seed);
   real s0 = real(1), s1 = real(1);
   if (m0.inv_alpha != real(0) || m1.inv_alpha != real(0)) {  // boost: Gamma(a) = Gamma(a + 1) * U^(1/a)
@@ -115,7 +135,8 @@ __device__ __forceinline__ void sample_pi2(uint64_t seed, uint32_t g, uint32_t r
   real g0 = real(0), g1 = real(0);
   bool ok0 = false, ok1 = false;
   for (uint32_t k = 0; k < 32u && !(ok0 && ok1); ++k) {
-    const uint4 w = philox4x32_10(make_uint4(g, r, step, STREAM_PI + k), key);
+    const uint4 w = (rk && k == 0u) ? philox4x32_10_keys(make_uint4(g, r, step, STREAM_PI), *rk)
+                                    : philox4x32_10(make_uint4(g, r, step, STREAM_PI + k), key);  // retries (rare): out of line
     float n0, n1;
     box_muller(w.x, w.y, n0, n1);
     if (!ok0) ok0 = m0.attempt(n0, 1.0f - u01(w.z), g0);
@@ -465,24 +486,32 @@ struct SaddlePair {
 //   term1 + term2 (+-term4) = C2 D / delta^2 + beta (2 alpha - beta) / (s T^3 delta),   D = l(u) G^-1.5 - 1,
 //   C2 = 2 alpha beta^2 / (s T^4), s = sqrt(2 alpha beta / T); the 1 / delta term equals -C2 c1 / delta with
 //   c1 = T (2 alpha - beta) / (2 alpha beta) and D = -c1 delta + O(delta^2), so
-//   term1234 = C2 (D + c1 delta) / delta^2 - s l(u) / alpha,      D = (1 + l1(u)) (1 + expm1(-1.5 log1p(G1))) - 1.
+//   term1234 = C2 (D + c1 delta) / delta^2 - s l(u) / alpha,      D = (1 + l1(u)) (1 + [(1 + G1)^-1.5 - 1]) - 1.
 // l1 and g1 are series for small |y| (no cancellation), the defining expressions otherwise.  The second component is the
 // same with alpha <-> beta, u <-> v, delta -> -delta, and shares g1(u), g1(v), G.
 // (l1, g1)(y) = (log1p(y) / y - 1,  2 (y - log1p(y)) / y^2 - 1): series for small |y|, one shared log1p otherwise
 __device__ __forceinline__ void saddle_l1_g1(float y, float& l1, float& g1) {
   if (fabsf(y) < 0.3f) {
-    float p = 1.0f / 13.0f, q = 2.0f / 14.0f;
-#pragma unroll
-    for (int k = 12; k >= 2; --k) p = fmaf(p, y, (k & 1) ? 1.0f / k : -1.0f / k);
+    // ONE series: g1 = y q(y), q = -2/3 + 2y/4 - 2y^2/5 ...; and log1p(y)/y = 1 - y/2 (1 + g1) identically, so l1 = -y/2 (1 + g1)
+    float q = 2.0f / 14.0f;
 #pragma unroll
     for (int k = 13; k >= 3; --k) q = fmaf(q, y, (k & 1) ? -2.0f / k : 2.0f / k);
-    l1 = p * y;
     g1 = q * y;
+    l1 = -0.5f * y * (1.0f + g1);
   } else {
     const float lp = log1pf(y), iy = rcp_ftz(y);
     l1 = lp * iy - 1.0f;
     g1 = 2.0f * (y - lp) * iy * iy - 1.0f;
   }
+}
+
+// (1 + z)^-1.5 - 1 without cancellation and without libm: with q = sqrt(1 + z), e = 1/q - 1 = -z / (q (1 + q)) and
+// (1 + e)^3 - 1 = e (3 + e (3 + e)).  ~12 instructions against ~90 for expm1f(-1.5f * log1pf(z)); same worst error of the
+// assembled gradient (tests/test_saddle_float_form.py).
+__device__ __forceinline__ float pow_m15_minus1(float z) {
+  const float q = sqrtf(1.0f + z);
+  const float e = -z * rcp_ftz(q * (1.0f + q));
+  return e * (3.0f + e * (3.0f + e));
 }
 
 struct SaddlePairF {
@@ -524,7 +553,7 @@ struct SaddlePairF {
     float l1u, l1v, g1u, g1v;
     saddle_l1_g1(u, l1u, g1u);
     saddle_l1_g1(v, l1v, g1v);
-    const float wm1 = expm1f(-1.5f * log1pf(om * g1u + m * g1v));           // G^-1.5 - 1
+    const float wm1 = pow_m15_minus1(om * g1u + m * g1v);                   // G^-1.5 - 1
     const float D0 = l1u + wm1 + l1u * wm1, D1 = l1v + wm1 + l1v * wm1;    // (1 + l1)(1 + wm1) - 1
     const float id2 = rcp_ftz(d * d);
     const float t0 = C2a * (D0 + c1a * d) * id2 - s * (1.0f + l1u) * ia;

@@ -123,11 +123,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
       mt1.init(cg[1]);
     }
     real elbo_g = real(0);
-#ifdef BEAN_HOIST_A0
-    constexpr bool HOIST = LFIX;
-#else
-    constexpr bool HOIST = false;
-#endif
+    constexpr bool HOIST = LFIX;  // (-1 % of the kernel's time at c5, A/B in profiles/r2j_variants.jsonl)
     real a0h0 = real(0), a0h1 = real(0);  // prior precision of the guide's two rows: replicate-independent
     if (HOIST) {
       a0h0 = p.a0[g];
@@ -157,7 +153,11 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
           pi0 = p.pi_in[((size_t)g * R + r) * 2];
           pi1 = p.pi_in[((size_t)g * R + r) * 2 + 1];
         } else {
+#ifdef BEAN_PHILOX_PARAM_KEYS
+          sample_pi2(p.seed, (uint32_t)g + p.guide_offset, (uint32_t)r, p.step, mt0, mt1, pi0, pi1, &p.rk);
+#else
           sample_pi2(p.seed, (uint32_t)g + p.guide_offset, (uint32_t)r, p.step, mt0, mt1, pi0, pi1);
+#endif
         }
         if (p.pi_out) {
           p.pi_out[((size_t)g * R + r) * 2] = pi0;
@@ -311,6 +311,16 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
         // pathwise derivative of pi w.r.t. the guide concentration (torch _Dirichlet_backward)
         // evaluated in double even on the float path, as torch's CPU kernel does (accscalar_t = double):
         // the saddle-point branch cancels badly in float
+        if (SPLIT && sizeof(real) == 4) {
+          // go_a - (pi0 go0 + pi1 go1) without forming the weighted mean: with s = 1 - pi0 - pi1 (a few ulp: pi is a clamped,
+          // rounded normalisation) it equals s go_a + pi_b (go_a - go_b), where nothing cancels -- as accurate as the double
+          // evaluation rounded to float, in 6 FP32 instructions instead of 4 conversions + 4 FP64 operations
+          const real s = (real(1) - pi0) - pi1, dgo = go0 - go1;
+          typename Vec4<real>::type rec;
+          rec.x = pi0; rec.y = pi1; rec.z = fma(pi1, dgo, s * go0); rec.w = fma(pi0, -dgo, s * go1);
+          reinterpret_cast<typename Vec4<real>::type*>(p.pw)[(size_t)r * p.G + g] = rec;
+          continue;
+        }
         const double gbar = (double)pi0 * (double)go0 + (double)pi1 * (double)go1;
         const double w0 = (double)go0 - gbar, w1 = (double)go1 - gbar;
         if (SPLIT) {
@@ -458,6 +468,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.G = s->n_guides; p.R = s->n_reps; p.B = s->n_bins; p.L = s->n_layers; p.T = state->n_variants;
   p.mixture = mix; p.sd_is_sqrt = cfg->sd_is_sqrt; p.mu_prior_normal = cfg->mu_prior_normal; p.apply_update = cfg->apply_update;
   p.seed = cfg->seed;
+  philox_round_keys(p.seed, p.rk);
   p.guide_offset = cfg->guide_offset;
   p.variant_offset = cfg->variant_offset;
   p.mask_thres = real(s->mask_thres);

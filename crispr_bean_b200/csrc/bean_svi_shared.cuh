@@ -31,6 +31,7 @@ struct SviParams {
   int mixture, sd_is_sqrt, mu_prior_normal, apply_update, fit_noise;
   uint32_t step, guide_offset, variant_offset;
   uint64_t seed;
+  PhiloxKeys rk;  // Philox round keys of `seed` (philox_round_keys)
   real mask_thres;
   // screen
   const real* x;
@@ -209,30 +210,66 @@ __global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviPa
   alpha_update(p, g, al0, al1, pa0, cm0, cm1, dc.x, dc.y, dcg0, dcg1);
 }
 
+// Column sums of rows first, first + stride, ... (< n_rows) of a row-major [n_rows][C] array of doubles, C <= VAR_THREADS, by
+// one CTA of VAR_THREADS threads: thread t accumulates column t % C over every (VAR_THREADS / C)-th row of the set, the partial
+// sums meet in shared memory in a fixed order.  Every thread calls; thread j < C receives column j.
+__device__ __forceinline__ double column_sums(const double* a, int n_rows, int C, int first, int stride, double* s_cs) {
+  const int slots = VAR_THREADS / C, col = threadIdx.x % C, slot = threadIdx.x / C;
+  double acc = 0.0;
+  if (slot < slots)
+    for (long long row = first + (long long)slot * stride; row < n_rows; row += (long long)slots * stride) acc += __ldcg(a + row * C + col);
+  s_cs[threadIdx.x] = acc;
+  __syncthreads();
+  double tot = 0.0;
+  if ((int)threadIdx.x < C)
+    for (int m = 0; m < slots; ++m) tot += s_cs[m * C + threadIdx.x];
+  __syncthreads();
+  return tot;
+}
+
+// One step's per-variant work: the segmented sum of the guides' (d mu, d sd) over the variant's guide range (VAR_LANES lanes
+// per variant, coalesced), then -- compacted through shared memory so that the first warp runs it with every lane busy instead
+// of one lane in VAR_LANES -- the draw, priors, entropy and ClippedAdam of the variant.  Every CTA also folds its slice of the
+// guide kernel's ELBO partials into its own partial, so the last CTA's fixed-order reduction reads n_partial_var numbers, not
+// n_partial_guide + n_partial_var (31 k + 6 k at c5: that serial tail was a third of this kernel's time).
 template <typename real>
 __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParams<real> p) {
   __shared__ double red[32];
   __shared__ bool is_last;
-  const int v = blockIdx.x * VAR_PER_CTA + threadIdx.x / VAR_LANES;
+  __shared__ real s_d[2][VAR_PER_CTA];
+  __shared__ double s_cs[VAR_THREADS];
+  const int vl = threadIdx.x / VAR_LANES;
   const int sub = threadIdx.x % VAR_LANES;
-  const bool valid = v < p.T;
-  // segmented reduction of the guide gradients over the variant's contiguous guide range
-  real dmu = real(0), dsd = real(0);
-  if (valid) {
-    const int beg = p.variant_ptr[v], end = p.variant_ptr[v + 1];
-    for (int j = beg + sub; j < end; j += VAR_LANES) {
-      const int k = p.gather_idx ? p.gather_idx[j] : j;
-      dmu += p.d_guide[k];
-      if (p.has_sd) dsd += p.d_guide[(size_t)p.G + k];
+  {
+    const int v = blockIdx.x * VAR_PER_CTA + vl;
+    // segmented reduction of the guide gradients over the variant's contiguous guide range
+    real dmu = real(0), dsd = real(0);
+    if (v < p.T) {
+      const int beg = p.variant_ptr[v], end = p.variant_ptr[v + 1];
+      for (int j = beg + sub; j < end; j += VAR_LANES) {
+        const int k = p.gather_idx ? p.gather_idx[j] : j;
+        dmu += p.d_guide[k];
+        if (p.has_sd) dsd += p.d_guide[(size_t)p.G + k];
+      }
+    }
+#pragma unroll
+    for (int o = VAR_LANES / 2; o > 0; o >>= 1) {
+      dmu += __shfl_xor_sync(0xffffffffu, dmu, o);
+      dsd += __shfl_xor_sync(0xffffffffu, dsd, o);
+    }
+    if (sub == 0) {
+      s_d[0][vl] = dmu;
+      s_d[1][vl] = dsd;
     }
   }
-#pragma unroll
-  for (int o = VAR_LANES / 2; o > 0; o >>= 1) {
-    dmu += __shfl_xor_sync(0xffffffffu, dmu, o);
-    dsd += __shfl_xor_sync(0xffffffffu, dsd, o);
-  }
+  // this CTA's slice of the guide kernel's partials (fixed assignment: deterministic)
   double elbo = 0.0;
-  if (valid && sub == 0) {
+  for (int i = blockIdx.x * VAR_THREADS + threadIdx.x; i < p.n_partial_guide; i += gridDim.x * VAR_THREADS) elbo += p.partial[i];
+  __syncthreads();
+  const int v = blockIdx.x * VAR_PER_CTA + threadIdx.x;
+  if (threadIdx.x < VAR_PER_CTA && v < p.T) {
+    const real dmu = s_d[0][threadIdx.x];
+    real dsd = s_d[1][threadIdx.x];
     real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y;
     variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y);
     if (p.eps_out) {
@@ -260,7 +297,7 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
     // guide densities (entropy side)
     const real lq_mu = -Num<real>::log(mu_scale) - HL2PI - real(0.5) * e_mu * e_mu;
     const real lq_sd = -y - Num<real>::log(sd_scale) - HL2PI - real(0.5) * e_sd * e_sd;
-    elbo = (double)lp_mu - (double)lq_mu + (p.has_sd ? (double)lp_sd - (double)lq_sd : 0.0);
+    elbo += (double)lp_mu - (double)lq_mu + (p.has_sd ? (double)lp_sd - (double)lq_sd : 0.0);
     if (p.dsd_times_sd) dsd *= sd_t;  // sd_allele = sqrt(sum sd_edit^2): d sd_allele / d sd_edit = sd_edit / sd_allele
     const real dE_mu = dmu + dlp_mu;
     const real dE_sd = dsd + dlp_sd;
@@ -284,7 +321,20 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
       }
     }
   }
-  const double tot = block_sum(elbo, red);
+  // survival: the library-wide sums of the NEXT step's abundance draw (sum_g gamma[r][g], sum_g q0[g]) from the per-warp
+  // partials [n_abund_partial][R + 1] the guide kernel left, in two fixed-order levels: CTA b < M folds rows b, b + M, ...
+  // into row n_abund_partial + b (the buffer's BEAN_SURV_FOLD_ROWS spare rows), the last CTA sums those M rows.  With guides
+  // sharded over GPUs the host all-reduces these R + 1 numbers.
+  const int C = p.R + 1;
+  const int M = p.sums_next ? min(min((int)gridDim.x, BEAN_SURV_FOLD_ROWS), p.n_abund_partial) : 0;
+  if ((int)blockIdx.x < M) {
+    const double tot_j = column_sums(p.abund_partial, p.n_abund_partial, C, (int)blockIdx.x, M, s_cs);
+    if ((int)threadIdx.x < C) {
+      p.abund_partial[((size_t)p.n_abund_partial + blockIdx.x) * C + threadIdx.x] = tot_j;
+      __threadfence();
+    }
+  }
+  const double tot = block_sum(elbo, red);  // (its barriers also order the row written above before thread 0's fence)
   if (threadIdx.x == 0) {
     p.partial[p.n_partial_guide + blockIdx.x] = tot;
     __threadfence();
@@ -293,28 +343,29 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
   }
   __syncthreads();
   if (is_last) {
-    // last CTA: fixed-order reduction of every partial of this step -> loss[t] = -ELBO
+    // last CTA: fixed-order reduction of every CTA's partial of this step -> loss[t] = -ELBO
     __threadfence();
-    double acc = 0.0;
-    const int n = p.n_partial_guide + p.n_partial_var;
-    for (int i = threadIdx.x; i < n; i += VAR_THREADS) acc += p.partial[i];
-    const double all = block_sum(acc, red);
+    const double* pv = p.partial + p.n_partial_guide;
+    const int n = p.n_partial_var;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four loads in flight per thread
+    int i = threadIdx.x;
+    for (; i + 3 * VAR_THREADS < n; i += 4 * VAR_THREADS) {
+      a0 += __ldcg(pv + i);
+      a1 += __ldcg(pv + i + VAR_THREADS);
+      a2 += __ldcg(pv + i + 2 * VAR_THREADS);
+      a3 += __ldcg(pv + i + 3 * VAR_THREADS);
+    }
+    for (; i < n; i += VAR_THREADS) a0 += __ldcg(pv + i);
+    const double all = block_sum((a0 + a1) + (a2 + a3), red);
     if (threadIdx.x == 0) {
       p.loss[p.step] = -(all + p.ll_const);
       *p.counter = 0u;
     }
-    // survival: the library-wide sums of the NEXT step's abundance draw (sum_g gamma[r][g], sum_g q0[g]) from the per-warp
-    // partials the guide kernel left; fixed order.  With guides sharded over GPUs the host all-reduces these R + 1 numbers.
     if (p.sums_next) {
-      for (int j = 0; j <= p.R; ++j) {
-        double a = 0.0;
-        for (int i = threadIdx.x; i < p.n_abund_partial; i += VAR_THREADS) a += p.abund_partial[(size_t)i * (p.R + 1) + j];
-        const double tot_j = block_sum(a, red);
-        if (threadIdx.x == 0) p.sums_next[j] = tot_j;
-      }
+      const double tot_j = column_sums(p.abund_partial + (size_t)p.n_abund_partial * C, M, C, 0, 1, s_cs);
+      if ((int)threadIdx.x < C) p.sums_next[threadIdx.x] = tot_j;
     }
   }
 }
-
 
 }  // namespace bean

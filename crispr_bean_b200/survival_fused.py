@@ -74,7 +74,7 @@ class SurvivalFusedEngine:
         self.sums = [torch.zeros(R + 1, dtype=torch.float64, device=dev), torch.zeros(R + 1, dtype=torch.float64, device=dev)]
         n_partial = self.lib.bean_svi_num_partials(G, T)
         self.partial = torch.zeros(n_partial, dtype=torch.float64, device=dev)
-        self.abund_partial = torch.zeros(((G + 127) // 128 * 4, R + 1), dtype=torch.float64, device=dev)
+        self.abund_partial = torch.zeros(((G + 127) // 128 * 4 + _lib.SURV_FOLD_ROWS, R + 1), dtype=torch.float64, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss = torch.zeros(max(self.num_steps, 1) + 1, dtype=torch.float64, device=dev)
         self.pw, self.dconc = torch.empty((R, G, 4), **kw), torch.empty((G, 4), **kw)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 11
+#define BEAN_ABI_VERSION 12
 
 enum {
   BEAN_OK = 0,
@@ -48,6 +48,7 @@ enum { BEAN_MODE_SORTING = 0, BEAN_MODE_SURVIVAL = 1 };
 #define BEAN_MAX_RB 64         /* n_reps * n_bins per guide */
 #define BEAN_MAX_ALLELES 4096  /* alleles per guide incl. wild type (raw tiling allele tables reach hundreds) */
 #define BEAN_MAX_LAYERS 2
+#define BEAN_SURV_FOLD_ROWS 1024 /* spare rows of BeanSurvivalState.abund_partial (second level of the abundance sums) */
 
 int bean_abi_version(void);
 const char* bean_last_error(void);
@@ -275,7 +276,7 @@ typedef struct BeanSurvivalState {
   void* q0_grad;                 /* real [G] out or NULL */
   void* gamma[2];                /* real [R][G] x 2: unnormalised abundance draws of even / odd steps */
   double* sums[2];               /* f64 [R + 1] x 2: sum_g gamma[r][g] (r < R), sum_g q0[g] */
-  double* abund_partial;         /* f64 [ceil(G / 128) * 4][R + 1] scratch */
+  double* abund_partial;         /* f64 [ceil(G / 128) * 4 + BEAN_SURV_FOLD_ROWS][R + 1] scratch */
 } BeanSurvivalState;
 typedef struct BeanSurvivalNoise { /* optional injected noise of the survival-only sites (parity runs) */
   const void* eps_negctrl;       /* real [G] standard-normal draw behind mu_negctrl */

@@ -43,14 +43,25 @@ def test_fused_step_equals_oracle(cuda_device, dtype, tol, shape):
         loss, _ = O.elbo_multi_mixture_normal(d, ps, noise=noise)
         ps.zero_grad()
         loss.backward()
+        # how well float64 itself defines alpha_pi's gradient here: the same formula evaluated a second time on the CPU in another
+        # order (oracle/tiling_closed_form.py, numpy, the same torch._dirichlet_grad).  With 16 alleles most of a guide's
+        # alleles do not exist, their concentrations are ~1e-6, and torch's pathwise derivative forms psi(c) + 1/c from two
+        # numbers of size 1e6 for each: two float64 evaluations agree to ~6e-10 only (800 x 16; 1e-12 at 120 x 8).
+        from oracle import tiling_closed_form as TC
+
+        _, closed = TC.tiling_step(d, {k: v.detach() for k, v in ps.unconstrained.items()}, noise)
+        floor = rel_err(torch.as_tensor(closed["alpha_pi"]).reshape(ps.unconstrained["alpha_pi"].shape), ps.unconstrained["alpha_pi"].grad)
     ref = float(loss.detach())
     errs = {"loss": abs(got["loss"].item() - ref) / abs(ref)}
     for k, v in ps.unconstrained.items():
         errs[k] = rel_err(got[k], v.grad)
-    print(dtype, shape, errs)
+    print(dtype, shape, errs, "float64 floor of alpha_pi", floor)
     assert errs["loss"] <= tol
     for k, e in errs.items():
-        assert e <= (10 * tol if dtype == torch.float32 else tol), (k, e)
+        bound = 10 * tol if dtype == torch.float32 else tol
+        if k == "alpha_pi":
+            bound = max(bound, 5 * floor)
+        assert e <= bound, (k, e, bound)
 
 
 def test_fused_steps_equal_autograd_engine_steps(cuda_device):

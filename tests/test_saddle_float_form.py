@@ -14,11 +14,18 @@ def series(y, first_k, last_k, coef):
     return f(acc * y)
 
 
-def l1(y):  # log1p(y) / y - 1
+def l1(y):  # log1p(y) / y - 1  (small |y|: from the g1 series, log1p(y) / y = 1 - y / 2 (1 + g1) identically)
     y = f(y)
     if abs(y) < 0.3:
-        return series(y, 2, 13, lambda k: (1.0 if k % 2 else -1.0) / k)
+        return f(f(-0.5) * y * f(f(1) + g1(y)))
     return f(np.log1p(y) / y - f(1))
+
+
+def pow_m15_minus1(z):  # (1 + z)^-1.5 - 1 = e (3 + e (3 + e)), e = 1 / sqrt(1 + z) - 1 = -z / (q (1 + q))
+    z = f(z)
+    q = f(np.sqrt(f(f(1) + z)))
+    e = f(-z / f(q * f(f(1) + q)))
+    return f(e * f(f(3) + f(e * f(f(3) + e))))
 
 
 def g1(y):  # 2 (y - log1p(y)) / y^2 - 1
@@ -49,7 +56,7 @@ def saddle_pair_f32(x0, a, b):
     c1a, c1b = h * (2 * a - b), h * (2 * b - a)
     l1u, l1v = l1(u), l1(v)
     G1 = om * g1(u) + m * g1(v)
-    wm1 = np.expm1(f(-1.5) * np.log1p(G1))  # G^-1.5 - 1
+    wm1 = pow_m15_minus1(G1)  # G^-1.5 - 1
     D0, D1 = l1u + wm1 + l1u * wm1, l1v + wm1 + l1v * wm1  # (1 + l1)(1 + wm1) - 1
     t0 = C2a * (D0 + c1a * d) / (d * d) - s * (1 + l1u) / a
     t1 = C2b * (D1 - c1b * d) / (d * d) - s * (1 + l1v) / b
