@@ -183,20 +183,30 @@ __device__ __forceinline__ real beta_grad_alpha_small(real x, real alpha, real b
 // double: torch's expression AS WRITTEN (factor + 1 / (alpha + i) with factor = psi(alpha) - psi(alpha + beta) - ln x).  For
 // tiny concentrations (non-existent tiling alleles: ~1e-7) its cancellation costs the reference ~1e-9 of relative accuracy,
 // and fp64 parity means reproducing that number, not the better one.
-template <>
-__device__ __forceinline__ double beta_grad_alpha_small<double>(double x, double alpha, double beta) {
-  const double factor = digamma_f64(alpha) - digamma_f64(alpha + beta) - ::log(x);
+// `psi_diff` = psi(alpha) - psi(alpha + beta): a caller that evaluates many draws of one concentration vector passes it in
+// (NaN = compute it here); it is O(1) accurate either way -- the cancellation is between psi(alpha) and 1 / alpha below.
+__device__ __forceinline__ double beta_grad_alpha_small_f64(double x, double alpha, double beta, double psi_diff) {
+  if (isnan(psi_diff)) psi_diff = digamma_f64(alpha) - digamma_f64(alpha + beta);
+  const double factor = psi_diff - ::log(x);
   double numer = 1.0;
   double series = numer / alpha * (factor + 1.0 / alpha);
 #pragma unroll 1
   for (int i = 1; i <= 10; ++i) {
     const double ci = (double)i;
     numer *= (ci - beta) * x / ci;
+    // draws of absent alleles sit at ~1e-300: numer underflows, and every division by a denormal takes the FP64 divide's slow
+    // path (30 % of the fused tiling kernel's instructions before this line).  Terms below 1e-280 cannot change `series`,
+    // whose first term is >= (-ln x) / alpha ~ 600 / alpha there: the result is bit-identical.
+    if (::fabs(numer) < 1e-280) break;
     const double denom = alpha + ci;
     series += numer / denom * (factor + 1.0 / denom);
   }
   const double result = x * ::pow(1.0 - x, -beta) * series;
   return isnan(result) ? 0.0 : result;
+}
+template <>
+__device__ __forceinline__ double beta_grad_alpha_small<double>(double x, double alpha, double beta) {
+  return beta_grad_alpha_small_f64(x, alpha, beta, nan(""));
 }
 
 // x near 0, derivative w.r.t. beta (torch: _beta_grad_beta_small)
@@ -303,14 +313,11 @@ __device__ __forceinline__ double beta_grad_alpha_mid<double>(double x, double a
   return prefactor * stirling * term1234;
 }
 
-// -(d/dalpha cdf(x; alpha, total - alpha)) / pdf / (1 - x): what torch._dirichlet_grad evaluates per element.
+// torch's rational correction to the asymptotic approximation x (psi(total) - psi(alpha)) / beta (dirichlet_grad_one, table
+// c[2][3][3][4]); `dpsi` = psi(total) - psi(alpha)
 template <typename real>
-__device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real total) {
+__device__ __forceinline__ real dirichlet_grad_rational(real x, real alpha, real total, real dpsi) {
   const real beta = total - alpha;
-  const real boundary = total * x * (real(1) - x);
-  if (x <= real(0.5) && boundary < real(2.5)) return beta_grad_alpha_small(x, alpha, beta);
-  if (x >= real(0.5) && boundary < real(0.75)) return -beta_grad_beta_small(real(1) - x, beta, alpha);
-  if (alpha > real(6) && beta > real(6)) return beta_grad_alpha_mid(x, alpha, beta);
   // rational-correction coefficients (torch: dirichlet_grad_one, table c[2][3][3][4])
   constexpr double kDirGradC[2][3][3][4] = {
     {{{1.003668233, -0.01061107488, -0.0657888334, 0.01201642863},
@@ -347,8 +354,19 @@ __device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real tota
       q += ua * (real(kDirGradC[1][i][j][0]) + b * (real(kDirGradC[1][i][j][1]) + b * (real(kDirGradC[1][i][j][2]) + b * real(kDirGradC[1][i][j][3]))));
     }
   }
-  const real approx = x * (digamma_full(total) - digamma_full(alpha)) / beta;
+  const real approx = x * dpsi / beta;
   return p / q * approx;
+}
+
+// -(d/dalpha cdf(x; alpha, total - alpha)) / pdf / (1 - x): what torch._dirichlet_grad evaluates per element.
+template <typename real>
+__device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real total) {
+  const real beta = total - alpha;
+  const real boundary = total * x * (real(1) - x);
+  if (x <= real(0.5) && boundary < real(2.5)) return beta_grad_alpha_small(x, alpha, beta);
+  if (x >= real(0.5) && boundary < real(0.75)) return -beta_grad_beta_small(real(1) - x, beta, alpha);
+  if (alpha > real(6) && beta > real(6)) return beta_grad_alpha_mid(x, alpha, beta);
+  return dirichlet_grad_rational<real>(x, alpha, total, digamma_full(total) - digamma_full(alpha));
 }
 
 // Single out-of-line copies (code size: the SVI kernel lives or dies by its instruction-cache footprint -- with
@@ -358,6 +376,16 @@ __device__ __forceinline__ real dirichlet_grad_one(real x, real alpha, real tota
 //   the saddle-point regime alone in double.
 static __device__ __noinline__ double dirichlet_grad_one_f64(double x, double alpha, double total) {
   return dirichlet_grad_one<double>(x, alpha, total);
+}
+// The same with psi(total) - psi(alpha) supplied (replicate-independent: the tiling kernel has it from the Dirichlet sites): the
+// boundary series and the rational regime need exactly this difference; the other two regimes do not use digamma at all.
+static __device__ __noinline__ double dirichlet_grad_one_f64_psi(double x, double alpha, double total, double psi_total_minus_alpha) {
+  const double beta = total - alpha;
+  const double boundary = total * x * (1.0 - x);
+  if (x <= 0.5 && boundary < 2.5) return beta_grad_alpha_small_f64(x, alpha, beta, -psi_total_minus_alpha);
+  if (x >= 0.5 && boundary < 0.75) return -beta_grad_beta_small(1.0 - x, beta, alpha);
+  if (alpha > 6.0 && beta > 6.0) return beta_grad_alpha_mid<double>(x, alpha, beta);
+  return dirichlet_grad_rational<double>(x, alpha, total, psi_total_minus_alpha);
 }
 static __device__ __noinline__ float dirichlet_grad_tail_f32(float x, float alpha, float total) {
   return dirichlet_grad_one<float>(x, alpha, total);

@@ -140,8 +140,18 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
       stage(0);
       cp_async_commit();
     }
+#ifdef BEAN_RMASK_BITS
+    // repguide_mask of all replicates up front: R independent byte loads in flight at once (replicate-major: a warp reads 32
+    // consecutive bytes each) instead of one exposed load latency per replicate
+    uint32_t rmask_bits = 0u;
+    for (int r = 0; r < R; ++r) rmask_bits |= (p.row_mask[(size_t)r * p.G + g] != 0 ? 1u : 0u) << r;
+#endif
     for (int r = 0; r < R; ++r) {
+#ifdef BEAN_RMASK_BITS
+      const bool rmask = (rmask_bits >> r) & 1u;
+#else
       const bool rmask = p.row_mask[(size_t)r * p.G + g] != 0;  // replicate-major: a warp reads 32 consecutive bytes
+#endif
       if (STAGE) {
         if (r + 1 < R) stage(r + 1);
         cp_async_commit();   // one group per iteration (possibly empty), so that "all but the newest" = replicate r has landed
@@ -153,11 +163,9 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
           pi0 = p.pi_in[((size_t)g * R + r) * 2];
           pi1 = p.pi_in[((size_t)g * R + r) * 2 + 1];
         } else {
-#ifdef BEAN_PHILOX_PARAM_KEYS
+          // first proposal through the inlined Philox with host-made round keys: -3 % of the kernel's time at c5
+          // (profiles/r2k_variants.jsonl)
           sample_pi2(p.seed, (uint32_t)g + p.guide_offset, (uint32_t)r, p.step, mt0, mt1, pi0, pi1, &p.rk);
-#else
-          sample_pi2(p.seed, (uint32_t)g + p.guide_offset, (uint32_t)r, p.step, mt0, mt1, pi0, pi1);
-#endif
         }
         if (p.pi_out) {
           p.pi_out[((size_t)g * R + r) * 2] = pi0;

@@ -169,8 +169,11 @@ template <> struct SaddleOf<double> { typedef SaddlePair type; };
 // Second half of the split guide step: pathwise Dirichlet derivative of every draw (saddle-point pairs in place, the other
 // regimes through the per-warp queue), alpha_pi gradient and its ClippedAdam update.  One thread per guide.
 constexpr int ALPHA_THREADS = 128;
+#ifndef BEAN_ALPHA_MIN_CTAS
+#define BEAN_ALPHA_MIN_CTAS 6
+#endif
 template <typename real>
-__global__ void __launch_bounds__(ALPHA_THREADS, 6) svi_alpha_kernel(const SviParams<real> p) {
+__global__ void __launch_bounds__(ALPHA_THREADS, BEAN_ALPHA_MIN_CTAS) svi_alpha_kernel(const SviParams<real> p) {
   __shared__ TailQueue<real> tail_queues[ALPHA_THREADS / SVI_WARP];
   const int g = blockIdx.x * ALPHA_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31;

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(TILING_WARPS * 32) tiling_guide_kernel(const T
     }
     // ---- pathwise derivative of the draw w.r.t. the guide concentration (torch _Dirichlet_backward)
     const double dot = warp_all_sum(has ? pi_a * go : 0.0);
-    if (has) dcg += dirichlet_grad_one_f64(pi_a, cg, sum_g) * (go - dot);
+    if (has) dcg += dirichlet_grad_one_f64_psi(pi_a, cg, sum_g, dgd_g) * (go - dot);
   }
   elbo += lane == 0 ? (double)n_in * norm_diff : 0.0;
   // ---- d ELBO / d (allele mean, sd) into the allele's slot; the per-edit kernel reduces the slots over the CSC map

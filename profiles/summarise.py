@@ -23,7 +23,9 @@ def ncu(rep, *args):
 
 
 def metrics(rep, title, out):
-    rows = list(csv.reader(ncu(rep, "--page", "raw", "--csv").splitlines()))
+    # the .ncu-rep, or the raw page already exported on the GPU box (tools/ncu_export.sh: gpurun brings back <= 64 MiB)
+    text = open(rep).read() if rep.endswith(".csv") else ncu(rep, "--page", "raw", "--csv")
+    rows = list(csv.reader(l for l in text.splitlines() if l.startswith('"')))
     d = {h: (rows[2][i], rows[1][i]) for i, h in enumerate(rows[0])}
     lines = [title]
     for k in KEEP + sorted(k for k in d if "issue_stalled" in k and "per_issue_active" in k and "not_issued" not in k):
@@ -37,14 +39,22 @@ def metrics(rep, title, out):
 
 def main(tag):
     g = os.path.join(ROOT, "gpurun_out")
-    for kern in ("guide", "alpha"):
+    what = {"guide": "svi_guide_kernel, c5 (1M guides x 8 x 4), step 500 of profiles/steady_state.py 600 (steady state)",
+            "alpha": "svi_alpha_kernel, c5 (1M guides x 8 x 4), step 500 of profiles/steady_state.py 600 (steady state)",
+            "surv_guide": "surv_guide_kernel, c4 at scale (1M guides x 3 x 3), step 200 of profiles/survival_steady.py 300",
+            "tiling_guide": "tiling_guide_kernel, c3 (800 guides x <= 16 alleles x 4 replicates), step 100 of profiles/tiling_steady.py 200"}
+    for kern in ("guide", "alpha", "surv_guide", "tiling_guide"):
         rep = f"{g}/prof_{tag}_{kern}.ncu-rep"
-        if not os.path.exists(rep):
+        exported = f"{g}/prof_{tag}_{kern}_raw.csv"
+        if not os.path.exists(rep) and not os.path.exists(exported):
             continue
-        metrics(rep, f"ncu --set full --clock-control none, svi_{kern}_kernel, c5 (1M guides x 8 x 4), step 500 of profiles/steady_state.py 600 "
-                     f"(steady state), capture {tag}", f"{ROOT}/profiles/{tag}_{kern}_metrics.txt")
-        src = f"{g}/src_{tag}_{kern}.csv"
-        open(src, "w").write(ncu(rep, "--page", "source", "--csv", "--print-source", "cuda,sass"))
+        title = f"ncu --set full --clock-control none, {what[kern]}, capture {tag}"
+        src = f"{g}/prof_{tag}_{kern}_src.csv"
+        if os.path.exists(rep):
+            metrics(rep, title, f"{ROOT}/profiles/{tag}_{kern}_metrics.txt")
+            open(src, "w").write(ncu(rep, "--page", "source", "--csv", "--print-source", "cuda,sass"))
+        else:
+            metrics(exported, title, f"{ROOT}/profiles/{tag}_{kern}_metrics.txt")
         top = subprocess.run([sys.executable, f"{ROOT}/profiles/agg_source.py", src, "40"], capture_output=True, text=True).stdout
         open(f"{ROOT}/profiles/{tag}_{kern}_source_top.txt", "w").write(top)
     launches = f"{g}/launches_{tag}.csv"
