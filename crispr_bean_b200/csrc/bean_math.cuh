@@ -190,15 +190,10 @@ __device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
 
 // (cv, dl, 1/z) of z.x and z.y
 __device__ __forceinline__ void gamma_corr2(float2 z, float2& cv, float2& dl, float2& iz) {
-#ifdef BEAN_GAMMA_FSET
   // z + [z < 1] as a float (FSET.BF) and ONE packed add, instead of add + compare + select per component
   const float bx = z.x < 1.0f ? 1.0f : 0.0f, by = z.y < 1.0f ? 1.0f : 0.0f;
   const float2 zs = add2(z, make_float2(bx, by));
   const bool sx = bx != 0.0f, sy = by != 0.0f;
-#else
-  const bool sx = z.x < 1.0f, sy = z.y < 1.0f;
-  const float2 zs = make_float2(sx ? z.x + 1.0f : z.x, sy ? z.y + 1.0f : z.y);
-#endif
   const float2 w = make_float2(rcp_ftz(zs.x), rcp_ftz(zs.y));
   const float2 s = mul2(w, w);
   float2 q = splat2(-4.973261975e-05f), r = splat2(3.128883582e-04f);

@@ -140,18 +140,9 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
       stage(0);
       cp_async_commit();
     }
-#ifdef BEAN_RMASK_BITS
-    // repguide_mask of all replicates up front: R independent byte loads in flight at once (replicate-major: a warp reads 32
-    // consecutive bytes each) instead of one exposed load latency per replicate
-    uint32_t rmask_bits = 0u;
-    for (int r = 0; r < R; ++r) rmask_bits |= (p.row_mask[(size_t)r * p.G + g] != 0 ? 1u : 0u) << r;
-#endif
     for (int r = 0; r < R; ++r) {
-#ifdef BEAN_RMASK_BITS
-      const bool rmask = (rmask_bits >> r) & 1u;
-#else
+      // (all R mask bytes loaded up front into a bit mask was tried: +1 %, profiles/r2l_variants.jsonl)
       const bool rmask = p.row_mask[(size_t)r * p.G + g] != 0;  // replicate-major: a warp reads 32 consecutive bytes
-#endif
       if (STAGE) {
         if (r + 1 < R) stage(r + 1);
         cp_async_commit();   // one group per iteration (possibly empty), so that "all but the newest" = replicate r has landed

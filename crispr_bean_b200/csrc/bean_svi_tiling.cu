@@ -5,7 +5,8 @@
 // oracle/tiling_closed_form.py):
 //
 //   tiling_draw_kernel   one thread per edit: reparameterised draws mu_e ~ Normal, sd_e ~ LogNormal (counter-based noise).
-//   tiling_guide_kernel  one WARP per guide, one LANE per allele (wild type + up to 31 edited alleles): allele mean / sd from
+//   tiling_guide_kernel  one CTA per guide, one WARP per replicate (+ one for the Dirichlet normalisers), one LANE per allele
+//       (wild type + up to 31 edited alleles): allele mean / sd from
 //       its edits through the CSR map (the reference's dense (G, A-1, E) matmul / norm, model.py:618-625), Normal-CDF bin masses
 //       per allele, per replicate: pi ~ Dirichlet draw (one gamma per lane, normalised by a warp sum), allele mixture by warp
 //       reductions over the alleles, get_alpha + Dirichlet-Multinomial rows of the count layers (evaluated identically by all
@@ -24,7 +25,7 @@
 
 namespace bean {
 
-constexpr int TILING_WARPS = 4;  // guides per CTA
+constexpr int TILING_MAX_REP_WARPS = 8;  // replicate warps per guide (CTA = these + one site warp)
 enum : uint32_t { STREAM_TILING_PI = 96 };
 
 template <typename real>
@@ -101,12 +102,22 @@ __global__ void __launch_bounds__(VAR_THREADS) tiling_draw_kernel(const SviParam
   sd_e[e] = sd_t;
 }
 
-template <typename real>
-__global__ void __launch_bounds__(TILING_WARPS * 32) tiling_guide_kernel(const TilingParams<real> p) {
-  constexpr int NB = BEAN_MAX_BINS;
-  const int lane = threadIdx.x & 31;
-  const int g = blockIdx.x * TILING_WARPS + (threadIdx.x >> 5);
-  if (g >= p.G) return;  // warp-uniform
+// One CTA per guide, NW = blockDim / 32 warps: warp w takes replicates w, w + NW, ... (draw, allele mixture, count rows,
+// editing-rate sites, pathwise derivative); the last warp then adds the replicate-independent normalisers of the two Dirichlet
+// sites (lgamma / digamma of the model's concentrations).  The kernel is bound by the LATENCY of its double-precision chains
+// (800 guides = 5 warps per SM with a warp per guide: 78 us at c3), so the host picks the largest NW whose warps are all
+// resident at once (tiling_run) and the replicates run side by side instead of one after the other.  The warps' accumulators
+// meet in shared memory and warp 0 adds them in a fixed order (deterministic), then does the per-allele epilogue.  Every warp
+// repeats the cheap prologue (concentrations, allele mean / sd, bin masses).
+template <typename real, int NB>
+__global__ void __launch_bounds__(TILING_MAX_REP_WARPS * 32) tiling_guide_kernel(const TilingParams<real> p) {
+  __shared__ double s_elbo[TILING_MAX_REP_WARPS][32], s_slp[TILING_MAX_REP_WARPS][32], s_path[TILING_MAX_REP_WARPS][32];
+  __shared__ real s_dP[TILING_MAX_REP_WARPS][NB][32];
+  __shared__ int s_nin[TILING_MAX_REP_WARPS];
+  __shared__ double s_dgd_m[32], s_norm_diff;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NW = (int)(blockDim.x >> 5);
+  const int g = blockIdx.x;
   const int R = p.R, B = p.B, A = p.A, C = p.C;
   const bool has = lane < A;
   const bool exists = has && p.allele_mask[(size_t)g * A + lane] != 0;
@@ -120,9 +131,8 @@ __global__ void __launch_bounds__(TILING_WARPS * 32) tiling_guide_kernel(const T
   const double cm_raw = has ? (al + eps / A) / S1 * pa0 : 1.0;
   const bool cm_live = cm_raw >= eps;              // `pi_a_scaled[pi_a_scaled < eps] = eps` (model.py:651): no gradient there
   const double cm = cm_live ? cm_raw : eps;
-  const double sum_g = warp_all_sum(has ? cg : 0.0), sum_m = warp_all_sum(has ? cm : 0.0);
-  const double dgd_g = digamma_f64(sum_g) - digamma_f64(cg), dgd_m = digamma_f64(sum_m) - digamma_f64(cm);  // psi(sum) - psi(c_a)
-  const double norm_diff = (::lgamma(sum_m) - warp_all_sum(has ? ::lgamma(cm) : 0.0)) - (::lgamma(sum_g) - warp_all_sum(has ? ::lgamma(cg) : 0.0));
+  const double sum_g = warp_all_sum(has ? cg : 0.0);
+  const double dgd_g = digamma_f64(sum_g) - digamma_f64(cg);  // psi(sum) - psi(c_a): Dirichlet site and pathwise derivative
   // ---- allele mean / sd from its edits (model.py:618-625): wild type (0, 1)
   real mu_a = real(0), sd_a = real(1);
   long long slot = -1;
@@ -143,10 +153,10 @@ __global__ void __launch_bounds__(TILING_WARPS * 32) tiling_guide_kernel(const T
     dP[b] = real(0);
     P[b] = (b < B && exists) ? bin_mass_sorting(p.t.thr_u[b], p.t.thr_l[b], mu_a, sd_a) : real(0);  // utils.py:73-74: absent -> 0
   }
-  double elbo = 0.0, dcm = 0.0, dcg = 0.0;
+  double elbo = 0.0, slp = 0.0, path = 0.0;  // sum of log pi over the masked replicates; sum of the pathwise terms
   int n_in = 0;
   const real epsr = real(1e-5);
-  for (int r = 0; r < R; ++r) {
+  for (int r = warp; r < R; r += NW) {
     const bool rmask = p.row_mask[(size_t)r * p.G + g] != 0;
     // ---- pi ~ Dirichlet(cg): one gamma per lane, normalised over the warp, clamped like torch's sampler
     double pi_a = 0.0;
@@ -217,8 +227,7 @@ __global__ void __launch_bounds__(TILING_WARPS * 32) tiling_guide_kernel(const T
       if (has) {
         elbo += (cm - cg) * lp;
         go += (cm - cg) / pi_a;
-        dcm += dgd_m + lp;
-        dcg -= dgd_g + lp;
+        slp += lp;
       }
       const double Sp = warp_all_sum(has ? pi_a : 0.0);
       const double n = has ? pi_a / Sp : 0.5;
@@ -234,9 +243,37 @@ __global__ void __launch_bounds__(TILING_WARPS * 32) tiling_guide_kernel(const T
     }
     // ---- pathwise derivative of the draw w.r.t. the guide concentration (torch _Dirichlet_backward)
     const double dot = warp_all_sum(has ? pi_a * go : 0.0);
-    if (has) dcg += dirichlet_grad_one_f64_psi(pi_a, cg, sum_g, dgd_g) * (go - dot);
+    if (has) path += dirichlet_grad_one_f64_psi(pi_a, cg, sum_g, dgd_g) * (go - dot);
   }
-  elbo += lane == 0 ? (double)n_in * norm_diff : 0.0;
+  if (warp == NW - 1) {  // the model site's psi(sum) - psi(c_a) and the difference of the two Dirichlet normalisers
+    const double sum_m = warp_all_sum(has ? cm : 0.0);
+    s_dgd_m[lane] = digamma_f64(sum_m) - digamma_f64(cm);
+    const double nd = (::lgamma(sum_m) - warp_all_sum(has ? ::lgamma(cm) : 0.0)) - (::lgamma(sum_g) - warp_all_sum(has ? ::lgamma(cg) : 0.0));
+    if (lane == 0) s_norm_diff = nd;
+  }
+  s_elbo[warp][lane] = elbo;
+  s_slp[warp][lane] = slp;
+  s_path[warp][lane] = path;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) s_dP[warp][b][lane] = dP[b];
+  if (lane == 0) s_nin[warp] = n_in;
+  __syncthreads();
+  if (warp != 0) return;
+  // ---- warp 0: the replicate warps' sums in warp order, then the per-allele epilogue
+  elbo = 0.0; slp = 0.0; path = 0.0; n_in = 0;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dP[b] = real(0);
+  for (int w = 0; w < NW; ++w) {
+    elbo += s_elbo[w][lane];
+    slp += s_slp[w][lane];
+    path += s_path[w][lane];
+    n_in += s_nin[w];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) dP[b] += s_dP[w][b][lane];
+  }
+  const double dcm = has ? (double)n_in * s_dgd_m[lane] + slp : 0.0;   // d / d cm: n_in (psi(sum) - psi(cm)) + sum log pi
+  const double dcg = has ? path - ((double)n_in * dgd_g + slp) : 0.0;  // d / d cg: pathwise - [n_in (psi(sum) - psi(cg)) + sum log pi]
+  elbo += lane == 0 ? (double)n_in * s_norm_diff : 0.0;
   // ---- d ELBO / d (allele mean, sd) into the allele's slot; the per-edit kernel reduces the slots over the CSC map
   if (slot >= 0) {
     real dmu = real(0), dsd = real(0);
@@ -340,13 +377,28 @@ static int tiling_run(const BeanScreen* s, const BeanTilingState* ts, const Bean
   p.beta1 = v.beta1; p.beta2 = v.beta2; p.adam_eps = v.adam_eps; p.clip = v.clip;
   fill_tables(s, p.t);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // warps per guide: as many as stay resident all at once (one wave), at most one per replicate
+  int n_rep_warps = 1;
+  {
+    cudaFuncAttributes fa;
+    BEAN_CUDA(s->n_bins <= 4 ? cudaFuncGetAttributes(&fa, tiling_guide_kernel<real, 4>) : cudaFuncGetAttributes(&fa, tiling_guide_kernel<real, BEAN_MAX_BINS>));
+    int sms = bean_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int regs = ((fa.numRegs + 7) / 8) * 8;
+    const long long resident_warps = (long long)sms * (65536 / (regs * 32));
+    const int cap = s->n_reps < TILING_MAX_REP_WARPS ? s->n_reps : TILING_MAX_REP_WARPS;
+    while (n_rep_warps * 2 <= cap && (long long)G * (n_rep_warps * 2) <= resident_warps) n_rep_warps *= 2;
+  }
   for (int i = 0; i < n_steps; ++i) {
     const int t = first_step + i;
     v.step = p.step = (uint32_t)t;
     const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
     v.step_size = p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
     tiling_draw_kernel<real><<<(E + VAR_THREADS - 1) / VAR_THREADS, VAR_THREADS, 0, st>>>(v, static_cast<real*>(ts->mu_e), static_cast<real*>(ts->sd_e));
-    tiling_guide_kernel<real><<<(G + TILING_WARPS - 1) / TILING_WARPS, TILING_WARPS * 32, 0, st>>>(p);
+    if (s->n_bins <= 4)  // bin arrays of 4 instead of BEAN_MAX_BINS registers: more guides resident per SM
+      tiling_guide_kernel<real, 4><<<G, n_rep_warps * 32, 0, st>>>(p);
+    else
+      tiling_guide_kernel<real, BEAN_MAX_BINS><<<G, n_rep_warps * 32, 0, st>>>(p);
     svi_variant_kernel<real><<<v.n_partial_var, VAR_THREADS, 0, st>>>(v);
   }
   BEAN_CUDA(cudaPeekAtLastError());
