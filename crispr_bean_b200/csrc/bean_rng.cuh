@@ -465,6 +465,7 @@ static __device__ __noinline__ void dirichlet_pair_saddle_f64(double x0, double 
 // `svi_alpha_kernel`: one division, one rsqrt and ~25 multiplies per guide instead of per draw) and the per-draw part.
 struct SaddlePair {
   double a, b, iT, m0, m1, lim_w, rs, s, stirling, k, a2, b2;
+  __device__ __forceinline__ void prepare_near_mean(float*, int) {}
   __device__ __forceinline__ void init(double a_, double b_) {
     a = a_; b = b_;
     const double T = a + b;
@@ -542,8 +543,35 @@ __device__ __forceinline__ float pow_m15_minus1(float z) {
   return e * (3.0f + e * (3.0f + e));
 }
 
+// torch's near-mean polynomial (beta_grad_mid_near_mean) is LINEAR in x: with the prefactor folded in it is
+// (k0 + kx x + k1 (1 - x)) / (1 - x), k0, kx, k1 functions of the concentrations only (all three groups free of cancellation for
+// alpha, beta > 6: 5e-7 against torch's double evaluation, tests/test_saddle_float_form.py).
+__device__ __forceinline__ void near_mean_coeffs(float al, float be, float T, float& k0, float& kx, float& k1) {
+  const float b2 = be * be, b3 = b2 * be, a3 = al * al * al;
+  const float c0 = al * (43.0f * b3 + al * (3.0f * (59.0f + 180.0f * be) * b2 + al * 453.0f * be));
+  const float cx = 47.0f * b2 * b2 + al * (20.0f * (16.0f + 27.0f * be) * b3 - al * (270.0f * b2 + al * 455.0f * be));
+  const float c1 = a3 * (1620.0f * b2 + al * 8.0f * (135.0f * be - 11.0f));
+  const float K = (1.0f + 12.0f * al) * (1.0f + 12.0f * be) / (T * T) / (12960.0f * a3 * b2 * (1.0f + 12.0f * T));
+  k0 = c0 * K; kx = cx * K; k1 = c1 * K;
+}
+
 struct SaddlePairF {
   float a, b, iT, m, om, im, iom, lim_w, s, is, stirling, C2a, C2b, c1a, c1b, ia, ib;
+  const float* nm;  // this thread's six near-mean coefficients in shared memory, stride nm_stride (prepare_near_mean)
+  int nm_stride;
+  // The near-mean regime holds 8 % of the draws, so nearly every warp meets it in every replicate with 2-3 lanes active: the
+  // polynomial's ~70 instructions were 13 % of the alpha kernel.  Its coefficients are made once per guide with all lanes busy
+  // and parked in shared memory; a draw then costs one reciprocal and three FMAs per component.
+  __device__ __forceinline__ void prepare_near_mean(float* smem, int stride) {
+    nm = smem; nm_stride = stride;
+    if (a > 6.0f && b > 6.0f) {
+      float k0, kx, k1;
+      near_mean_coeffs(a, b, a + b, k0, kx, k1);
+      smem[0] = k0; smem[stride] = kx; smem[2 * stride] = k1;
+      near_mean_coeffs(b, a, a + b, k0, kx, k1);
+      smem[3 * stride] = k0; smem[4 * stride] = kx; smem[5 * stride] = k1;
+    }
+  }
   __device__ __forceinline__ void init(float a_, float b_) {
     a = a_; b = b_;
     const float T = a + b;
@@ -572,9 +600,10 @@ struct SaddlePairF {
     const float hi = 1.0f - x0, lo = (1.0f - hi) - x0;
     const float pa = hi * a, ea = fmaf(hi, a, -pa);
     const float d = fmaf(-lo, a, fmaf(x0, b, -pa) - ea) * iT;
-    if (d * d <= lim_w) {  // |x - mean| <= 0.1 std: torch's polynomial (all terms positive for beta > 6: float is fine)
-      g0 = beta_grad_mid_near_mean(x0, a, b, iT);
-      g1 = beta_grad_mid_near_mean(x1, b, a, iT);
+    if (d * d <= lim_w) {  // |x - mean| <= 0.1 std: torch's polynomial, from the per-guide coefficients
+      const float o0 = 1.0f - x0, o1 = 1.0f - x1;
+      g0 = fmaf(nm[2 * nm_stride], o0, fmaf(nm[nm_stride], x0, nm[0])) * rcp_ftz(o0);
+      g1 = fmaf(nm[5 * nm_stride], o1, fmaf(nm[4 * nm_stride], x1, nm[3 * nm_stride])) * rcp_ftz(o1);
       return;
     }
     const float u = d * im, v = -d * iom;

@@ -175,6 +175,7 @@ constexpr int ALPHA_THREADS = 128;
 template <typename real>
 __global__ void __launch_bounds__(ALPHA_THREADS, BEAN_ALPHA_MIN_CTAS) svi_alpha_kernel(const SviParams<real> p) {
   __shared__ TailQueue<real> tail_queues[ALPHA_THREADS / SVI_WARP];
+  __shared__ float s_near_mean[6][ALPHA_THREADS];
   const int g = blockIdx.x * ALPHA_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const real eps = real(1e-5);
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(ALPHA_THREADS, BEAN_ALPHA_MIN_CTAS) svi_alpha_
   // saddle-point regime: float kernels use the cancellation-free single-precision form, double kernels torch's expression
   typename SaddleOf<real>::type sp;
   sp.init(cg0, cg1);
+  sp.prepare_near_mean(&s_near_mean[0][threadIdx.x], ALPHA_THREADS);
   const typename Vec4<real>::type* pw = reinterpret_cast<const typename Vec4<real>::type*>(p.pw) + g;
   typename Vec4<real>::type nxt = pw[0];
   for (int r = 0; r < p.R; ++r) {

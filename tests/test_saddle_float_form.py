@@ -86,3 +86,38 @@ def test_float_saddle_form_matches_torch_double():
         worst = max(worst, abs(got[0] - ref[0]) / abs(ref[0]), abs(got[1] - ref[1]) / abs(ref[1]))
         n += 1
     assert worst < 3e-6, worst  # observed 9e-7 (3e-5 before delta was formed without the rounding of the mean)
+
+
+def near_mean_coeffs(al, be, T):  # csrc/bean_rng.cuh: near_mean_coeffs, in float32
+    al, be, T = f(al), f(be), f(T)
+    b2 = f(be * be)
+    b3 = f(b2 * be)
+    a3 = f(f(al * al) * al)
+    c0 = f(al * f(f(f(43) * b3) + f(al * f(f(f(f(3) * f(f(59) + f(f(180) * be))) * b2) + f(f(al * f(453)) * be)))))
+    cx = f(f(f(f(47) * b2) * b2) + f(al * f(f(f(f(20) * f(f(16) + f(f(27) * be))) * b3) - f(al * f(f(f(270) * b2) + f(f(al * f(455)) * be))))))
+    c1 = f(a3 * f(f(f(1620) * b2) + f(f(al * f(8)) * f(f(f(135) * be) - f(11)))))
+    K = f(f(f(f(f(1) + f(f(12) * al)) * f(f(1) + f(f(12) * be))) / f(T * T)) / f(f(f(f(12960) * a3) * b2) * f(f(1) + f(f(12) * T))))
+    return f(c0 * K), f(cx * K), f(c1 * K)
+
+
+def test_near_mean_polynomial_from_per_guide_coefficients_matches_torch_double():
+    """|x - mean| <= 0.1 std inside the saddle-point regime: torch's polynomial is linear in x, the kernel evaluates it as
+    (k0 + kx x + k1 (1 - x)) / (1 - x) with per-guide coefficients."""
+    rng = np.random.default_rng(1)
+    worst, n = 0.0, 0
+    while n < 3000:
+        a = float(np.exp(rng.uniform(np.log(6.2), np.log(5000))))
+        b = float(np.exp(rng.uniform(np.log(6.2), np.log(5000))))
+        T = a + b
+        m, sd = a / T, np.sqrt(a * b / (T + 1)) / T
+        x = float(np.float32(m + rng.uniform(-0.099, 0.099) * sd))
+        if abs(x - m) > 0.1 * sd or not (0 < x < 1):
+            continue
+        ref = torch._dirichlet_grad(torch.tensor([x], dtype=torch.float64), torch.tensor([a], dtype=torch.float64),
+                                    torch.tensor([T], dtype=torch.float64)).item()
+        k0, kx, k1 = near_mean_coeffs(a, b, T)
+        o = f(f(1) - f(x))
+        got = float(f(f(np.float64(k1) * np.float64(o) + np.float64(f(np.float64(kx) * np.float64(f(x)) + np.float64(k0)))) / o))
+        worst = max(worst, abs(got - ref) / abs(ref))
+        n += 1
+    assert worst < 2e-6, worst  # observed 6e-7 (torch's own polynomial order in float32: 6e-7)
