@@ -33,6 +33,7 @@ WORKLOADS = {
     "c5_genome_scale": (200_000, 5, 8),
     "c2_ldlc_variant": (690, 5, 4),
     "tiny": (2_000, 5, 8),
+    "c5_quarter": (50_000, 5, 8),  # the shard one of four GPUs holds under strong scaling (kernel A/B at that size)
     # BASELINE.json config 4: proliferation / survival variant screen (MixtureNormal survival program), 3 replicates x
     # 3 timepoints (D0, D7, D14; control D7 stays selected), at the c5 guide count so that 1/2/4/8 GPUs have work to split
     "c4_survival": (200_000, 5, 3),

@@ -168,9 +168,14 @@ template <> struct SaddleOf<double> { typedef SaddlePair type; };
 
 // Second half of the split guide step: pathwise Dirichlet derivative of every draw (saddle-point pairs in place, the other
 // regimes through the per-warp queue), alpha_pi gradient and its ClippedAdam update.  One thread per guide.
-constexpr int ALPHA_THREADS = 128;
+// one warp per CTA: the work per draw differs by regime, and small CTAs hand their SM slot on as soon as their own 32 guides are
+// done (128 / 64 / 32 threads: 0.161 / 0.160 / 0.155 ms at c5, 0.057 / 0.055 / 0.054 at a quarter of it; profiles/r2p_variants.jsonl)
+#ifndef BEAN_ALPHA_THREADS
+#define BEAN_ALPHA_THREADS 32
+#endif
+constexpr int ALPHA_THREADS = BEAN_ALPHA_THREADS;
 #ifndef BEAN_ALPHA_MIN_CTAS
-#define BEAN_ALPHA_MIN_CTAS 6
+#define BEAN_ALPHA_MIN_CTAS (768 / BEAN_ALPHA_THREADS)
 #endif
 template <typename real>
 __global__ void __launch_bounds__(ALPHA_THREADS, BEAN_ALPHA_MIN_CTAS) svi_alpha_kernel(const SviParams<real> p) {

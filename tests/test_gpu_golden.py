@@ -79,13 +79,16 @@ def test_fp64_step_equals_reference_float64_run(cuda_device, name):
 #
 # KNOWN_EXCESS: (case, parameter) pairs where the kernels are measured ABOVE that yardstick, with the measured error
 # (B200, tools/fp32_error_report.py, round 2).  Three are in the fused sorting step (two of them within 7 % of the
-# yardstick; the alpha_pi gradient of the reference's 30-guide var_mini screen is at 3e-5), none in the fused survival
-# step; the rest are in the torch-autograd engines (tiling, survival Normal), whose float32 glue ops are torch's own.  The
-# bound asserted is 2 x the measured value; the list is exact (an entry that no longer exceeds the yardstick fails the test).
+# yardstick; the alpha_pi gradient of the reference's 30-guide var_mini screen is at 4e-5: ONE element, guide 3, whose
+# gradient 0.39 is 2.28 x the sum of four pathwise terms of magnitude 5-10 with alternating signs -- the kernel's absolute
+# error there, 2.5e-5, is 1e-6 of those terms, i.e. float32 rounding of the likelihood gradient they are products of; every
+# other element of the case is below 5e-7 (tools/diag_var_mini.py)), none in the fused survival step; the rest are in the
+# torch-autograd engines (tiling, survival Normal), whose float32 glue ops are torch's own.  The bound asserted is 2 x the
+# measured value; the list is exact (an entry that no longer exceeds the yardstick fails the test).
 KNOWN_EXCESS = {
     ("mixture_acc_fitnoise", "noise_scale"): 1.02e-5,
     ("mixture_ragged_lowdepth", "alpha_pi"): 1.06e-5,
-    ("real_var_mini_mixture", "alpha_pi"): 3.0e-5,
+    ("real_var_mini_mixture", "alpha_pi"): 4.1e-5,
     ("survival_normal", "initial_abundance"): 2.2e-5,
     ("survival_normal_bcmatch", "initial_abundance"): 1.5e-4,
     ("survival_normal_bcmatch", "mu_scale"): 1.1e-5,
