@@ -15,6 +15,7 @@ BEAN_OK = 0
 MODE_SORTING, MODE_SURVIVAL = 0, 1
 MAX_BINS, MAX_RB, MAX_ALLELES, MAX_LAYERS = 8, 64, 4096, 2
 SURV_FOLD_ROWS = 1024  # BEAN_SURV_FOLD_ROWS
+MAX_PEERS, PEER_MAX_VALS = 8, 72  # BEAN_MAX_PEERS, BEAN_PEER_MAX_VALS
 
 
 class BeanError(RuntimeError):
@@ -124,11 +125,20 @@ class BeanDirichletArgs(C.Structure):
                 ("seed", C.c_uint64), ("guide_offset", C.c_uint32), ("step", C.c_void_p), ("step_value", C.c_int64)]
 
 
+class BeanPeerBuffer(C.Structure):  # lives in device memory; mirrored for its size and layout only
+    _fields_ = [("vals", C.c_double * PEER_MAX_VALS * MAX_PEERS * 2), ("flag", C.c_uint64 * MAX_PEERS * 2), ("timeouts", C.c_uint64)]
+
+
+class BeanPeerExchange(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("buf", C.c_void_p * MAX_PEERS)]
+
+
 class BeanSurvivalState(C.Structure):
     _fields_ = [("n_controls", C.c_int32), ("prime", C.c_int32), ("n_guides_total", C.c_int64),
                 ("control_time", C.POINTER(C.c_double)), ("negctrl_loc", C.c_double), ("negctrl_scale", C.c_double),
                 ("log_obs", C.c_void_p), ("q0_u", C.c_void_p), ("q0_m", C.c_void_p), ("q0_v", C.c_void_p), ("q0_grad", C.c_void_p),
-                ("gamma", C.c_void_p * 2), ("sums", C.c_void_p * 2), ("abund_partial", C.c_void_p)]
+                ("gamma", C.c_void_p * 2), ("sums", C.c_void_p * 2), ("abund_partial", C.c_void_p),
+                ("peers", C.POINTER(BeanPeerExchange))]
 
 
 class BeanSurvivalNoise(C.Structure):
@@ -152,7 +162,7 @@ class BeanTilingNoise(C.Structure):
 
 SURV_PRIME_NONE, SURV_PRIME_AND_RUN, SURV_PRIME_ONLY = 0, 1, 2
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 12  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 13  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -177,6 +187,12 @@ _PROTOTYPES = {
     "bean_svi_survival_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSurvivalState),
                                             C.POINTER(BeanSviConfig), C.POINTER(BeanSviNoise), C.POINTER(BeanSurvivalNoise),
                                             C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_peer_exchange_bytes": (C.c_int, []),
+    "bean_peer_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "bean_peer_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "bean_peer_close": (C.c_int, [C.c_void_p]),
+    "bean_peer_free": (C.c_int, [C.c_void_p]),
+    "bean_peer_timeouts": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "bean_svi_tiling_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
     "bean_svi_tiling_run_f32": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanTilingState), C.POINTER(BeanSviConfig),
                                           C.POINTER(BeanTilingNoise), C.c_int32, C.c_int32, C.c_void_p]),

@@ -492,7 +492,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   p.fit_noise = cfg->fit_noise;
   p.has_sd = 1;
   p.gather_idx = nullptr; p.dsd_times_sd = 0;
-  p.sums_next = nullptr; p.abund_partial = nullptr; p.n_abund_partial = 0;
+  p.sums_next = nullptr; p.abund_partial = nullptr; p.n_abund_partial = 0; p.peer_world = 0;
   p.d_guide = static_cast<real*>(state->d_guide);
   p.var_grad = static_cast<real*>(state->var_grad);
   p.alpha_grad = static_cast<real*>(state->alpha_grad);

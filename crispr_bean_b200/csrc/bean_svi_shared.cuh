@@ -94,6 +94,10 @@ struct SviParams {
   double* sums_next;
   double* abund_partial;                // [warps][R + 1] per-warp partial sums behind sums_next
   int n_abund_partial;
+  // device-side exchange of the sums between the ranks of a sharded run (include/bean_b200.h: BeanPeerBuffer)
+  int peer_world, peer_rank;            // peer_world <= 1: none
+  int peer_consume;                     // this step's guide kernel takes its sums from the exchange buffer, not from sums_cur
+  BeanPeerBuffer* peer_buf[BEAN_MAX_PEERS];
   const real* eps_negctrl;              // injected noise (parity runs)
   const real* q0_in;                    // [R][G] injected abundance draw (already normalised)
   // ---- tiling step (bean_svi_tiling.cu): the "variants" are edits, whose gradient entries sit in allele slots ----
@@ -218,6 +222,45 @@ __global__ void __launch_bounds__(ALPHA_THREADS, BEAN_ALPHA_MIN_CTAS) svi_alpha_
   }
   if (n_tail > 0) tail_queue_flush(tq, n_tail, wmask, lane, dcg0, dcg1);
   alpha_update(p, g, al0, al1, pa0, cm0, cm1, dc.x, dc.y, dcg0, dcg1);
+}
+
+// This step's library-wide sums into shared memory: from `sums_cur` (single GPU, or the first step of a call: all-reduced by the
+// host), or from the exchange buffer in this rank's own memory once the flags of all ranks for this step have arrived -- added in
+// rank order (deterministic).  Every thread of the CTA calls; n_vals <= BEAN_PEER_MAX_VALS.
+#ifndef BEAN_PEER_TIMEOUT_NS
+#define BEAN_PEER_TIMEOUT_NS 30000000000ull
+#endif
+template <typename real>
+__device__ __forceinline__ void load_library_sums(const SviParams<real>& p, int n_vals, double* s_sums) {
+  if (p.peer_world > 1 && p.peer_consume) {
+    BeanPeerBuffer* own = p.peer_buf[p.peer_rank];
+    const int slot = (int)(p.step & 1u);
+    if ((int)threadIdx.x < p.peer_world) {
+      volatile unsigned long long* f = &own->flag[slot][threadIdx.x];
+      const unsigned long long want = (unsigned long long)p.step + 1ull;
+      unsigned long long t0 = 0ull;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (*f < want) {
+        __nanosleep(200);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > BEAN_PEER_TIMEOUT_NS) {  // a peer died or never ran this step: give up (counted; the host reports it)
+          atomicAdd(&own->timeouts, 1ull);
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n_vals) {
+      double a = 0.0;
+      for (int k = 0; k < p.peer_world; ++k) a += *(volatile const double*)&own->vals[slot][k][threadIdx.x];
+      s_sums[threadIdx.x] = a;
+    }
+  } else if ((int)threadIdx.x < n_vals) {
+    s_sums[threadIdx.x] = p.sums_cur[threadIdx.x];
+  }
+  __syncthreads();
 }
 
 // Column sums of rows first, first + stride, ... (< n_rows) of a row-major [n_rows][C] array of doubles, C <= VAR_THREADS, by
@@ -374,6 +417,24 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
     if (p.sums_next) {
       const double tot_j = column_sums(p.abund_partial + (size_t)p.n_abund_partial * C, M, C, 0, 1, s_cs);
       if ((int)threadIdx.x < C) p.sums_next[threadIdx.x] = tot_j;
+      if (p.peer_world > 1) {
+        // publish this rank's partial sums of step t + 1 into every rank's exchange buffer (remote stores over NVLink), then --
+        // after a system-scope fence on every writer and the barrier -- the flag that tells that rank they are there
+        const int slot = (int)((p.step + 1u) & 1u);
+        if ((int)threadIdx.x < C) {
+          for (int k = 0; k < p.peer_world; ++k) {
+            volatile double* dst = &p.peer_buf[k]->vals[slot][p.peer_rank][threadIdx.x];
+            *dst = tot_j;
+          }
+          __threadfence_system();
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < p.peer_world) {
+          __threadfence_system();
+          volatile unsigned long long* f = &p.peer_buf[threadIdx.x]->flag[slot][p.peer_rank];
+          *f = (unsigned long long)p.step + 2ull;
+        }
+      }
     }
   }
 }

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
   const bool owns = g < p.G;
   double elbo = 0.0;
   real c_next = real(0);
+  __shared__ double s_sums[BEAN_PEER_MAX_VALS];
+  load_library_sums(p, R + 1, s_sums);
   if (owns) {
     const int v = p.guide_variant[g];
     real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
     }
     // abundance sites: q0[g] and the library-wide sums
     const real c = Num<real>::exp(p.q0_u[g]);
-    const double Csum = p.sums_cur[R];
+    const double Csum = s_sums[R];
     real d_c = real(0), dmu1 = real(0);
     // float: psi(c + 1) - psi(sum q0), the guide-only part of the pathwise derivative of a draw at the lower clamp (below)
     real psi_diff = real(0);
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
         if (p.q0_in) {
           xq = p.q0_in[(size_t)r * p.G + g];
         } else {
-          xq = real((double)p.gamma_cur[(size_t)r * p.G + g] / p.sums_cur[r]);
+          xq = real((double)p.gamma_cur[(size_t)r * p.G + g] / s_sums[r]);
           xq = Num<real>::fmin(Num<real>::fmax(xq, Lim<real>::tiny()), Lim<real>::one_minus());
         }
         const real lx = log_pos(xq);
@@ -397,9 +399,23 @@ static int survival_run(const BeanScreen* s, const BeanSviState* state, const Be
   p.n_abund_partial = p.n_partial_guide;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (p.G + SVI_THREADS - 1) / SVI_THREADS;
+  // device-side exchange of the sums (sharded guides): whole, updating steps only; the first step of a call reads `sums`
+  p.peer_world = 0; p.peer_rank = 0; p.peer_consume = 0;
+  for (int k = 0; k < BEAN_MAX_PEERS; ++k) p.peer_buf[k] = nullptr;
+  if (sv->peers && sv->peers->world > 1 && cfg->phases == 0 && cfg->apply_update && sv->prime == BEAN_SURV_PRIME_NONE) {
+    BEAN_REQUIRE(sv->peers->world <= BEAN_MAX_PEERS && sv->peers->rank >= 0 && sv->peers->rank < sv->peers->world, BEAN_EINVAL,
+                 "peer exchange: world %d / rank %d out of range", sv->peers->world, sv->peers->rank);
+    BEAN_REQUIRE(s->n_reps + 1 <= BEAN_PEER_MAX_VALS, BEAN_EINVAL, "peer exchange: n_reps + 1 > %d", BEAN_PEER_MAX_VALS);
+    p.peer_world = sv->peers->world; p.peer_rank = sv->peers->rank;
+    for (int k = 0; k < p.peer_world; ++k) {
+      BEAN_REQUIRE(sv->peers->buf[k] != nullptr, BEAN_EINVAL, "peer exchange: buffer of rank %d is NULL", k);
+      p.peer_buf[k] = static_cast<BeanPeerBuffer*>(sv->peers->buf[k]);
+    }
+  }
   for (int i = 0; i < n_steps; ++i) {
     const int t = first_step + i;
     p.step = (uint32_t)t;
+    p.peer_consume = i > 0 ? 1 : 0;
     const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
     p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
     // the abundance draw of step t lives in buffer t & 1 (written by the step before, or primed here)

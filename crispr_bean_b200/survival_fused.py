@@ -7,12 +7,17 @@ alpha_pi = alpha_prior (G, 2), q0 = 1 / G (G,).
 
 Sharding: guides may be split over the ranks of a torch.distributed group in contiguous variant blocks
 (`dist.shard_data`).  The program's Dirichlet over ALL guides then needs R + 1 library-wide sums per step -- sum_g gamma[r][g]
-and sum_g q0[g] -- which the kernels leave in one small device buffer; this engine all-reduces it (ONE NCCL all-reduce of
-R + 1 doubles) between consecutive steps.  That is the path's only data-path collective.
+and sum_g q0[g] -- the path's only data-path collective.  Where the ranks are the GPUs of one box they trade these numbers
+INSIDE the kernels through CUDA-IPC-mapped peer memory (the per-variant kernel's last CTA stores its partial sums into every
+rank's buffer over NVLink and raises a flag, the next step's guide kernel waits for the flags; csrc/bean_peer.cu), so that N
+steps are one C call as on a single GPU and the host all-reduces only the sums the next call starts from.  Otherwise (peer
+mapping unavailable, a single step, a kernel timed alone) this engine launches step by step and all-reduces the buffer with
+NCCL between consecutive steps.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -139,8 +144,68 @@ class SurvivalFusedEngine:
         v.sums[0], v.sums[1] = self.sums[0].data_ptr(), self.sums[1].data_ptr()
         v.abund_partial = self.abund_partial.data_ptr()
         self.surv = v
+        self.peers = self._open_peer_exchange() if self.sharded else None
 
     # ---------------------------------------------------------------------------------------------
+    def _open_peer_exchange(self):
+        """The device-side exchange of the library-wide sums (include/bean_b200.h: BeanPeerBuffer): this rank's buffer, the
+        other ranks' mapped through CUDA IPC.  Returns None (the host all-reduces between the steps instead) where peer
+        mapping is not available -- a group that is not the GPUs of one box, or IPC refused by the driver."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if world > _lib.MAX_PEERS or self.R + 1 > _lib.PEER_MAX_VALS or os.environ.get("BEAN_NO_PEER_EXCHANGE"):
+            return None
+        own, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        ok = self.lib.bean_peer_alloc(C.byref(own), handle) == 0
+        mine = torch.tensor(list(handle) + [1 if ok else 0], dtype=torch.uint8, device=self.device)
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine, group=self.group)
+        ex = _lib.BeanPeerExchange()
+        ex.world, ex.rank = world, rank
+        opened, good = [], ok and all(int(h[64]) == 1 for h in everyone)
+        if good:
+            for k, h in enumerate(everyone):
+                if k == rank:
+                    ex.buf[k] = own.value
+                    continue
+                ptr, raw = C.c_void_p(), (C.c_ubyte * 64)(*h[:64].tolist())
+                if self.lib.bean_peer_open(raw, C.byref(ptr)) != 0:
+                    good = False
+                    break
+                ex.buf[k] = ptr.value
+                opened.append(ptr.value)
+        # every rank must take the same path: one that cannot map its peers sends everybody back to the host exchange
+        flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            for ptr in opened:
+                self.lib.bean_peer_close(ptr)
+            if ok:
+                self.lib.bean_peer_free(own)
+            return None
+        self._peer_own, self._peer_opened = own.value, opened
+        return ex
+
+    def peer_timeouts(self) -> int:
+        """Waits of the device-side exchange that gave up (0 on a healthy run); synchronises."""
+        if self.peers is None:
+            return 0
+        out = C.c_uint64()
+        _lib.check(self.lib.bean_peer_timeouts(self._peer_own, C.byref(out)), "bean_peer_timeouts")
+        return int(out.value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "peers", None) is not None:
+                torch.cuda.synchronize(self.device)
+                for ptr in self._peer_opened:
+                    self.lib.bean_peer_close(ptr)
+                self.lib.bean_peer_free(self._peer_own)
+                self.peers = None
+        except Exception:  # pragma: no cover  (interpreter shutdown)
+            pass
+
     def _all_reduce(self, t):
         if _dist_active(self.group):
             import torch.distributed as dist
@@ -188,8 +253,20 @@ class SurvivalFusedEngine:
         ns = self._noise_structs(noise)
         self.cfg.apply_update = 1 if apply_update else 0
         first = self.step
+        self.surv.peers = None
         if not self.sharded:
             self._launch(first, n_steps, ns, _lib.SURV_PRIME_NONE if self._primed else _lib.SURV_PRIME_AND_RUN)
+        elif self.peers is not None and apply_update and self.cfg.phases == 0 and n_steps > 1:
+            # device-side exchange: the ranks trade their R + 1 partial sums through peer memory inside the kernels, the host
+            # all-reduces only the sums the NEXT call starts from
+            if not self._primed:
+                self._launch(first, 1, ns, _lib.SURV_PRIME_ONLY)
+                self._all_reduce(self.sums[first & 1])
+                self._primed = True
+            self.surv.peers = C.pointer(self.peers)
+            self._launch(first, n_steps, ns, _lib.SURV_PRIME_NONE)
+            self.surv.peers = None
+            self._all_reduce(self.sums[(first + n_steps) & 1])
         else:
             for t in range(first, first + n_steps):
                 if not self._primed:

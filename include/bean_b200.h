@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 12
+#define BEAN_ABI_VERSION 13
 
 enum {
   BEAN_OK = 0,
@@ -49,6 +49,8 @@ enum { BEAN_MODE_SORTING = 0, BEAN_MODE_SURVIVAL = 1 };
 #define BEAN_MAX_ALLELES 4096  /* alleles per guide incl. wild type (raw tiling allele tables reach hundreds) */
 #define BEAN_MAX_LAYERS 2
 #define BEAN_SURV_FOLD_ROWS 1024 /* spare rows of BeanSurvivalState.abund_partial (second level of the abundance sums) */
+#define BEAN_MAX_PEERS 8        /* GPUs of one box */
+#define BEAN_PEER_MAX_VALS 72   /* >= n_reps + 1 */
 
 int bean_abi_version(void);
 const char* bean_last_error(void);
@@ -261,6 +263,28 @@ int bean_svi_run_f64(const BeanScreen* screen, const BeanSviState* state, const 
  * n_steps = 1 and all-reduce `sums[(t + 1) & 1]` between steps (prime = BEAN_SURV_PRIME_ONLY first, all-reduce
  * `sums[t & 1]`, then prime = BEAN_SURV_PRIME_NONE).
  * ---------------------------------------------------------------------------------------------- */
+/* Device-side exchange of those sums (guides sharded over the GPUs of one box, one process per GPU): every rank owns one
+ * BeanPeerBuffer in its own GPU memory (bean_peer_alloc) and maps the other ranks' through CUDA IPC (bean_peer_open of the
+ * handles, exchanged by the host once).  The last CTA of step t's per-variant kernel stores its rank's partial sums for step
+ * t + 1 into slot (t + 1) & 1 of EVERY rank's buffer over NVLink and then raises flag[(t + 1) & 1][rank] = t + 2 there; the
+ * guide kernel of step t + 1 waits in its own memory until all `world` flags have arrived and adds the partials in rank order.
+ * With `peers` set, bean_svi_survival_run runs n_steps > 1 steps in one call without the host (the first step of a call still
+ * reads `sums`, all-reduced by the host after the previous call).  A wait gives up after 30 s (bean_peer_timeouts). */
+typedef struct BeanPeerBuffer {
+  double vals[2][BEAN_MAX_PEERS][BEAN_PEER_MAX_VALS];
+  unsigned long long flag[2][BEAN_MAX_PEERS];
+  unsigned long long timeouts;
+} BeanPeerBuffer;
+typedef struct BeanPeerExchange {
+  int32_t world, rank;
+  void* buf[BEAN_MAX_PEERS];     /* BeanPeerBuffer of every rank, as mapped in THIS process (buf[rank]: its own) */
+} BeanPeerExchange;
+int bean_peer_exchange_bytes(void);
+int bean_peer_alloc(void** ptr, unsigned char* handle64);        /* cudaMalloc + zero; handle64: 64-byte CUDA IPC handle */
+int bean_peer_open(const unsigned char* handle64, void** ptr);   /* map another rank's buffer */
+int bean_peer_close(void* ptr);
+int bean_peer_free(void* ptr);
+int bean_peer_timeouts(const void* own, unsigned long long* out);
 enum { BEAN_SURV_PRIME_NONE = 0, BEAN_SURV_PRIME_AND_RUN = 1, BEAN_SURV_PRIME_ONLY = 2 };
 typedef struct BeanSurvivalState {
   int32_t n_controls;            /* C: control conditions of the reporter Multinomial (BeanSviState.allele_counts is [R][C][G][2]) */
@@ -277,6 +301,7 @@ typedef struct BeanSurvivalState {
   void* gamma[2];                /* real [R][G] x 2: unnormalised abundance draws of even / odd steps */
   double* sums[2];               /* f64 [R + 1] x 2: sum_g gamma[r][g] (r < R), sum_g q0[g] */
   double* abund_partial;         /* f64 [ceil(G / 128) * 4 + BEAN_SURV_FOLD_ROWS][R + 1] scratch */
+  const BeanPeerExchange* peers; /* device-side exchange of `sums` between the ranks of a sharded run, or NULL */
 } BeanSurvivalState;
 typedef struct BeanSurvivalNoise { /* optional injected noise of the survival-only sites (parity runs) */
   const void* eps_negctrl;       /* real [G] standard-normal draw behind mu_negctrl */

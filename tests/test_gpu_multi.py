@@ -97,16 +97,25 @@ def _fused_worker(rank, world, port, out_dir):
     sub, off = shard_data(data, rank, world)
     res = {}
     for dtype in (torch.float64, torch.float32):
-        # sharded over the two ranks: the library-wide sums of the abundance Dirichlet are all-reduced every step
+        # sharded over the two ranks: the library-wide sums of the abundance Dirichlet travel through peer memory inside the kernels
         eng = SurvivalFusedEngine(sub, f"cuda:{rank}", dtype=dtype, num_steps=12, seed=4, guide_offset=off["guide_offset"],
                                   variant_offset=off["variant_offset"])
-        eng.run(12)
+        eng.run(5)   # two calls: the second starts from sums the host all-reduced after the first
+        eng.run(7)
         loss = eng.losses().to(f"cuda:{rank}")
         dist.all_reduce(loss)
+        # the same shards with the host all-reducing between the steps (the path taken where peer memory cannot be mapped)
+        os.environ["BEAN_NO_PEER_EXCHANGE"] = "1"
+        host = SurvivalFusedEngine(sub, f"cuda:{rank}", dtype=dtype, num_steps=12, seed=4, guide_offset=off["guide_offset"],
+                                   variant_offset=off["variant_offset"])
+        del os.environ["BEAN_NO_PEER_EXCHANGE"]
+        host.run(12)
         full = SurvivalFusedEngine(data, f"cuda:{rank}", dtype=dtype, num_steps=12, seed=4, group=solo)  # unsharded, same seed
         full.run(12)
-        res[str(dtype)] = {"loss": loss.cpu(), "full_loss": full.losses(), "off": off,
-                           "got": {k: v.cpu() for k, v in eng.params().items()}, "full": {k: v.cpu() for k, v in full.params().items()}}
+        res[str(dtype)] = {"loss": loss.cpu(), "full_loss": full.losses(), "off": off, "peer_path": eng.peers is not None,
+                           "host_path": host.peers is None, "timeouts": eng.peer_timeouts(),
+                           "got": {k: v.cpu() for k, v in eng.params().items()}, "full": {k: v.cpu() for k, v in full.params().items()},
+                           "host": {k: v.cpu() for k, v in host.params().items()}}
     torch.save(res, f"{out_dir}/f{rank}.pt")
     dist.destroy_process_group()
 
@@ -121,7 +130,10 @@ def test_fused_survival_run_sharded_over_two_gpus_equals_single_gpu(tmp_path):
         res = torch.load(f"{tmp_path}/f{rank}.pt")
         for dtype, r in res.items():
             tol = 1e-9 if "64" in dtype else 1e-4
+            assert r["peer_path"] and r["host_path"] and r["timeouts"] == 0, (r["peer_path"], r["host_path"], r["timeouts"])
             torch.testing.assert_close(r["loss"], r["full_loss"], rtol=tol, atol=0)
+            for k, g in r["got"].items():  # device-side exchange vs NCCL between the steps: the same sums up to their order
+                torch.testing.assert_close(g.double(), r["host"][k].double(), rtol=tol * 10, atol=tol * 10 * g.abs().mean().item())
             off = r["off"]
             gb, ge = off["guide_offset"], off["guide_offset"] + off["n_guides"]
             vb, ve = off["variant_offset"], off["variant_offset"] + off["n_variants"]
