@@ -144,7 +144,7 @@ class SurvivalFusedEngine:
         v.sums[0], v.sums[1] = self.sums[0].data_ptr(), self.sums[1].data_ptr()
         v.abund_partial = self.abund_partial.data_ptr()
         self.surv = v
-        self.peers = self._open_peer_exchange() if self.sharded else None
+        self.peers, self._peers_tried = None, False  # opened by the first multi-step call of a sharded run (_open_peer_exchange)
 
     # ---------------------------------------------------------------------------------------------
     def _open_peer_exchange(self):
@@ -186,6 +186,12 @@ class SurvivalFusedEngine:
             return None
         self._peer_own, self._peer_opened = own.value, opened
         return ex
+
+    def _peer_exchange(self):
+        if not self._peers_tried:  # a collective of the group: every rank gets here in the same call
+            self._peers_tried = True
+            self.peers = self._open_peer_exchange()
+        return self.peers
 
     def peer_timeouts(self) -> int:
         """Waits of the device-side exchange that gave up (0 on a healthy run); synchronises."""
@@ -256,7 +262,7 @@ class SurvivalFusedEngine:
         self.surv.peers = None
         if not self.sharded:
             self._launch(first, n_steps, ns, _lib.SURV_PRIME_NONE if self._primed else _lib.SURV_PRIME_AND_RUN)
-        elif self.peers is not None and apply_update and self.cfg.phases == 0 and n_steps > 1:
+        elif apply_update and self.cfg.phases == 0 and n_steps > 1 and self._peer_exchange() is not None:
             # device-side exchange: the ranks trade their R + 1 partial sums through peer memory inside the kernels, the host
             # all-reduces only the sums the NEXT call starts from
             if not self._primed:

@@ -105,11 +105,11 @@ def _fused_worker(rank, world, port, out_dir):
         loss = eng.losses().to(f"cuda:{rank}")
         dist.all_reduce(loss)
         # the same shards with the host all-reducing between the steps (the path taken where peer memory cannot be mapped)
-        os.environ["BEAN_NO_PEER_EXCHANGE"] = "1"
         host = SurvivalFusedEngine(sub, f"cuda:{rank}", dtype=dtype, num_steps=12, seed=4, guide_offset=off["guide_offset"],
                                    variant_offset=off["variant_offset"])
-        del os.environ["BEAN_NO_PEER_EXCHANGE"]
+        os.environ["BEAN_NO_PEER_EXCHANGE"] = "1"
         host.run(12)
+        del os.environ["BEAN_NO_PEER_EXCHANGE"]
         full = SurvivalFusedEngine(data, f"cuda:{rank}", dtype=dtype, num_steps=12, seed=4, group=solo)  # unsharded, same seed
         full.run(12)
         res[str(dtype)] = {"loss": loss.cpu(), "full_loss": full.losses(), "off": off, "peer_path": eng.peers is not None,
