@@ -332,6 +332,10 @@ def main():
     final_loss = float(eng.loss[eng.step - 1].item())
 
     # --- per-kernel timing for the roofline: each kernel alone, same launches, CUDA events --------
+    # sharded survival: whether the library-wide sums travelled through peer memory inside the kernels, and waits that gave up
+    peer_exchange = None
+    if survival and world > 1:
+        peer_exchange = {"used": getattr(eng, "peers", None) is not None, "timeouts": eng.peer_timeouts()}
     ms_guide = max_over_ranks(time_steps(eng, args.steps, phases=1) / args.steps)
     split = getattr(eng, "split", True)
     ms_alpha = max_over_ranks(time_steps(eng, args.steps, phases=4) / args.steps) if split else 0.0
@@ -486,6 +490,8 @@ def main():
         "roofline": roofline,
         "final_loss": final_loss,
     }
+    if peer_exchange is not None:
+        line["peer_exchange"] = peer_exchange
     if full_run:
         line["full_run"] = full_run
     if world == 1 and not args.no_cpu_baseline:
