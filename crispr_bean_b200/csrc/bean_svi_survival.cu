@@ -100,8 +100,11 @@ __global__ void __launch_bounds__(VAR_THREADS) surv_sums_kernel(const SviParams<
 }
 
 // EXACT: the screen has exactly NB timepoints (no `b < B` predicates in the bin loops).
+#ifndef BEAN_SURV_MIN_CTAS
+#define BEAN_SURV_MIN_CTAS 6
+#endif
 template <typename real, int NB, bool EXACT>
-__global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_guide_kernel(const SviParams<real> p) {
+__global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? BEAN_SURV_MIN_CTAS : 3) surv_guide_kernel(const SviParams<real> p) {
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = EXACT ? NB : p.B;
   const real eps = real(1e-5);
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? 6 : 3) surv_g
         pi0 = p.pi_in[((size_t)g * R + r) * 2];
         pi1 = p.pi_in[((size_t)g * R + r) * 2 + 1];
       } else {
-        sample_pi2(p.seed, (uint32_t)g + p.guide_offset, (uint32_t)r, p.step, mt0, mt1, pi0, pi1);
+        sample_pi2(p.seed, (uint32_t)g + p.guide_offset, (uint32_t)r, p.step, mt0, mt1, pi0, pi1, &p.rk);
       }
       if (p.pi_out) {
         p.pi_out[((size_t)g * R + r) * 2] = pi0;
@@ -357,6 +360,7 @@ static int survival_run(const BeanScreen* s, const BeanSviState* state, const Be
   p.G = s->n_guides; p.R = s->n_reps; p.B = s->n_bins; p.L = s->n_layers; p.T = state->n_variants;
   p.mixture = 1; p.has_sd = 0; p.mu_prior_normal = cfg->mu_prior_normal; p.apply_update = cfg->apply_update;
   p.seed = cfg->seed; p.guide_offset = cfg->guide_offset; p.variant_offset = cfg->variant_offset;
+  philox_round_keys(p.seed, p.rk);
   p.mask_thres = real(s->mask_thres);
   p.x = static_cast<const real*>(s->x);
   p.a0 = static_cast<const real*>(s->a0);
