@@ -153,7 +153,8 @@ class BeanTilingState(C.Structure):
                 ("mu_e", C.c_void_p), ("sd_e", C.c_void_p), ("d_slot", C.c_void_p),
                 ("partial", C.c_void_p), ("counter", C.c_void_p), ("loss", C.c_void_p),
                 ("mu_prior_loc_v", C.c_void_p), ("mu_prior_scale_v", C.c_void_p), ("sd_prior_loc_v", C.c_void_p), ("sd_prior_scale_v", C.c_void_p),
-                ("epsilon", C.c_double), ("pi_tiny", C.c_double)]
+                ("epsilon", C.c_double), ("pi_tiny", C.c_double),
+                ("edit_sum", C.c_void_p), ("edit_iota", C.c_void_p), ("edit_term_weight", C.c_double)]
 
 
 class BeanTilingNoise(C.Structure):
@@ -162,7 +163,7 @@ class BeanTilingNoise(C.Structure):
 
 SURV_PRIME_NONE, SURV_PRIME_AND_RUN, SURV_PRIME_ONLY = 0, 1, 2
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 13  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 14  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 

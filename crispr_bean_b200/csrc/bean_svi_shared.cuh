@@ -102,6 +102,8 @@ struct SviParams {
   const real* q0_in;                    // [R][G] injected abundance draw (already normalised)
   // ---- tiling step (bean_svi_tiling.cu): the "variants" are edits, whose gradient entries sit in allele slots ----
   const int32_t* gather_idx;            // [nnz] CSC: d_guide index of the j-th entry of a segment (NULL: j itself)
+  real* seg_sum_out;                    // [2][T] sharded tiling step: write the segment sums here and do nothing else
+  int variant_terms_off;                // the per-variant ELBO terms stay out of loss[t] (another rank counts them)
   int dsd_times_sd;                     // d_guide's second row holds d/d(sd_allele) / sd_allele: multiply the sum by the edit's sd
 };
 
@@ -313,8 +315,13 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
     if (sub == 0) {
       s_d[0][vl] = dmu;
       s_d[1][vl] = dsd;
+      if (p.seg_sum_out && v < p.T) {
+        p.seg_sum_out[v] = dmu;
+        p.seg_sum_out[(size_t)p.T + v] = dsd;
+      }
     }
   }
+  if (p.seg_sum_out) return;  // reduce-only launch (grid-uniform)
   // this CTA's slice of the guide kernel's partials (fixed assignment: deterministic)
   double elbo = 0.0;
   for (int i = blockIdx.x * VAR_THREADS + threadIdx.x; i < p.n_partial_guide; i += gridDim.x * VAR_THREADS) elbo += p.partial[i];
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParam
     // guide densities (entropy side)
     const real lq_mu = -Num<real>::log(mu_scale) - HL2PI - real(0.5) * e_mu * e_mu;
     const real lq_sd = -y - Num<real>::log(sd_scale) - HL2PI - real(0.5) * e_sd * e_sd;
-    elbo += (double)lp_mu - (double)lq_mu + (p.has_sd ? (double)lp_sd - (double)lq_sd : 0.0);
+    if (!p.variant_terms_off) elbo += (double)lp_mu - (double)lq_mu + (p.has_sd ? (double)lp_sd - (double)lq_sd : 0.0);
     if (p.dsd_times_sd) dsd *= sd_t;  // sd_allele = sqrt(sum sd_edit^2): d sd_allele / d sd_edit = sd_edit / sd_allele
     const real dE_mu = dmu + dlp_mu;
     const real dE_sd = dsd + dlp_sd;

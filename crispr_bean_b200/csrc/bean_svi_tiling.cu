@@ -389,11 +389,26 @@ static int tiling_run(const BeanScreen* s, const BeanTilingState* ts, const Bean
     const int cap = s->n_reps < TILING_MAX_REP_WARPS ? s->n_reps : TILING_MAX_REP_WARPS;
     while (n_rep_warps * 2 <= cap && (long long)G * (n_rep_warps * 2) <= resident_warps) n_rep_warps *= 2;
   }
+  // guides sharded over ranks: phase 1 leaves this shard's per-edit sums in edit_sum, phase 2 (after the host's all-reduce)
+  // updates every edit from them -- `u` = the per-edit kernel's parameters with the reduced sums as a one-entry-per-edit CSR
+  const bool sharded = ts->edit_sum != nullptr;
+  SviParams<real> u = v;
+  if (sharded) {
+    BEAN_REQUIRE(ts->edit_iota != nullptr, BEAN_EINVAL, "edit_sum needs edit_iota");
+    BEAN_REQUIRE(cfg->phases == 1 || cfg->phases == 2, BEAN_EINVAL, "sharded tiling step: phases must be 1 (reduce) or 2 (update), got %d", cfg->phases);
+    v.seg_sum_out = static_cast<real*>(ts->edit_sum);
+    u.G = E; u.d_guide = static_cast<real*>(ts->edit_sum); u.variant_ptr = ts->edit_iota; u.gather_idx = nullptr;
+    u.variant_terms_off = ts->edit_term_weight == 0.0 ? 1 : 0;
+  }
   for (int i = 0; i < n_steps; ++i) {
     const int t = first_step + i;
-    v.step = p.step = (uint32_t)t;
+    v.step = u.step = p.step = (uint32_t)t;
     const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
-    v.step_size = p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
+    v.step_size = u.step_size = p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
+    if (sharded && cfg->phases == 2) {
+      svi_variant_kernel<real><<<u.n_partial_var, VAR_THREADS, 0, st>>>(u);
+      continue;
+    }
     tiling_draw_kernel<real><<<(E + VAR_THREADS - 1) / VAR_THREADS, VAR_THREADS, 0, st>>>(v, static_cast<real*>(ts->mu_e), static_cast<real*>(ts->sd_e));
     if (s->n_bins <= 4)  // bin arrays of 4 instead of BEAN_MAX_BINS registers: more guides resident per SM
       tiling_guide_kernel<real, 4><<<G, n_rep_warps * 32, 0, st>>>(p);

@@ -461,7 +461,20 @@ class _TilingReporterMixin:
         return dense.reshape(self.n_guides, self.n_max_alleles - 1, self.n_edits)
 
     def __getitem__(self, guide_idx):
-        raise NotImplementedError("guide subsetting of tiling screens")
+        """Guide subset (sharding over GPUs): the guide-axis tensors and the CSR rows of the chosen guides; the EDITS stay those
+        of the whole screen (`n_edits`, `edit_index`): an edit's alleles sit in guides of several shards."""
+        idx = np.asarray(torch.as_tensor(np.asarray(guide_idx)).long().numpy(), dtype=np.int64)
+        nd = super().__getitem__(idx)
+        a1 = self.n_max_alleles - 1
+        ptr = self.allele_ptr.numpy().astype(np.int64)
+        slots = (idx[:, None] * a1 + np.arange(a1)[None, :]).reshape(-1)
+        lens = ptr[slots + 1] - ptr[slots]
+        new_ptr = np.concatenate([[0], np.cumsum(lens)])
+        take = np.repeat(ptr[slots] - new_ptr[:-1], lens) + np.arange(new_ptr[-1])
+        nd.allele_ptr = torch.as_tensor(new_ptr.astype(np.int32))
+        nd.allele_edit = self.allele_edit[torch.as_tensor(take)] if len(take) else self.allele_edit[:0]
+        nd.allele_mask = self.allele_mask[torch.as_tensor(idx)]
+        return nd
 
 
 class TilingSortingReporterScreenData(_TilingReporterMixin, SortingScreenData):

@@ -41,8 +41,20 @@ def shard_variants(target_lengths, world: int) -> List[Tuple[int, int, int, int]
     return [(int(cuts[r]), int(cuts[r + 1]), int(starts[cuts[r]]), int(starts[cuts[r + 1]])) for r in range(world)]
 
 
+def shard_guides(n_guides: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous guide blocks of (nearly) equal size: the tiling designs, whose guides have no variant of their own."""
+    cuts = [round(r * n_guides / world) for r in range(world + 1)]
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
 def shard_data(data, rank: int, world: int):
     """This rank's slice of a tensorised screen (+ its global offsets)."""
+    if getattr(data, "is_tiling", False):  # guides only: every rank keeps ALL edits (their gradients are summed over the ranks)
+        gb, ge = shard_guides(data.n_guides, world)[rank]
+        if ge == gb:
+            raise ValueError(f"rank {rank} of {world} received no guides")
+        sub = data[np.arange(gb, ge)] if (gb, ge) != (0, data.n_guides) else data
+        return sub, {"variant_offset": 0, "guide_offset": gb, "n_variants": int(data.n_edits), "n_guides": ge - gb}
     vb, ve, gb, ge = shard_variants(data.target_lengths.numpy(), world)[rank]
     if ge == gb:
         raise ValueError(f"rank {rank} of {world} received no variants")
@@ -92,8 +104,9 @@ def run_sharded(make_engine: Callable, data, num_steps: int, rank: int, world: i
     # the one collective of the path: the per-step ELBO scalars, reduced once for the whole run
     loss = all_reduce_sum(eng.losses().clone().to(_device_of(eng)))
     params = {}
+    replicated = getattr(eng, "replicated_params", ())  # tiling: the per-edit parameters, identical on every rank
     for k, v in eng.params().items():
-        if v.dim() == 0:
+        if v.dim() == 0 or k in replicated:
             params[k] = v
         else:
             params[k] = torch.cat(all_gather(v.contiguous()), dim=0)

@@ -62,7 +62,7 @@ def make_engine(model, guide, data, initial_lr=0.01, gamma=0.1, num_steps=2000, 
             return tiling_fused.TilingFusedEngine(data, device=device, dtype=dtype, use_bcmatch=True, num_steps=num_steps,
                                                   initial_lr=initial_lr, gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
                                                   sd_scale=float(mkw.get("sd_scale", 0.01)), epsilon=float(mkw.get("epsilon", 1e-5)),
-                                                  prior_params=mkw.get("prior_params"))
+                                                  prior_params=mkw.get("prior_params"), guide_offset=guide_offset)
         return TilingSviEngine(data, device=device, dtype=dtype, use_bcmatch=True, num_steps=num_steps, initial_lr=initial_lr,
                                gamma=gamma, seed=seed, alpha_prior=float(mkw.get("alpha_prior", 1.0)),
                                sd_scale=float(mkw.get("sd_scale", 0.01)), epsilon=float(mkw.get("epsilon", 1e-5)),
@@ -94,9 +94,15 @@ def shards_over_ranks(model, data) -> bool:
     """Whether a (model, screen) pair is split over the ranks of torch.distributed: the variant designs
     shard by contiguous variant blocks; ControlNormal (a handful of global scalars over ~100 control guides), the covariate
     Normal model (replicate-level parameters) and the tiling designs (edits shared between overlapping guides) run as
-    replicas -- every rank fits the whole screen and returns the same result."""
-    name, _ = resolve(model)
-    if name in ("ControlNormal", "MultiMixtureNormal"):
+    replicas -- every rank fits the whole screen and returns the same result.  The tiling sorting design shards by guide blocks
+    where the fused step serves it (every rank keeps all edits and the per-edit gradient sums are all-reduced each step)."""
+    name, mkw = resolve(model)
+    scale_by_acc = bool(mkw.get("scale_by_accessibility", False))
+    if name == "MultiMixtureNormal":  # guide blocks, the per-edit gradients all-reduced every step: the fused tiling step only
+        from . import tiling_fused
+
+        return (not getattr(data, "is_survival", False)) and tiling_fused.supports(data, scale_by_acc) and int(data.n_guides) >= 2
+    if name == "ControlNormal":
         return False
     if getattr(data, "sample_covariates", None) is not None or not hasattr(data, "target_lengths"):
         return False

@@ -29,13 +29,16 @@ def supports(data, scale_by_accessibility: bool = False) -> bool:
 class TilingFusedEngine:
     def __init__(self, data, device="cuda", dtype=torch.float32, use_bcmatch: bool = True, num_steps: int = 2000,
                  initial_lr: float = 0.01, gamma: float = 0.1, seed: int = 101, alpha_prior: float = 1.0, sd_scale: float = 0.01,
-                 epsilon: float = 1e-5, prior_params: Optional[dict] = None):
+                 epsilon: float = 1e-5, prior_params: Optional[dict] = None, guide_offset: int = 0, group=None):
         if not torch.cuda.is_available():
             raise _lib.BeanError("TilingFusedEngine needs a CUDA device: there is no CPU fallback")
         if not supports(data):
             raise ValueError(f"the fused tiling step takes 2..{MAX_ALLELES} alleles per guide (got {data.n_max_alleles})")
         self.lib = _lib.lib()
         self.model, self.dtype, self.device = "MultiMixtureNormal", dtype, torch.device(device)
+        # guides sharded over the ranks of `group` (dist.shard_data): `data` is this rank's guide block with ALL edits of the screen
+        self.group, self.sharded = group, _dist_active(group)
+        self.replicated_params = ("mu_loc", "mu_scale", "sd_loc", "sd_scale")  # per edit: identical on every rank
         self.num_steps = int(num_steps)
         use_bcmatch = bool(use_bcmatch) and getattr(data, "X_bcmatch_masked", None) is not None
         self.screen = DeviceScreen(data, self.device, dtype=dtype, use_bcmatch=use_bcmatch, mask_thres=10)
@@ -92,6 +95,7 @@ class TilingFusedEngine:
         c.lr0, c.lrd = float(initial_lr), float(gamma) ** (1.0 / max(self.num_steps, 1))
         c.beta1, c.beta2, c.adam_eps, c.clip = 0.9, 0.999, 1e-8, 10.0
         c.ll_const, c.seed = ll_const, int(seed)
+        c.guide_offset = int(guide_offset)
         # pi carries pi_a0's dtype in the reference (float64 out of the fit, float32 with the fallback coefficients): torch's
         # Multinomial clamps probabilities at that dtype's eps and its Dirichlet sampler at that dtype's smallest normal number
         pa0 = getattr(data, "pi_a0", None)
@@ -114,6 +118,13 @@ class TilingFusedEngine:
             if key in self._prior_v:
                 setattr(s, field, self._prior_v[key].data_ptr())
         s.epsilon, s.pi_tiny = float(epsilon), float(torch.finfo(ref_dtype).tiny)
+        if self.sharded:
+            import torch.distributed as dist
+
+            self.edit_sum = torch.zeros((2, E), **kw)
+            self.edit_iota = torch.arange(E + 1, dtype=torch.int32, device=dev)
+            s.edit_sum, s.edit_iota = self.edit_sum.data_ptr(), self.edit_iota.data_ptr()
+            s.edit_term_weight = 1.0 if dist.get_rank(group) == 0 else 0.0  # the per-edit ELBO terms count once
         self.state = s
 
     # ---------------------------------------------------------------------------------------------
@@ -149,8 +160,21 @@ class TilingFusedEngine:
         n, keep = self._noise_struct(noise)
         self.cfg.apply_update = 1 if apply_update else 0
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        rc = getattr(self.lib, _RUN[self.dtype])(self.screen.c, self.state, self.cfg, n, self.step, n_steps, stream)
-        _lib.check(rc, _RUN[self.dtype])
+        run = getattr(self.lib, _RUN[self.dtype])
+        if not self.sharded:
+            _lib.check(run(self.screen.c, self.state, self.cfg, n, self.step, n_steps, stream), _RUN[self.dtype])
+        else:
+            # per step: this shard's guides -> per-edit gradient sums; one all-reduce of 2 E numbers (edits are shared between
+            # guides of different shards); then every rank updates every edit from the same sums
+            import torch.distributed as dist
+
+            for t in range(self.step, self.step + n_steps):
+                self.cfg.phases = 1
+                _lib.check(run(self.screen.c, self.state, self.cfg, n, t, 1, stream), _RUN[self.dtype])
+                dist.all_reduce(self.edit_sum, group=self.group)
+                self.cfg.phases = 2
+                _lib.check(run(self.screen.c, self.state, self.cfg, n, t, 1, stream), _RUN[self.dtype])
+            self.cfg.phases = 0
         first = self.step
         if apply_update:
             self.step += n_steps
@@ -173,6 +197,12 @@ class TilingFusedEngine:
 
     def losses(self):
         return self.loss[: self.step].cpu()
+
+
+def _dist_active(group) -> bool:
+    import torch.distributed as dist
+
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
 def C_pointer(struct):

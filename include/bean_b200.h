@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 13
+#define BEAN_ABI_VERSION 14
 
 enum {
   BEAN_OK = 0,
@@ -354,6 +354,14 @@ typedef struct BeanTilingState {
   const void* sd_prior_scale_v;
   double epsilon;                /* the model's epsilon (1e-5) */
   double pi_tiny;                /* lower clamp of the pi draws = smallest normal number of the dtype pi has in the reference */
+  /* Guides sharded over ranks (every rank holds ALL edits: an edit's alleles sit in guides of several shards).  With edit_sum
+   * set, BeanSviConfig.phases splits the step: bit 0 = draws + guide kernel + per-edit sums of this shard's allele-slot
+   * gradients into edit_sum (no update); the host all-reduces edit_sum over the ranks; bit 1 = priors, guide densities and
+   * ClippedAdam of every edit from the reduced sums (identical on every rank) + loss[t].  edit_term_weight scales the
+   * per-edit ELBO terms in loss[t] (1 on one rank, 0 on the others, so that the ranks' losses add up). */
+  void* edit_sum;                /* real [2][E] or NULL (not sharded) */
+  const int32_t* edit_iota;      /* i32 [E + 1] = 0, 1, ..., E (needed with edit_sum) */
+  double edit_term_weight;
 } BeanTilingState;
 typedef struct BeanTilingNoise { /* all optional */
   const void* eps_mu;            /* real [E] */

@@ -187,3 +187,58 @@ def test_run_inference_shards_over_the_ranks_of_torch_distributed(tmp_path):
         torch.testing.assert_close(res["survival"]["loss"], torch.tensor(ssolo["loss"]), rtol=1e-4, atol=0)
         for k, v in ssolo["params"].items():
             torch.testing.assert_close(res["survival"]["params"][k], v, rtol=1e-3, atol=1e-3 * v.abs().mean().item())
+
+
+def _tiling_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from crispr_bean_b200 import model as sm
+    from crispr_bean_b200.data_class import TilingSortingReporterScreenData
+    from crispr_bean_b200.dist import shard_data
+    from crispr_bean_b200.run import run_inference
+    from crispr_bean_b200.synth import make_tiling_screen
+    from crispr_bean_b200.tiling_fused import TilingFusedEngine
+
+    solo = dist.new_group([rank], use_local_synchronization=True)
+    scr = make_tiling_screen(n_guides=90, max_alleles=8, n_reps=3, seed=11)
+    data = TilingSortingReporterScreenData(scr, control_can_be_selected=True, allele_df_key="allele_counts")
+    sub, off = shard_data(data, rank, world)
+    res = {}
+    for dtype in (torch.float64, torch.float32):
+        eng = TilingFusedEngine(sub, f"cuda:{rank}", dtype=dtype, num_steps=10, seed=4, guide_offset=off["guide_offset"])
+        eng.run(10)
+        loss = eng.losses().to(f"cuda:{rank}")
+        dist.all_reduce(loss)
+        full = TilingFusedEngine(data, f"cuda:{rank}", dtype=dtype, num_steps=10, seed=4, group=solo)  # unsharded, same seed
+        full.run(10)
+        res[str(dtype)] = {"loss": loss.cpu(), "full_loss": full.losses(), "off": off,
+                           "got": {k: v.cpu() for k, v in eng.params().items()}, "full": {k: v.cpu() for k, v in full.params().items()}}
+    # and through the seam: run_inference shards the tiling design over the ranks and returns the whole screen's result
+    params, hist = run_inference(sm.MultiMixtureNormalModel, sm.MultiMixtureNormalGuide, data, num_steps=10, device=f"cuda:{rank}",
+                                 dtype=torch.float64, seed=4)
+    res["seam"] = {"loss": torch.tensor(hist["loss"]), "params": {k: torch.as_tensor(v).cpu() for k, v in hist["params"].items()}}
+    torch.save(res, f"{out_dir}/t{rank}.pt")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_tiling_run_sharded_over_two_gpus_equals_single_gpu(tmp_path):
+    """10 free-running steps of the tiling step with the guides split over two GPUs (all edits on both, their gradient sums
+    all-reduced every step; Philox draws keyed by global guide ids): the same losses and parameters as on one GPU."""
+    port = 29990 + os.getpid() % 9
+    mp.spawn(_tiling_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        res = torch.load(f"{tmp_path}/t{rank}.pt")
+        for dtype in ("torch.float64", "torch.float32"):
+            r = res[dtype]
+            tol = 1e-9 if "64" in dtype else 1e-4
+            torch.testing.assert_close(r["loss"], r["full_loss"], rtol=tol, atol=0)
+            gb, ge = r["off"]["guide_offset"], r["off"]["guide_offset"] + r["off"]["n_guides"]
+            for k, g in r["got"].items():
+                f = r["full"][k][gb:ge] if k == "alpha_pi" else r["full"][k]   # per-edit parameters: replicated on every rank
+                torch.testing.assert_close(g.double(), f.double(), rtol=tol * 10, atol=tol * 10 * f.abs().mean().item())
+        seam, full = res["seam"], res["torch.float64"]
+        torch.testing.assert_close(seam["loss"], full["full_loss"], rtol=1e-9, atol=0)
+        for k, v in full["full"].items():
+            torch.testing.assert_close(seam["params"][k].double().reshape(v.shape), v.double(), rtol=1e-8, atol=1e-8 * v.abs().mean().item())
