@@ -220,7 +220,9 @@ def main():
     footprint = 700.0 * nv * gpv / (world if args.scaling == "strong" else 1)
     flush = footprint < 2 * 126e6
     exchange = (f"per-step ELBO scalars all-reduced over NCCL every {LOSS_BATCH} steps" +
-                (f" + the {R + 1} library-wide sums of the abundance Dirichlet all-reduced EVERY step" if survival else "") +
+                (f" + the {R + 1} library-wide sums of the abundance Dirichlet exchanged EVERY step (through CUDA-IPC peer memory inside "
+                 f"the kernels where the steps run many per call; an NCCL all-reduce between the launches where every step is "
+                 f"timed on its own)" if survival else "") +
                 ", inside the timed region")
     config = {"workload": f"{args.workload}: {program}, {G_total} guides x {R} reps x {B} bins in total, "
                           f"bcmatch layer + reporter edits",

@@ -463,7 +463,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
   if (noise && (noise->eps_mu || noise->eps_sd))
     BEAN_REQUIRE(noise->eps_mu && noise->eps_sd, BEAN_EINVAL, "eps_mu and eps_sd must be injected together");
 
-  SviParams<real> p;
+  SviParams<real> p{};  // zero: every optional pointer NULL, every mode flag off
   p.G = s->n_guides; p.R = s->n_reps; p.B = s->n_bins; p.L = s->n_layers; p.T = state->n_variants;
   p.mixture = mix; p.sd_is_sqrt = cfg->sd_is_sqrt; p.mu_prior_normal = cfg->mu_prior_normal; p.apply_update = cfg->apply_update;
   p.seed = cfg->seed;

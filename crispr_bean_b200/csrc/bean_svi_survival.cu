@@ -355,7 +355,7 @@ static int survival_run(const BeanScreen* s, const BeanSviState* state, const Be
   BEAN_REQUIRE(first_step >= 0 && n_steps >= 0 && first_step + n_steps <= state->loss_capacity, BEAN_EINVAL, "bad step range %d + %d (capacity %d)",
                first_step, n_steps, state->loss_capacity);
 
-  SviParams<real> p;
+  SviParams<real> p{};  // zero: every optional pointer NULL, every mode flag off
   memset(&p, 0, sizeof(p));
   p.G = s->n_guides; p.R = s->n_reps; p.B = s->n_bins; p.L = s->n_layers; p.T = state->n_variants;
   p.mixture = 1; p.has_sd = 0; p.mu_prior_normal = cfg->mu_prior_normal; p.apply_update = cfg->apply_update;

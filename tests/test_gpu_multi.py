@@ -217,7 +217,7 @@ def _tiling_worker(rank, world, port, out_dir):
     # and through the seam: run_inference shards the tiling design over the ranks and returns the whole screen's result
     params, hist = run_inference(sm.MultiMixtureNormalModel, sm.MultiMixtureNormalGuide, data, num_steps=10, device=f"cuda:{rank}",
                                  dtype=torch.float64, seed=4)
-    res["seam"] = {"loss": torch.tensor(hist["loss"]), "params": {k: torch.as_tensor(v).cpu() for k, v in hist["params"].items()}}
+    res["seam"] = {"loss": torch.tensor(hist["loss"], dtype=torch.float64), "params": {k: torch.as_tensor(v).cpu() for k, v in hist["params"].items()}}
     torch.save(res, f"{out_dir}/t{rank}.pt")
     dist.destroy_process_group()
 
