@@ -121,7 +121,7 @@ static int launch_dirichlet(const BeanDirichletArgs* a, void* stream) {
                BEAN_MAX_ALLELES);
   BEAN_REQUIRE(a->conc && a->x, BEAN_EINVAL, "conc / x must be non-NULL");
   if (GRAD) BEAN_REQUIRE(a->grad_x && a->d_conc, BEAN_EINVAL, "grad_x / d_conc must be non-NULL");
-  DirichletParams<real> p;
+  DirichletParams<real> p{};
   p.G = a->n_guides; p.R = a->n_reps; p.A = a->n_alleles;
   p.conc = static_cast<const real*>(a->conc);
   p.x = static_cast<real*>(a->x);

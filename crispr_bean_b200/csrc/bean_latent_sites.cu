@@ -97,7 +97,7 @@ static int launch_latent(const BeanLatentSitesArgs* a, void* stream) {
   BEAN_REQUIRE(!a->has_sd || (a->sd_loc && a->sd_log_scale && a->eps_sd && a->sd), BEAN_EINVAL, "sd site buffers must be non-NULL");
   BEAN_REQUIRE(!a->mu_prior_normal || a->mu_prior_scale_v || a->mu_prior_scale > 0, BEAN_EINVAL, "mu prior scale must be > 0");
   BEAN_REQUIRE(!a->has_sd || a->sd_prior_scale_v || a->sd_prior_scale > 0, BEAN_EINVAL, "sd prior scale must be > 0");
-  LatentParams<real> p;
+  LatentParams<real> p{};
   p.n = a->n; p.has_sd = a->has_sd; p.mu_prior_normal = a->mu_prior_normal;
   p.mu_loc = static_cast<const real*>(a->mu_loc); p.mu_ls = static_cast<const real*>(a->mu_log_scale);
   p.sd_loc = static_cast<const real*>(a->sd_loc); p.sd_ls = static_cast<const real*>(a->sd_log_scale);
@@ -118,7 +118,7 @@ static int launch_latent_grad(const BeanLatentSitesGradArgs* a, void* stream) {
   BEAN_REQUIRE(a != nullptr && a->n > 0, BEAN_EINVAL, "args is NULL or n <= 0");
   BEAN_REQUIRE(a->mu_log_scale && a->eps_mu && a->dv && a->grad, BEAN_EINVAL, "mu site buffers must be non-NULL");
   BEAN_REQUIRE(!a->has_sd || (a->sd_log_scale && a->eps_sd && a->sd), BEAN_EINVAL, "sd site buffers must be non-NULL");
-  LatentGradParams<real> p;
+  LatentGradParams<real> p{};
   p.n = a->n; p.has_sd = a->has_sd;
   p.mu_ls = static_cast<const real*>(a->mu_log_scale); p.sd_ls = static_cast<const real*>(a->sd_log_scale);
   p.eps_mu = static_cast<const real*>(a->eps_mu); p.eps_sd = static_cast<const real*>(a->eps_sd);

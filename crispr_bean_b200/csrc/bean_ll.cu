@@ -239,7 +239,7 @@ static int launch_ll(const BeanScreen* s, const BeanLLArgs* a, void* stream) {
   BEAN_REQUIRE(a->pi != nullptr || a->n_alleles == 1, BEAN_EINVAL, "pi may only be NULL when n_alleles == 1");
   BEAN_REQUIRE(a->ll_partial && a->d_mu && a->d_sd, BEAN_EINVAL, "ll_partial / d_mu / d_sd must be non-NULL");
   BEAN_REQUIRE(a->pi == nullptr || a->d_pi != nullptr, BEAN_EINVAL, "d_pi must be non-NULL when pi is given");
-  LLParams<real> p;
+  LLParams<real> p{};
   p.G = s->n_guides; p.R = s->n_reps; p.B = s->n_bins; p.L = s->n_layers; p.A = a->n_alleles; p.mode = s->mode;
   p.mask_thres = real(s->mask_thres);
   p.x = static_cast<const real*>(s->x);

@@ -51,7 +51,7 @@ static int launch_adam(const BeanAdamArgs* a, void* stream) {
                a->n_tensors, BEAN_ADAM_MAX_TENSORS);
   BEAN_REQUIRE(a->step_sizes && a->step && a->n_steps >= 1, BEAN_EINVAL, "step_sizes / step must be non-NULL, n_steps >= 1");
   BEAN_REQUIRE(a->clip > 0 && a->beta1 >= 0 && a->beta1 < 1 && a->beta2 >= 0 && a->beta2 < 1, BEAN_EINVAL, "bad optimiser constants");
-  AdamParams<real> p;
+  AdamParams<real> p{};
   long long n_max = 0;
   for (int i = 0; i < a->n_tensors; ++i) {
     const BeanAdamTensor& s = a->tensors[i];

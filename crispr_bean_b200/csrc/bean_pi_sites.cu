@@ -158,7 +158,7 @@ static int launch_pi_sites(const BeanPiSitesArgs* a, void* stream) {
   BEAN_REQUIRE((a->growth == nullptr) == (a->d_growth == nullptr), BEAN_EINVAL, "growth and d_growth go together");
   BEAN_REQUIRE(a->growth == nullptr || a->control_time != nullptr, BEAN_EINVAL, "growth needs control_time");
   BEAN_REQUIRE(a->prob_eps > 0 && a->prob_eps < 0.5, BEAN_EINVAL, "prob_eps out of range");
-  PiSitesParams<real> p;
+  PiSitesParams<real> p{};
   p.G = a->n_guides; p.R = a->n_reps; p.A = a->n_alleles; p.C = a->n_controls; p.mask_guide_site = a->mask_guide_site;
   p.conc_g = static_cast<const real*>(a->conc_guide);
   p.conc_m = static_cast<const real*>(a->conc_model);
