@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(SVI_THREADS, ((SPLIT || !MIXTURE) && sizeof(re
 #endif
   __shared__ __align__(16) float4 s_x[STAGE ? 2 * BEAN_MAX_LAYERS * SVI_THREADS : 1];  // [buffer][layer][thread]
   __shared__ __align__(8) float2 s_ac[STAGE ? 2 * SVI_THREADS : 1];                    // [buffer][thread]
+  grid_dependency_wait();
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = FAST ? NB : p.B;
   constexpr bool LFIX = FAST == 2;  // both count layers present (all reads + barcode-matched reads): L is a constant
@@ -423,19 +424,19 @@ static void launch_guide(const SviParams<real>& p, cudaStream_t st, bool guide, 
   constexpr bool HAS_FAST = true;
   if (!guide) {
   } else if (HAS_FAST && fast && p.B == 4 && p.L == 2)
-    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 2><<<grid, SVI_THREADS, 0, st>>>(p);
+    launch_after(svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 2>, grid, SVI_THREADS, st, p);
   else if (HAS_FAST && fast && p.B == 4)
-    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 1><<<grid, SVI_THREADS, 0, st>>>(p);
+    launch_after(svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 1>, grid, SVI_THREADS, st, p);
   else if (HAS_FAST && fast && p.B == 5)
-    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, 1><<<grid, SVI_THREADS, 0, st>>>(p);
+    launch_after(svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, 1>, grid, SVI_THREADS, st, p);
   else if (p.B <= 4)
-    svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 0><<<grid, SVI_THREADS, 0, st>>>(p);
+    launch_after(svi_guide_kernel<real, 4, MIXTURE, ACC, SPLIT, 0>, grid, SVI_THREADS, st, p);
   else if (p.B == 5)
-    svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, 0><<<grid, SVI_THREADS, 0, st>>>(p);
+    launch_after(svi_guide_kernel<real, 5, MIXTURE, ACC, SPLIT, 0>, grid, SVI_THREADS, st, p);
   else
-    svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC, SPLIT, 0><<<grid, SVI_THREADS, 0, st>>>(p);
+    launch_after(svi_guide_kernel<real, BEAN_MAX_BINS, MIXTURE, ACC, SPLIT, 0>, grid, SVI_THREADS, st, p);
   // (one thread per (guide, replicate) with a shuffle reduction was tried for this kernel: 0.42 vs 0.27 ms)
-  if (MIXTURE && SPLIT && alpha) svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
+  if (MIXTURE && SPLIT && alpha) launch_after(svi_alpha_kernel<real>, (p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, st, p);
 }
 
 template <typename real>
@@ -548,7 +549,7 @@ static int svi_run(const BeanScreen* s, const BeanSviState* state, const BeanSvi
       else if (mix) { if (split) launch_guide<real, true, false, true>(p, st, do_guide, do_alpha, fast); else launch_guide<real, true, false, false>(p, st, do_guide, false, fast); }
       else launch_guide<real, false, false, false>(p, st, do_guide, false, fast);
     }
-    if (ph & 2) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
+    if (ph & 2) launch_after(svi_variant_kernel<real>, p.n_partial_var, VAR_THREADS, st, p);
   }
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;

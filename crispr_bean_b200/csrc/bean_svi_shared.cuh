@@ -21,9 +21,11 @@ constexpr int SVI_MIN_CTAS_SPLIT = BEAN_GUIDE_MIN_CTAS;  // split guide step and
 // ELBO partials are per WARP (no CTA barrier: per-guide cost varies with the Dirichlet-gradient regime of its draws,
 // so the warps of a CTA finish far apart).  1-warp CTAs were tried and were 4 % slower.
 constexpr int SVI_WARP = 32;
-constexpr int VAR_THREADS = 256;
-constexpr int VAR_LANES = 8;  // lanes cooperating on one variant
-constexpr int VAR_PER_CTA = VAR_THREADS / VAR_LANES;
+#ifndef BEAN_VAR_THREADS
+#define BEAN_VAR_THREADS 256
+#endif
+constexpr int VAR_THREADS = BEAN_VAR_THREADS;
+constexpr int VAR_PER_CTA = VAR_THREADS;  // one thread per variant
 
 template <typename real>
 struct SviParams {
@@ -172,6 +174,33 @@ template <typename real> struct SaddleOf;
 template <> struct SaddleOf<float> { typedef SaddlePairF type; };
 template <> struct SaddleOf<double> { typedef SaddlePair type; };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with `launch_after` may have its CTAs scheduled while the kernel
+// before it on the stream is still draining; it must call `grid_dependency_wait()` before it touches anything that kernel wrote
+// (here: first thing).  What this buys is the launch latency and ramp-up of three dependent kernels per step -- a few
+// microseconds each, which is what a step is made of once a screen is split over eight GPUs.
+#ifndef BEAN_NO_PDL
+#define BEAN_PDL 1
+#endif
+__device__ __forceinline__ void grid_dependency_wait() {
+#ifdef BEAN_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+template <typename Kernel, typename Params>
+static inline void launch_after(Kernel kernel, int grid, int block, cudaStream_t st, const Params& p) {
+#ifdef BEAN_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, p);
+#else
+  kernel<<<grid, block, 0, st>>>(p);
+#endif
+}
+
 // Second half of the split guide step: pathwise Dirichlet derivative of every draw (saddle-point pairs in place, the other
 // regimes through the per-warp queue), alpha_pi gradient and its ClippedAdam update.  One thread per guide.
 // one warp per CTA: the work per draw differs by regime, and small CTAs hand their SM slot on as soon as their own 32 guides are
@@ -187,6 +216,7 @@ template <typename real>
 __global__ void __launch_bounds__(ALPHA_THREADS, BEAN_ALPHA_MIN_CTAS) svi_alpha_kernel(const SviParams<real> p) {
   __shared__ TailQueue<real> tail_queues[ALPHA_THREADS / SVI_WARP];
   __shared__ float s_near_mean[6][ALPHA_THREADS];
+  grid_dependency_wait();
   const int g = blockIdx.x * ALPHA_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const real eps = real(1e-5);
@@ -282,54 +312,69 @@ __device__ __forceinline__ double column_sums(const double* a, int n_rows, int C
   return tot;
 }
 
-// One step's per-variant work: the segmented sum of the guides' (d mu, d sd) over the variant's guide range (VAR_LANES lanes
-// per variant, coalesced), then -- compacted through shared memory so that the first warp runs it with every lane busy instead
-// of one lane in VAR_LANES -- the draw, priors, entropy and ClippedAdam of the variant.  Every CTA also folds its slice of the
-// guide kernel's ELBO partials into its own partial, so the last CTA's fixed-order reduction reads n_partial_var numbers, not
-// n_partial_guide + n_partial_var (31 k + 6 k at c5: that serial tail was a third of this kernel's time).
+// One step's per-variant work, ONE THREAD PER VARIANT: the segmented sum of the guides' (d mu, d sd) over the variant's guide
+// range, then the draw, priors, entropy and ClippedAdam of the variant.  A variant has a handful of guides (5 at c5), whose
+// gradients sit in L2: one thread walking them in order beats 8 cooperating lanes by 3 x (0.042 -> 0.013 ms at c5, measured
+// for 8 / 4 / 2 / 1 lanes: profiles/r2aa_, r2ab_variants.jsonl) because every lane then also has a variant to update.  Segments
+// longer than VAR_SHORT_SEG (a variant with hundreds of guides; the tiling step's edits shared by many alleles) are summed by
+// the whole warp instead, strided and tree-reduced -- both orders are fixed, the result is deterministic.  Every CTA also folds
+// its slice of the guide kernel's ELBO partials into its own partial, so the last CTA's fixed-order reduction reads
+// n_partial_var numbers, not n_partial_guide + n_partial_var.
+constexpr int VAR_SHORT_SEG = 32;
 template <typename real>
 __global__ void __launch_bounds__(VAR_THREADS) svi_variant_kernel(const SviParams<real> p) {
   __shared__ double red[32];
   __shared__ bool is_last;
-  __shared__ real s_d[2][VAR_PER_CTA];
   __shared__ double s_cs[VAR_THREADS];
-  const int vl = threadIdx.x / VAR_LANES;
-  const int sub = threadIdx.x % VAR_LANES;
+  grid_dependency_wait();
+  const int v = blockIdx.x * VAR_PER_CTA + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  real dmu = real(0), dsd = real(0);
   {
-    const int v = blockIdx.x * VAR_PER_CTA + vl;
-    // segmented reduction of the guide gradients over the variant's contiguous guide range
-    real dmu = real(0), dsd = real(0);
+    int beg = 0, end = 0;
     if (v < p.T) {
-      const int beg = p.variant_ptr[v], end = p.variant_ptr[v + 1];
-      for (int j = beg + sub; j < end; j += VAR_LANES) {
+      beg = p.variant_ptr[v];
+      end = p.variant_ptr[v + 1];
+    }
+    const bool is_long = end - beg > VAR_SHORT_SEG;
+    if (!is_long) {
+      for (int j = beg; j < end; ++j) {
         const int k = p.gather_idx ? p.gather_idx[j] : j;
         dmu += p.d_guide[k];
         if (p.has_sd) dsd += p.d_guide[(size_t)p.G + k];
       }
     }
-#pragma unroll
-    for (int o = VAR_LANES / 2; o > 0; o >>= 1) {
-      dmu += __shfl_xor_sync(0xffffffffu, dmu, o);
-      dsd += __shfl_xor_sync(0xffffffffu, dsd, o);
-    }
-    if (sub == 0) {
-      s_d[0][vl] = dmu;
-      s_d[1][vl] = dsd;
-      if (p.seg_sum_out && v < p.T) {
-        p.seg_sum_out[v] = dmu;
-        p.seg_sum_out[(size_t)p.T + v] = dsd;
+    unsigned todo = __ballot_sync(0xffffffffu, is_long);
+    while (todo) {  // warp-uniform
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1u;
+      const int b0 = __shfl_sync(0xffffffffu, beg, src), e0 = __shfl_sync(0xffffffffu, end, src);
+      real a = real(0), c = real(0);
+      for (int j = b0 + lane; j < e0; j += 32) {
+        const int k = p.gather_idx ? p.gather_idx[j] : j;
+        a += p.d_guide[k];
+        if (p.has_sd) c += p.d_guide[(size_t)p.G + k];
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+      }
+      if (lane == src) {
+        dmu = a;
+        dsd = c;
+      }
+    }
+    if (p.seg_sum_out && v < p.T) {
+      p.seg_sum_out[v] = dmu;
+      p.seg_sum_out[(size_t)p.T + v] = dsd;
     }
   }
   if (p.seg_sum_out) return;  // reduce-only launch (grid-uniform)
   // this CTA's slice of the guide kernel's partials (fixed assignment: deterministic)
   double elbo = 0.0;
   for (int i = blockIdx.x * VAR_THREADS + threadIdx.x; i < p.n_partial_guide; i += gridDim.x * VAR_THREADS) elbo += p.partial[i];
-  __syncthreads();
-  const int v = blockIdx.x * VAR_PER_CTA + threadIdx.x;
-  if (threadIdx.x < VAR_PER_CTA && v < p.T) {
-    const real dmu = s_d[0][threadIdx.x];
-    real dsd = s_d[1][threadIdx.x];
+  if (v < p.T) {
     real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y;
     variant_draw(p, v, mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, y);
     if (p.eps_out) {

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(VAR_THREADS) surv_sums_kernel(const SviParams<
 #endif
 template <typename real, int NB, bool EXACT>
 __global__ void __launch_bounds__(SVI_THREADS, sizeof(real) == 4 ? BEAN_SURV_MIN_CTAS : 3) surv_guide_kernel(const SviParams<real> p) {
+  grid_dependency_wait();
   const int g = blockIdx.x * SVI_THREADS + threadIdx.x;
   const int R = p.R, B = EXACT ? NB : p.B;
   const real eps = real(1e-5);
@@ -440,14 +441,14 @@ static int survival_run(const BeanScreen* s, const BeanSviState* state, const Be
     const int ph = cfg->phases == 0 ? 7 : cfg->phases;
     if (ph & 1) {
       if (p.B == 3)
-        surv_guide_kernel<real, 3, true><<<grid, SVI_THREADS, 0, st>>>(p);
+        launch_after(surv_guide_kernel<real, 3, true>, grid, SVI_THREADS, st, p);
       else if (p.B <= 4)
-        surv_guide_kernel<real, 4, false><<<grid, SVI_THREADS, 0, st>>>(p);
+        launch_after(surv_guide_kernel<real, 4, false>, grid, SVI_THREADS, st, p);
       else
-        surv_guide_kernel<real, BEAN_MAX_BINS, false><<<grid, SVI_THREADS, 0, st>>>(p);
+        launch_after(surv_guide_kernel<real, BEAN_MAX_BINS, false>, grid, SVI_THREADS, st, p);
     }
-    if (ph & 4) svi_alpha_kernel<real><<<(p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, 0, st>>>(p);
-    if (ph & 2) svi_variant_kernel<real><<<p.n_partial_var, VAR_THREADS, 0, st>>>(p);
+    if (ph & 4) launch_after(svi_alpha_kernel<real>, (p.G + ALPHA_THREADS - 1) / ALPHA_THREADS, ALPHA_THREADS, st, p);
+    if (ph & 2) launch_after(svi_variant_kernel<real>, p.n_partial_var, VAR_THREADS, st, p);
   }
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;

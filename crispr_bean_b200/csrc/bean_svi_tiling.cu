@@ -94,6 +94,7 @@ __device__ __forceinline__ double tiling_gamma(uint64_t seed, uint32_t g, uint32
 
 template <typename real>
 __global__ void __launch_bounds__(VAR_THREADS) tiling_draw_kernel(const SviParams<real> p, real* mu_e, real* sd_e) {
+  grid_dependency_wait();
   const int e = blockIdx.x * VAR_THREADS + threadIdx.x;
   if (e >= p.T) return;
   real mu_t, sd_t, e_mu, e_sd, mu_scale, sd_scale, log_sd;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(VAR_THREADS) tiling_draw_kernel(const SviParam
 // repeats the cheap prologue (concentrations, allele mean / sd, bin masses).
 template <typename real, int NB>
 __global__ void __launch_bounds__(TILING_MAX_REP_WARPS * 32) tiling_guide_kernel(const TilingParams<real> p) {
+  grid_dependency_wait();
   __shared__ double s_elbo[TILING_MAX_REP_WARPS][32], s_slp[TILING_MAX_REP_WARPS][32], s_path[TILING_MAX_REP_WARPS][32];
   __shared__ real s_dP[TILING_MAX_REP_WARPS][NB][32];
   __shared__ int s_nin[TILING_MAX_REP_WARPS];
@@ -406,15 +408,15 @@ static int tiling_run(const BeanScreen* s, const BeanTilingState* ts, const Bean
     const double lr = cfg->lr0 * pow(cfg->lrd, (double)(t + 1));
     v.step_size = u.step_size = p.step_size = real(lr * sqrt(1.0 - pow(cfg->beta2, (double)(t + 1))) / (1.0 - pow(cfg->beta1, (double)(t + 1))));
     if (sharded && cfg->phases == 2) {
-      svi_variant_kernel<real><<<u.n_partial_var, VAR_THREADS, 0, st>>>(u);
+      launch_after(svi_variant_kernel<real>, u.n_partial_var, VAR_THREADS, st, u);
       continue;
     }
     tiling_draw_kernel<real><<<(E + VAR_THREADS - 1) / VAR_THREADS, VAR_THREADS, 0, st>>>(v, static_cast<real*>(ts->mu_e), static_cast<real*>(ts->sd_e));
     if (s->n_bins <= 4)  // bin arrays of 4 instead of BEAN_MAX_BINS registers: more guides resident per SM
-      tiling_guide_kernel<real, 4><<<G, n_rep_warps * 32, 0, st>>>(p);
+      launch_after(tiling_guide_kernel<real, 4>, G, n_rep_warps * 32, st, p);
     else
-      tiling_guide_kernel<real, BEAN_MAX_BINS><<<G, n_rep_warps * 32, 0, st>>>(p);
-    svi_variant_kernel<real><<<v.n_partial_var, VAR_THREADS, 0, st>>>(v);
+      launch_after(tiling_guide_kernel<real, BEAN_MAX_BINS>, G, n_rep_warps * 32, st, p);
+    launch_after(svi_variant_kernel<real>, v.n_partial_var, VAR_THREADS, st, v);
   }
   BEAN_CUDA(cudaPeekAtLastError());
   return BEAN_OK;
