@@ -112,3 +112,15 @@ def test_every_dirichlet_gradient_regime_and_queue_flush(cuda_device, dtype, tol
             assert rel_err(got[k], ref[k]) <= tol, (k, small)
         assert rel_err(got["alpha_pi"], ref["alpha_pi"]) <= tol_alpha, small
         assert torch.isfinite(got["alpha_pi"]).all()
+
+
+@pytest.mark.parametrize("dtype,tol,tol_alpha", CASES)
+def test_long_and_short_guide_segments_in_one_warp(cuda_device, dtype, tol, tol_alpha):
+    """The per-variant kernel sums a variant's guides in one thread up to 32 of them and with the whole warp beyond: variants
+    with 45 guides (warp-cooperative), with 33 (just over) and the 6-guide control variant (sequential), all in one warp."""
+    a = make_sorting_screen(5, 45, n_reps=2, seed=41, depth=200.0, n_negctrl_guides=6)
+    data = VariantSortingReporterScreenData(a, control_can_be_selected=True)
+    assert int(data.target_lengths.max()) == 45 and int(data.target_lengths.min()) == 6
+    check_grads("MixtureNormal", data, cuda_device, dtype, tol, tol_alpha, perturb_seed=3)
+    b = make_sorting_screen(3, 33, n_reps=2, seed=43, depth=200.0)
+    check_grads("MixtureNormal", VariantSortingReporterScreenData(b, control_can_be_selected=True), cuda_device, dtype, tol, tol_alpha, perturb_seed=5)
