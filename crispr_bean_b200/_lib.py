@@ -163,7 +163,7 @@ class BeanTilingNoise(C.Structure):
 
 SURV_PRIME_NONE, SURV_PRIME_AND_RUN, SURV_PRIME_ONLY = 0, 1, 2
 MODEL_NORMAL, MODEL_MIXTURE_NORMAL = 0, 1
-ABI_VERSION = 14  # include/bean_b200.h: BEAN_ABI_VERSION
+ABI_VERSION = 15  # include/bean_b200.h: BEAN_ABI_VERSION
 _GATHER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _SCATTER = [C.POINTER(BeanAlleleMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -188,6 +188,8 @@ _PROTOTYPES = {
     "bean_svi_survival_run_f64": (C.c_int, [C.POINTER(BeanScreen), C.POINTER(BeanSviState), C.POINTER(BeanSurvivalState),
                                             C.POINTER(BeanSviConfig), C.POINTER(BeanSviNoise), C.POINTER(BeanSurvivalNoise),
                                             C.c_int32, C.c_int32, C.c_void_p]),
+    "bean_row_const_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bean_row_const_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bean_peer_exchange_bytes": (C.c_int, []),
     "bean_peer_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
     "bean_peer_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),

@@ -28,6 +28,29 @@ def _dptr(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+_LOG_FACTORIAL = {}  # device -> f64 [4096] table of ln k!
+_ROW_CONST = {torch.float32: "bean_row_const_f32", torch.float64: "bean_row_const_f64"}
+
+
+def row_constants(x: torch.Tensor, with_xlogx: bool):
+    """`bean_row_const_*` on a contiguous CUDA tensor of counts (..., B): per row lgamma(N + 1) - sum lgamma(x + 1)
+    [+ sum x ln(x / max(N, 1))] and N, both float64 of shape x.shape[:-1].  One pass; asynchronous on the current stream."""
+    if not x.is_cuda:
+        raise _lib.BeanError("bean_row_const needs a CUDA tensor: there is no CPU fallback")
+    x = x.contiguous()
+    dev = x.device
+    if dev not in _LOG_FACTORIAL:
+        _LOG_FACTORIAL[dev] = torch.lgamma(torch.arange(1, 4097, dtype=torch.float64)).to(dev)
+    table = _LOG_FACTORIAL[dev]
+    rc = torch.empty(x.shape[:-1], dtype=torch.float64, device=dev)
+    tot = torch.empty(x.shape[:-1], dtype=torch.float64, device=dev)
+    name = _ROW_CONST[x.dtype]
+    rc_code = getattr(_lib.lib(), name)(x.data_ptr(), rc.numel(), x.shape[-1], 1 if with_xlogx else 0, table.data_ptr(), table.numel(),
+                                        rc.data_ptr(), tot.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc_code, name)
+    return rc, tot
+
+
 class DeviceScreen:
     """Device-resident, replicate-major copy of the per-step data of a *ScreenData object."""
 
@@ -56,13 +79,10 @@ class DeviceScreen:
             self._tp = np.ascontiguousarray(data.timepoints.double().numpy())
         # data-only part of every row's Dirichlet-Multinomial log-pmf, hoisted out of the SVI loop
         # (recomputed every step by the reference: L*(B+1) of its L*(3B+3) lgammas per row)
-        x64 = self.x.double()
-        n64 = x64.sum(-1)
-        self.row_const = (torch.lgamma(n64 + 1) - torch.lgamma(x64 + 1).sum(-1)
-                          + torch.xlogy(x64, x64 / n64.clamp(min=1.0).unsqueeze(-1)).sum(-1)).contiguous()  # (L, R, G)
+        self.row_const, n64 = row_constants(self.x, with_xlogx=True)  # (L, R, G) float64, one pass (csrc/bean_row_const.cu)
         self.row_weight = (n64 > self.mask_thres) & (self.row_mask != 0).unsqueeze(0)  # (L, R, G)
         self.ll_const = float((self.row_const * self.row_weight).sum())
-        del x64, n64
+        del n64
         s = _lib.BeanScreen()
         s.n_guides, s.n_reps, s.n_bins, s.n_layers = G, R, B, self.n_layers
         s.mode, s.mask_thres = self.mode, self.mask_thres

@@ -23,7 +23,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .device_pack import DeviceScreen
+from .device_pack import DeviceScreen, row_constants
 
 _RUN = {torch.float32: "bean_svi_survival_run_f32", torch.float64: "bean_svi_survival_run_f64"}
 
@@ -85,8 +85,7 @@ class SurvivalFusedEngine:
         self.pw, self.dconc = torch.empty((R, G, 4), **kw), torch.empty((G, 4), **kw)
         self.step, self._primed = 0, False
         # data-only parts of the ELBO: Dirichlet-Multinomial rows (DeviceScreen) + the reporter Multinomial's coefficient
-        a64 = self.allele_counts.double()
-        mconst = torch.lgamma(a64.sum(-1) + 1) - torch.lgamma(a64 + 1).sum(-1)  # (R, C, G)
+        mconst, _ = row_constants(self.allele_counts, with_xlogx=False)  # (R, C, G)
         ll_const = self.screen.ll_const + float((mconst * (self.screen.row_mask != 0).unsqueeze(1)).sum())
 
         c = _lib.BeanSviConfig()

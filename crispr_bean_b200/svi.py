@@ -13,7 +13,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .device_pack import DeviceScreen
+from .device_pack import DeviceScreen, row_constants
 
 _RUN = {torch.float32: "bean_svi_run_f32", torch.float64: "bean_svi_run_f64"}
 VAR_PARAM_NAMES = ("mu_loc", "mu_scale", "sd_loc", "sd_scale")  # rows of var_params; scales stored as log
@@ -67,8 +67,7 @@ class SviEngine:
             self.allele_counts = ac.to(dev, non_blocking=True)[:, 0].to(dtype).contiguous()  # (R, G, 2)
             self.pi_a0 = torch.as_tensor(data.pi_a0).to(**kw).contiguous()
             # data-only part of the Multinomial log-pmf, masked like the site (model.py:455, :470-474)
-            a64 = self.allele_counts.double()
-            mconst = torch.lgamma(a64.sum(-1) + 1) - torch.lgamma(a64 + 1).sum(-1)  # (R, G)
+            mconst, _ = row_constants(self.allele_counts, with_xlogx=False)  # (R, G)
             ll_const += float((mconst * (self.screen.row_mask != 0)).sum())
         self.acc = bool(scale_by_accessibility) and self.mixture
         self.fit_noise = bool(fit_noise) and self.acc

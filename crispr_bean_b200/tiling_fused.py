@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .device_pack import DeviceScreen
+from .device_pack import DeviceScreen, row_constants
 from .tiling import AlleleMap
 
 _RUN = {torch.float32: "bean_svi_tiling_run_f32", torch.float64: "bean_svi_tiling_run_f64"}
@@ -65,8 +65,7 @@ class TilingFusedEngine:
         self.loss = torch.zeros(max(self.num_steps, 1) + 1, dtype=torch.float64, device=dev)
         self.step = 0
         # data-only parts of the ELBO: Dirichlet-Multinomial rows + the reporter Multinomial's coefficient (under repguide_mask)
-        a64 = self.counts.double()
-        mconst = torch.lgamma(a64.sum(-1) + 1) - torch.lgamma(a64 + 1).sum(-1)  # (R, C, G)
+        mconst, _ = row_constants(self.counts, with_xlogx=False)  # (R, C, G)
         ll_const = self.screen.ll_const + float((mconst * (self.screen.row_mask != 0).unsqueeze(1)).sum())
 
         c = _lib.BeanSviConfig()

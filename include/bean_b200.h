@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BEAN_ABI_VERSION 14
+#define BEAN_ABI_VERSION 15
 
 enum {
   BEAN_OK = 0,
@@ -313,6 +313,20 @@ int bean_svi_survival_run_f32(const BeanScreen* screen, const BeanSviState* stat
 int bean_svi_survival_run_f64(const BeanScreen* screen, const BeanSviState* state, const BeanSurvivalState* survival,
                               const BeanSviConfig* cfg, const BeanSviNoise* noise, const BeanSurvivalNoise* survival_noise,
                               int32_t first_step, int32_t n_steps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bean_row_const_{f32,f64}: the data-only part of each row's count log-pmf, once per screen (the reference recomputes it inside
+ * every step: the lgamma(N + 1) - sum lgamma(x + 1) of pyro's DirichletMultinomial.log_prob, model.py:531-547, and the
+ * Multinomial coefficient of the reporter counts, model.py:464-474).
+ *   row_const[i] = lgamma(N_i + 1) - sum_b lgamma(x[i][b] + 1)  [+ sum_{x > 0} x[i][b] ln(x[i][b] / max(N_i, 1)) with_xlogx]
+ *   row_total[i] = N_i = sum_b x[i][b]   (optional)
+ * x: real [n_rows][n_bins] (device); log_factorial: f64 [table_size] (device), log_factorial[k] = ln k!: integer entries below
+ * table_size are looked up, everything else takes lgamma.  Feeds BeanScreen.row_const and BeanSviConfig.ll_const.
+ * ---------------------------------------------------------------------------------------------- */
+int bean_row_const_f32(const void* x, int64_t n_rows, int32_t n_bins, int32_t with_xlogx, const double* log_factorial, int32_t table_size,
+                       double* row_const, double* row_total, void* stream);
+int bean_row_const_f64(const void* x, int64_t n_rows, int32_t n_bins, int32_t with_xlogx, const double* log_factorial, int32_t table_size,
+                       double* row_const, double* row_total, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * bean_svi_tiling_run_{f32,f64}: n_steps complete SVI steps of the TILING sorting program (MultiMixtureNormal) on the device.
