@@ -27,7 +27,9 @@ def test_row_constants_equal_the_float64_torch_expression(cuda_device, dtype, wi
         ref = ref + torch.xlogy(x64, x64 / n64.clamp(min=1.0).unsqueeze(-1)).sum(-1)
     assert torch.equal(tot, n64)
     err = ((rc - ref).abs() / (ref.abs() + 1.0)).max().item()
-    assert err <= 1e-13, err
+    # with the x ln(x / N) term a row of 36,000 reads cancels from terms of size N ln N ~ 4e5 to O(10): both evaluations carry
+    # ~1e-16 * 4e5 of rounding there (ln x - ln N here, ln(x / N) in torch)
+    assert err <= (1e-10 if with_xlogx else 1e-13), err
     assert rc.shape == x.shape[:-1] and rc.dtype == torch.float64
 
 
