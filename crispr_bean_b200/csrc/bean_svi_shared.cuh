@@ -272,7 +272,8 @@ __device__ __forceinline__ void load_library_sums(const SviParams<real>& p, int 
       const unsigned long long want = (unsigned long long)p.step + 1ull;
       unsigned long long t0 = 0ull;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (*f < want) {
+      volatile unsigned long long* gave_up = &own->timeouts;
+      while (*f < want && *gave_up == 0ull) {  // once one wait has timed out nobody waits again: the run is lost, not hung
         __nanosleep(200);
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
